@@ -1,0 +1,327 @@
+"""Device-resident indexes and batched kernels: thin torch-tensor front-end of the C ABI (include/b200rag.h).
+
+PyTorch is plumbing here (device memory, streams); every computation is a hand-written CUDA kernel in
+libb200rag.so.  There is no CPU path: tensors must live on a CUDA device and the library must be built.
+
+    DenseIndex   row shard of fp16/bf16 vectors  -> exact top-k      (replaces Collection.search on the
+                 semantic / domain collections, reference src/advanced_rag/indexing.py:505-523)
+    SparseIndex  doc-range-blocked postings      -> sparse IP top-k  (replaces Collection.search on sparse_index)
+    rrf_fuse / mmr_select / merge_topk           -> reference retrieval.py:421-491 / :493-516 / shard reduce
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BF16, DENSE_AUTO, DENSE_EXACT, DENSE_TENSOR, F16, check  # noqa: F401
+
+_TORCH_DTYPE = {F16: torch.float16, BF16: torch.bfloat16}
+_DTYPE_CODE = {"f16": F16, "fp16": F16, "float16": F16, torch.float16: F16,
+               "bf16": BF16, "bfloat16": BF16, torch.bfloat16: BF16, F16: F16, BF16: BF16}
+
+
+def dtype_code(dtype) -> int:
+    try:
+        return _DTYPE_CODE[dtype]
+    except KeyError:
+        raise ValueError(f"unsupported vector dtype {dtype!r} (use 'f16' or 'bf16')") from None
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (b200rag has no CPU path)")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+class _Workspace:
+    """Grow-only scratch buffer per device, handed to the C ABI (the library never allocates)."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def get(self, device: torch.device, nbytes: int) -> torch.Tensor:
+        key = (device.type, device.index)
+        buf = self._buf.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            self._buf[key] = buf
+        return buf
+
+
+_WS = _Workspace()
+
+
+def device_info() -> Tuple[int, int, int]:
+    import ctypes
+    sm, maj, mnr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(_lib.load().b200rag_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr)))
+    return sm.value, maj.value, mnr.value
+
+
+def prepare_rows(x_f32: torch.Tensor, dtype, normalize: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 rows -> stored 16-bit rows (canonical L2 normalisation when `normalize`)."""
+    code = dtype_code(dtype)
+    x = x_f32.to(torch.float32).contiguous()
+    _require_cuda(x, "rows")
+    if x.dim() != 2:
+        raise ValueError("rows must be [n, dim]")
+    if out is None:
+        out = torch.empty(x.shape, dtype=_TORCH_DTYPE[code], device=x.device)
+    else:
+        _require_cuda(out, "out")
+        if out.shape != x.shape or out.dtype != _TORCH_DTYPE[code]:
+            raise ValueError("out has the wrong shape or dtype")
+    with torch.cuda.device(x.device):
+        check(_lib.load().b200rag_prepare_rows(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], code,
+                                               1 if normalize else 0, _stream_ptr(x.device)))
+    return out
+
+
+def dense_topk(corpus16: torch.Tensor, queries16: torch.Tensor, k: int, id_offset: int = 0, mode: int = DENSE_AUTO,
+               n_rows: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Exact top-k of stored rows.  Returns (scores f64 [B,k], ids i64 [B,k], flags i32 [B])."""
+    _require_cuda(corpus16, "corpus")
+    _require_cuda(queries16, "queries")
+    code = dtype_code(corpus16.dtype)
+    if queries16.dtype != corpus16.dtype:
+        raise ValueError("queries and corpus must share the 16-bit dtype")
+    n = corpus16.shape[0] if n_rows is None else n_rows
+    dim = corpus16.shape[1]
+    b = queries16.shape[0]
+    if queries16.shape[1] != dim:
+        raise ValueError(f"query dim {queries16.shape[1]} != corpus dim {dim}")
+    dev = corpus16.device
+    scores = torch.empty((b, k), dtype=torch.float64, device=dev)
+    ids = torch.empty((b, k), dtype=torch.int64, device=dev)
+    flags = torch.zeros((b,), dtype=torch.int32, device=dev)
+    L = _lib.load()
+    with torch.cuda.device(dev):
+        nbytes = L.b200rag_dense_topk_workspace_bytes(n, dim, b, k, mode)
+        ws = _WS.get(dev, nbytes)
+        check(L.b200rag_dense_topk(corpus16.data_ptr(), n, dim, code, queries16.data_ptr(), b, k, id_offset,
+                                   scores.data_ptr(), ids.data_ptr(), flags.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   mode, _stream_ptr(dev)))
+    return scores, ids, flags
+
+
+def merge_topk(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[B, M] candidates (f64 score, i64 id, id<0 = empty) -> top-k by (score desc, id asc)."""
+    _require_cuda(cand_scores, "cand_scores")
+    _require_cuda(cand_ids, "cand_ids")
+    if cand_scores.dtype != torch.float64 or cand_ids.dtype != torch.int64 or cand_scores.shape != cand_ids.shape:
+        raise ValueError("merge_topk expects f64 scores and i64 ids of the same [B, M] shape")
+    b, m = cand_ids.shape
+    dev = cand_ids.device
+    scores = torch.empty((b, k), dtype=torch.float64, device=dev)
+    ids = torch.empty((b, k), dtype=torch.int64, device=dev)
+    ws = _WS.get(dev, 256)
+    with torch.cuda.device(dev):
+        check(_lib.load().b200rag_merge_topk(cand_scores.data_ptr(), cand_ids.data_ptr(), b, m, k, scores.data_ptr(),
+                                             ids.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)))
+    return scores, ids
+
+
+@dataclass
+class FusedBatch:
+    ids: torch.Tensor      # i64 [B, L*K]  fused order, -1 padded
+    scores: torch.Tensor   # f64 [B, L*K]
+    mask: torch.Tensor     # i32 [B, L*K]  bit l: list l held the id
+    first: torch.Tensor    # i32 [B, L*K]  list*K + rank0 of the payload-supplying hit
+    n: torch.Tensor        # i32 [B]
+
+
+def rrf_fuse(list_ids: torch.Tensor, list_len: torch.Tensor, weights: torch.Tensor, rrf_k: int = 60) -> FusedBatch:
+    """list_ids i64 [L,B,K], list_len i32 [L,B], weights f64 [B,L] -> FusedBatch (reference retrieval.py:421-491)."""
+    for t, nm in ((list_ids, "list_ids"), (list_len, "list_len"), (weights, "weights")):
+        _require_cuda(t, nm)
+    if list_ids.dtype != torch.int64 or list_len.dtype != torch.int32 or weights.dtype != torch.float64:
+        raise ValueError("rrf_fuse expects i64 ids, i32 lengths, f64 weights")
+    nl, b, kmax = list_ids.shape
+    dev = list_ids.device
+    tot = nl * kmax
+    out = FusedBatch(torch.empty((b, tot), dtype=torch.int64, device=dev), torch.empty((b, tot), dtype=torch.float64, device=dev),
+                     torch.empty((b, tot), dtype=torch.int32, device=dev), torch.empty((b, tot), dtype=torch.int32, device=dev),
+                     torch.empty((b,), dtype=torch.int32, device=dev))
+    ws = _WS.get(dev, 256)
+    with torch.cuda.device(dev):
+        check(_lib.load().b200rag_rrf_fuse(list_ids.data_ptr(), list_len.data_ptr(), nl, b, kmax, weights.data_ptr(), rrf_k,
+                                           out.ids.data_ptr(), out.scores.data_ptr(), out.mask.data_ptr(),
+                                           out.first.data_ptr(), out.n.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)))
+    return out
+
+
+def mmr_select(cand_doc: torch.Tensor, cand_rel: torch.Tensor, cand_n: torch.Tensor, doc_tok_ptr: torch.Tensor,
+               doc_tok_ids: torch.Tensor, vocab_size: int, lam: torch.Tensor, k_sel: torch.Tensor, k_max: int
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Greedy MMR (reference retrieval.py:493-516).  Returns (picks i32 [B,k_max] positions into the candidates, n i32 [B])."""
+    for t, nm in ((cand_doc, "cand_doc"), (cand_rel, "cand_rel"), (cand_n, "cand_n"), (doc_tok_ptr, "doc_tok_ptr"),
+                  (doc_tok_ids, "doc_tok_ids"), (lam, "lambda"), (k_sel, "k_sel")):
+        _require_cuda(t, nm)
+    if (cand_doc.dtype, cand_rel.dtype, cand_n.dtype, doc_tok_ptr.dtype, doc_tok_ids.dtype, lam.dtype, k_sel.dtype) != (
+            torch.int32, torch.float64, torch.int32, torch.int64, torch.int32, torch.float64, torch.int32):
+        raise ValueError("mmr_select: wrong tensor dtypes")
+    b, nmax = cand_doc.shape
+    dev = cand_doc.device
+    picks = torch.empty((b, k_max), dtype=torch.int32, device=dev)
+    n = torch.empty((b,), dtype=torch.int32, device=dev)
+    ws = _WS.get(dev, 256)
+    with torch.cuda.device(dev):
+        check(_lib.load().b200rag_mmr_select(cand_doc.data_ptr(), cand_rel.data_ptr(), cand_n.data_ptr(), b, nmax,
+                                             doc_tok_ptr.data_ptr(), doc_tok_ids.data_ptr(), int(vocab_size), lam.data_ptr(),
+                                             k_sel.data_ptr(), k_max, picks.data_ptr(), n.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), _stream_ptr(dev)))
+    return picks, n
+
+
+class DenseIndex:
+    """A contiguous row shard of 16-bit vectors in HBM with exact inner-product / cosine search.
+
+    metric "COSINE" (the reference's semantic/domain collections, indexing.py:143-180) stores canonically
+    L2-normalised rows and normalises queries the same way; "IP" stores the plain rounded values.  Row i of this
+    shard has id  id_offset + i.
+    """
+
+    def __init__(self, dim: int, dtype="f16", metric: str = "COSINE", device="cuda", id_offset: int = 0,
+                 capacity: int = 0):
+        if dim % 8 != 0:
+            raise ValueError("dim must be a multiple of 8")
+        if metric not in ("COSINE", "IP"):
+            raise ValueError("metric must be COSINE or IP")
+        self.dim, self.metric, self.id_offset = dim, metric, int(id_offset)
+        self.code = dtype_code(dtype)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("DenseIndex lives on a CUDA device (b200rag has no CPU path)")
+        self._rows = torch.empty((max(capacity, 0), dim), dtype=_TORCH_DTYPE[self.code], device=self.device)
+        self.n = 0
+
+    @property
+    def rows(self) -> torch.Tensor:
+        return self._rows[: self.n]
+
+    def _reserve(self, n_total: int) -> None:
+        if n_total > self._rows.shape[0]:
+            cap = max(n_total, int(self._rows.shape[0] * 1.5), 1024)
+            new = torch.empty((cap, self.dim), dtype=self._rows.dtype, device=self.device)
+            new[: self.n] = self._rows[: self.n]
+            self._rows = new
+
+    def add(self, rows_f32: torch.Tensor, chunk: int = 1 << 18) -> None:
+        """Append fp32 rows (host or device); they are normalised / rounded on the GPU."""
+        if rows_f32.dim() != 2 or rows_f32.shape[1] != self.dim:
+            raise ValueError(f"rows must be [n, {self.dim}]")
+        self._reserve(self.n + rows_f32.shape[0])
+        for s in range(0, rows_f32.shape[0], chunk):
+            part = rows_f32[s: s + chunk].to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            prepare_rows(part, self.code, self.metric == "COSINE", out=self._rows[self.n: self.n + part.shape[0]])
+            self.n += part.shape[0]
+
+    def add_prepared(self, rows16: torch.Tensor) -> None:
+        """Append rows that are already in stored form (16-bit, normalised if COSINE)."""
+        if rows16.dtype != self._rows.dtype or rows16.shape[1] != self.dim:
+            raise ValueError("prepared rows have the wrong dtype or dim")
+        self._reserve(self.n + rows16.shape[0])
+        self._rows[self.n: self.n + rows16.shape[0]] = rows16.to(self.device)
+        self.n += rows16.shape[0]
+
+    def prepare_queries(self, queries_f32: torch.Tensor) -> torch.Tensor:
+        q = queries_f32.to(self.device, dtype=torch.float32, non_blocking=True)
+        if q.dim() == 1:
+            q = q[None, :]
+        return prepare_rows(q.contiguous(), self.code, self.metric == "COSINE")
+
+    def search(self, queries_f32: torch.Tensor, k: int, mode: int = DENSE_AUTO):
+        """queries fp32 [B, dim] (host or device) -> (scores f64 [B,k], ids i64 [B,k], flags i32 [B]) on device."""
+        q16 = self.prepare_queries(queries_f32)
+        return dense_topk(self._rows, q16, k, self.id_offset, mode, n_rows=self.n)
+
+    def search_prepared(self, queries16: torch.Tensor, k: int, mode: int = DENSE_AUTO):
+        return dense_topk(self._rows, queries16, k, self.id_offset, mode, n_rows=self.n)
+
+
+class SparseIndex:
+    """Doc-range-blocked postings in HBM (layout: include/b200rag.h, b200rag_sparse_topk).
+
+    Built from a doc-major CSR (rows = documents, columns = term ids, values = fp32 weights) -- the layout the
+    reference assembles for its sparse collection (indexing.py:379-404).  The re-blocking runs on the GPU with torch
+    sort/scan ops (ingest side, not the hot path).
+    """
+
+    def __init__(self, doc_ptr, term_ids, weights, n_terms: int, device="cuda", block_docs: int = 32768,
+                 id_offset: int = 0):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("SparseIndex lives on a CUDA device (b200rag has no CPU path)")
+        if block_docs % 32 or not 0 < block_docs <= 65536:
+            raise ValueError("block_docs must be a multiple of 32 in (0, 65536]")
+        doc_ptr = torch.as_tensor(np.asarray(doc_ptr, dtype=np.int64))
+        self.n_docs = int(doc_ptr.numel() - 1)
+        self.n_terms = int(n_terms)
+        self.block_docs = int(block_docs)
+        self.id_offset = int(id_offset)
+        self.n_blocks = max(1, -(-self.n_docs // block_docs))
+        dev = self.device
+        t = torch.as_tensor(np.asarray(term_ids, dtype=np.int64)).to(dev)
+        w = torch.as_tensor(np.asarray(weights, dtype=np.float32)).to(dev)
+        nnz = t.numel()
+        counts = (doc_ptr[1:] - doc_ptr[:-1]).to(dev)
+        d = torch.repeat_interleave(torch.arange(self.n_docs, device=dev, dtype=torch.int64), counts, output_size=nnz)
+        if nnz and (int(t.min()) < 0 or int(t.max()) >= n_terms):
+            raise ValueError("term id out of range")
+        blk = d // block_docs
+        key = (blk * n_terms + t) * block_docs + (d - blk * block_docs)
+        key, order = torch.sort(key)
+        if nnz > 1 and bool((key[1:] == key[:-1]).any()):
+            raise ValueError("duplicate (document, term) pair in the CSR")
+        local = key % block_docs
+        # u16 bit patterns held in an int16 tensor (values >= 32768 wrap; the kernel reads uint16_t)
+        self.post_doc = (((local + 32768) % 65536) - 32768).to(torch.int16).contiguous()
+        self.post_w = w[order].contiguous()
+        seg = key // block_docs                                      # blk * n_terms + term
+        # blk_term_ptr[b*(V+1) + t] : start of (block b, term t); one extra entry per block
+        cnt = torch.bincount(seg, minlength=self.n_blocks * n_terms) if nnz else torch.zeros(
+            self.n_blocks * n_terms, dtype=torch.int64, device=dev)
+        cnt = cnt.view(self.n_blocks, n_terms)
+        start = torch.cumsum(cnt.view(-1), 0) - cnt.view(-1)
+        ptr = torch.empty((self.n_blocks, n_terms + 1), dtype=torch.int64, device=dev)
+        ptr[:, :n_terms] = start.view(self.n_blocks, n_terms)
+        ptr[:, n_terms] = torch.cumsum(cnt.sum(1), 0)
+        self.blk_term_ptr = ptr.contiguous()
+        self.nnz = int(nnz)
+        # term-major global view kept for statistics (df per term)
+        self.df = torch.bincount(t, minlength=n_terms) if nnz else torch.zeros(n_terms, dtype=torch.int64, device=dev)
+
+    def search(self, q_ptr, q_terms, q_vals, k: int):
+        """CSR queries (q_ptr i64 [B+1], q_terms i32 ascending per query, q_vals f32) ->
+        (scores f32 [B,k], ids i64 [B,k], counts i32 [B]) on device."""
+        dev = self.device
+        q_ptr = torch.as_tensor(q_ptr, dtype=torch.int64).to(dev).contiguous()
+        q_terms = torch.as_tensor(q_terms, dtype=torch.int32).to(dev).contiguous()
+        q_vals = torch.as_tensor(q_vals, dtype=torch.float32).to(dev).contiguous()
+        b = q_ptr.numel() - 1
+        scores = torch.empty((b, k), dtype=torch.float32, device=dev)
+        ids = torch.empty((b, k), dtype=torch.int64, device=dev)
+        counts = torch.zeros((b,), dtype=torch.int32, device=dev)
+        L = _lib.load()
+        with torch.cuda.device(dev):
+            nbytes = L.b200rag_sparse_topk_workspace_bytes(self.n_docs, self.block_docs, b, k)
+            ws = _WS.get(dev, nbytes)
+            check(L.b200rag_sparse_topk(self.blk_term_ptr.data_ptr(), self.post_doc.data_ptr(), self.post_w.data_ptr(),
+                                        self.n_docs, self.n_terms, self.block_docs, q_ptr.data_ptr(), q_terms.data_ptr(),
+                                        q_vals.data_ptr(), b, k, self.id_offset, scores.data_ptr(), ids.data_ptr(),
+                                        counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)))
+        return scores, ids, counts
+
+    def query_bytes(self, q_ptr, q_terms) -> int:
+        """Algorithmic HBM bytes of a query batch: sum over query terms of df(t) * 6 (u16 doc + f32 weight)."""
+        qt = torch.as_tensor(q_terms, dtype=torch.int64).to(self.device)
+        return int(self.df[qt].sum().item()) * 6

@@ -1,0 +1,157 @@
+/*
+ * b200rag.h -- C ABI of the B200-native hybrid-retrieval engine (libb200rag.so).
+ *
+ * This is the drop-in boundary for the retrieval hot path of rnaarla/advanced-rag-milvus.  The reference has
+ * no FFI of its own: its seam is the duck-typed index manager that HybridRetriever calls
+ * (reference src/advanced_rag/retrieval.py:113-131), whose one arithmetic entry point is
+ * MilvusIndexManager.search() -> pymilvus Collection.search() (src/advanced_rag/indexing.py:445-551, call site
+ * :505-523), followed in-process by _fuse_results (retrieval.py:421-491) and _mmr_diversify
+ * (retrieval.py:493-516).  Each function below names the reference call it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference adds.
+ *
+ * Conventions
+ *   - plain C, no exceptions.  Every function returns 0 on success or a negative B200RAG_E_* code;
+ *     b200rag_last_error() returns a thread-local message for the last failure on the calling thread.
+ *   - all array arguments are DEVICE pointers owned by the caller (e.g. torch tensors' data_ptr()), contiguous,
+ *     row major.  Nothing caller-visible is allocated by the library; scratch is a caller-provided workspace whose
+ *     size the matching *_workspace_bytes() function reports.  Workspaces must be 256-byte aligned.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - 16-bit vector data is passed as raw bit patterns (fp16 or bf16, see b200rag_dtype).
+ *   - ranking rule everywhere: score descending, then id ascending.  Unused output slots: id -1, score -inf.
+ *   - there is NO CPU fallback: every function fails with B200RAG_E_CUDA if no sm_100 device is usable.
+ *
+ * Canonical arithmetic (identical, bit for bit, to oracle/exact_scan.c):
+ *   dense   sum_d q[d]*x[d] over the stored 16-bit values, fp64, 8 interleaved lanes, fixed combine tree.
+ *   cosine  = dense score of rows/queries normalised once by b200rag_prepare_rows(normalize=1).
+ *   sparse  fp32 fmaf chain over the query's terms in ascending term id.
+ *   rrf     fp64:  fused[id] += (1.0 / (rrf_k + rank)) * w   in list order; stable sort by score desc.
+ *   mmr     fp64:  lambda*rel - (1-lambda)*max_jaccard, strict '>' so the earliest candidate wins ties.
+ */
+#ifndef B200RAG_H_
+#define B200RAG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RAG_ABI_VERSION 1
+
+typedef enum { B200RAG_F16 = 0, B200RAG_BF16 = 1 } b200rag_dtype;
+
+/* dense scan engine selection (b200rag_dense_topk `mode`) */
+typedef enum {
+    B200RAG_DENSE_AUTO = 0,   /* tensor-core scan + exact re-score, exact fallback for flagged queries */
+    B200RAG_DENSE_EXACT = 1,  /* CUDA-core fp64 canonical scan only (slow; ground truth / fallback)    */
+    B200RAG_DENSE_TENSOR = 2  /* tensor-core scan + exact re-score, flags reported, NO fallback        */
+} b200rag_dense_mode;
+
+enum {
+    B200RAG_OK = 0,
+    B200RAG_E_INVALID = -1,    /* bad argument (null pointer, size, alignment, unsupported k / dim) */
+    B200RAG_E_WORKSPACE = -2,  /* workspace too small or misaligned */
+    B200RAG_E_CUDA = -3,       /* CUDA runtime / driver error, or no sm_100 device */
+    B200RAG_E_UNSUPPORTED = -4
+};
+
+/* Thread-local description of the last error on this thread ("" if none). */
+const char* b200rag_last_error(void);
+int b200rag_abi_version(void);
+/* Fills SM count and compute capability of the current device. */
+int b200rag_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Row preparation (ingest side and query side).  Replaces what Milvus does at insert time for a COSINE index
+ * (reference indexing.py:143-180 creates the collections with metric_type COSINE; vectors are inserted as fp32
+ * at :372,426) and the `query_embedding.tolist()` marshalling at indexing.py:500.
+ *   in_f32 [n_rows, dim] fp32  ->  out16 [n_rows, dim] 16-bit patterns of `dtype`
+ *   normalize=1: canonical L2 normalisation (fp64 sequential sum of squares, one rounding); 0: plain RNE cast.
+ */
+int b200rag_prepare_rows(const float* in_f32, void* out16, int64_t n_rows, int32_t dim, int32_t dtype,
+                         int32_t normalize, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Dense exact top-k  (K1 + K2).  Replaces Collection.search on "semantic_index" / "domain_index"
+ * (reference indexing.py:505-523, reached from retrieval.py:341-365 and :397-419) for a whole batch of queries.
+ *   corpus16  [n_rows, dim]   stored rows of this shard (dim % 8 == 0, 16-byte aligned base)
+ *   queries16 [n_queries, dim]
+ *   out_scores f64 [n_queries, k]  canonical scores;  out_ids i64 [n_queries, k] = local row + id_offset
+ *   out_flags  i32 [n_queries] or NULL: bit0 = the tensor-core candidate set could not be PROVEN complete for
+ *              this query (near-ties beyond the slack); in AUTO mode such queries were re-run on the exact path,
+ *              so results are always exact and the flag is informational.
+ */
+size_t b200rag_dense_topk_workspace_bytes(int64_t n_rows, int32_t dim, int32_t n_queries, int32_t k, int32_t mode);
+int b200rag_dense_topk(const void* corpus16, int64_t n_rows, int32_t dim, int32_t dtype,
+                       const void* queries16, int32_t n_queries, int32_t k, int64_t id_offset,
+                       double* out_scores, int64_t* out_ids, int32_t* out_flags,
+                       void* workspace, size_t workspace_bytes, int32_t mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Sparse inner-product top-k over doc-range-blocked postings (K3).  Replaces Collection.search on
+ * "sparse_index" (reference indexing.py:472,487-498,505-523, reached from retrieval.py:367-395).
+ * Postings layout ("blocked CSR"): documents are cut into blocks of `block_docs` consecutive rows
+ * (block_docs <= 65536); inside block b the postings of term t occupy
+ *   [blk_term_ptr[b*(n_terms+1)+t], blk_term_ptr[b*(n_terms+1)+t+1])  of post_doc / post_w,
+ * post_doc holding the row index RELATIVE to the block start (u16), ascending.
+ * Queries are a CSR over terms: q_ptr i64 [n_queries+1], q_terms i32 ascending per query, q_vals f32.
+ * Only documents sharing at least one term with the query are candidates; out_counts[q] = hits returned.
+ */
+size_t b200rag_sparse_topk_workspace_bytes(int64_t n_docs, int32_t block_docs, int32_t n_queries, int32_t k);
+int b200rag_sparse_topk(const int64_t* blk_term_ptr, const uint16_t* post_doc, const float* post_w,
+                        int64_t n_docs, int32_t n_terms, int32_t block_docs,
+                        const int64_t* q_ptr, const int32_t* q_terms, const float* q_vals,
+                        int32_t n_queries, int32_t k, int64_t id_offset,
+                        float* out_scores, int64_t* out_ids, int32_t* out_counts,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * k-way merge of gathered candidate lists (K4): the reduce after the NCCL all-gather of per-GPU top-k.  Stands
+ * in for the reduce Milvus' proxy performs across its shards (reference indexing.py:91,234-239 num_shards).
+ *   cand_scores f64 [n_queries, n_cand], cand_ids i64 [n_queries, n_cand]  (id < 0 = empty slot)
+ */
+size_t b200rag_merge_topk_workspace_bytes(int32_t n_queries, int32_t n_cand, int32_t k);
+int b200rag_merge_topk(const double* cand_scores, const int64_t* cand_ids, int32_t n_queries, int32_t n_cand,
+                       int32_t k, double* out_scores, int64_t* out_ids,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Weighted Reciprocal Rank Fusion (K5).  Replaces HybridRetriever._fuse_results (reference
+ * retrieval.py:421-491) for a batch.
+ *   list_ids  i64 [n_lists, n_queries, k_max]  ranked ids, list order = semantic, sparse[, domain]
+ *   list_len  i32 [n_lists, n_queries]
+ *   weights   f64 [n_queries, n_lists]         (dense_weight, sparse_weight[, 0.2]) per query
+ *   out_ids   i64 [n_queries, n_lists*k_max]   fused order (score desc, ties in first-seen order)
+ *   out_scores f64 same shape; out_mask i32 same shape (bit i: list i held the id);
+ *   out_first i32 same shape: position (list*k_max + rank0) of the hit that supplies the payload
+ *             (the reference keeps the first list's dict, retrieval.py:441,449-450,460-461);
+ *   out_n     i32 [n_queries] number of fused ids.
+ */
+size_t b200rag_rrf_fuse_workspace_bytes(int32_t n_lists, int32_t n_queries, int32_t k_max);
+int b200rag_rrf_fuse(const int64_t* list_ids, const int32_t* list_len, int32_t n_lists, int32_t n_queries,
+                     int32_t k_max, const double* weights, int32_t rrf_k,
+                     int64_t* out_ids, double* out_scores, int32_t* out_mask, int32_t* out_first, int32_t* out_n,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Greedy MMR selection on token-set Jaccard (K6).  Replaces HybridRetriever._mmr_diversify (reference
+ * retrieval.py:493-516) for a batch.
+ *   cand_doc  i32 [n_queries, n_max]  row of each candidate in the token CSR, in fused order
+ *   cand_rel  f64 [n_queries, n_max]  fused scores;  cand_n i32 [n_queries]
+ *   doc_tok_ptr i64 [n_docs+1], doc_tok_ids i32: per document the SORTED UNIQUE token ids of
+ *             set(content.lower().split()) (retrieval.py:497); ids < vocab_size
+ *   lambda f64 [n_queries], k_sel i32 [n_queries] (per-query profile values, retrieval.py:142-213)
+ *   out_pick i32 [n_queries, k_max]  selected candidate positions in pick order; out_n i32 [n_queries]
+ */
+size_t b200rag_mmr_select_workspace_bytes(int32_t n_queries, int32_t n_max, int32_t vocab_size);
+int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const int32_t* cand_n, int32_t n_queries,
+                       int32_t n_max, const int64_t* doc_tok_ptr, const int32_t* doc_tok_ids, int32_t vocab_size,
+                       const double* lambda, const int32_t* k_sel, int32_t k_max,
+                       int32_t* out_pick, int32_t* out_n,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RAG_H_ */
