@@ -96,10 +96,10 @@ int b200rag_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 int b200rag_prepare_rows(const float* in_f32, void* out16, int64_t n_rows, int32_t dim, int32_t dtype,
                          int32_t normalize, void* stream) {
-    B200_REQUIRE(in_f32 && out16, "prepare_rows: null pointer");
     B200_REQUIRE(n_rows >= 0 && dim > 0 && dim <= 8192, "prepare_rows: bad shape n_rows=%lld dim=%d", (long long)n_rows, dim);
     B200_REQUIRE(dtype == B200RAG_F16 || dtype == B200RAG_BF16, "prepare_rows: bad dtype %d", dtype);
     if (n_rows == 0) return B200RAG_OK;
+    B200_REQUIRE(in_f32 && out16, "prepare_rows: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     size_t smem = (size_t)PREP_ROWS * (dim + 1) * sizeof(float);
     int64_t blocks = (n_rows + PREP_ROWS - 1) / PREP_ROWS;

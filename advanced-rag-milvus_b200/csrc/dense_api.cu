@@ -27,6 +27,8 @@ int b200rag_dense_topk(const void* corpus16, int64_t n_rows, int32_t dim, int32_
                        const void* queries16, int32_t n_queries, int32_t k, int64_t id_offset,
                        double* out_scores, int64_t* out_ids, int32_t* out_flags,
                        void* workspace, size_t workspace_bytes, int32_t mode, void* stream) {
+    B200_REQUIRE(n_queries >= 0, "dense_topk: bad n_queries=%d", n_queries);
+    if (n_queries == 0) return B200RAG_OK;
     B200_REQUIRE(queries16 && out_scores && out_ids && workspace, "dense_topk: null pointer");
     B200_REQUIRE(corpus16 || n_rows == 0, "dense_topk: null corpus");
     B200_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 40), "dense_topk: bad n_rows %lld", (long long)n_rows);

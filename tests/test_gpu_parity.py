@@ -1,0 +1,247 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on identical seeded inputs.
+Integer / id results must be bit exact; fp64 / fp32 scores must be bit exact too (same canonical arithmetic)."""
+import numpy as np
+import pytest
+import torch
+
+from util import METHOD_NAMES, golden_lists, id_map, load_golden, to_bits_view
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from b200rag import engine
+    sm, major, minor = engine.device_info()
+    assert major >= 10, f"expected an sm_100 device, got sm_{major}{minor}"
+    return engine
+
+
+def _codes(o, eng):
+    return [(o.F16, eng.F16, torch.float16), (o.BF16, eng.BF16, torch.bfloat16)]
+
+
+# ------------------------------------------------------------------------------------------------ row preparation
+def test_prepare_rows_bit_exact(eng, oracle_lib):
+    o = oracle_lib
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((1000, 96)).astype(np.float32)
+    x[3] = 0.0                                  # all-zero row stays zero
+    x[4] *= 1e-6
+    x[5] *= 3e4
+    for oc, ec, td in _codes(o, eng):
+        for normalize in (True, False):
+            got = eng.prepare_rows(torch.from_numpy(x).to(DEV), ec, normalize)
+            assert got.dtype == td
+            ref = o.normalize_rows(x, oc) if normalize else o.round_f32(x, oc)
+            assert np.array_equal(to_bits_view(got), ref), (oc, normalize)
+
+
+# ------------------------------------------------------------------------------------------------ dense, exact mode
+@pytest.mark.parametrize("n,d,b,k", [(1, 8, 1, 1), (37, 16, 3, 50), (1000, 64, 5, 10), (4096, 384, 9, 40),
+                                     (20000, 768, 4, 100), (100000, 384, 8, 40)])
+def test_dense_exact_mode_matches_oracle(eng, oracle_lib, n, d, b, k):
+    o = oracle_lib
+    rng = np.random.default_rng(n + d)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((b, d)).astype(np.float32)
+    for oc, ec, td in _codes(o, eng):
+        xb, qb = o.normalize_rows(x, oc), o.normalize_rows(q, oc)
+        ref_s, ref_i = o.dense_topk(xb, qb, k, oc, id_offset=1000)
+        idx = eng.DenseIndex(d, ec, "COSINE", DEV, id_offset=1000)
+        idx.add(torch.from_numpy(x))
+        assert np.array_equal(to_bits_view(idx.rows), xb)
+        s, i, f = idx.search(torch.from_numpy(q), k, mode=eng.DENSE_EXACT)
+        assert np.array_equal(i.cpu().numpy(), ref_i)
+        assert np.array_equal(s.cpu().numpy().view(np.uint64), ref_s.view(np.uint64))   # bit exact fp64
+        assert int(f.sum()) == 0
+
+
+def test_dense_exact_ties_and_ip_metric(eng, oracle_lib):
+    o = oracle_lib
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((7, 64)).astype(np.float32)
+    x = np.concatenate([base] * 300)                       # 300 exact copies of each row -> massive ties
+    q = base[:3] * 2.5
+    xb, qb = o.round_f32(x, o.F16), o.round_f32(q, o.F16)
+    ref_s, ref_i = o.dense_topk(xb, qb, 100, o.F16)
+    idx = eng.DenseIndex(64, "f16", "IP", DEV)
+    idx.add(torch.from_numpy(x))
+    s, i, _ = idx.search(torch.from_numpy(q), 100, mode=eng.DENSE_EXACT)
+    assert np.array_equal(i.cpu().numpy(), ref_i)
+    assert np.array_equal(s.cpu().numpy(), ref_s)
+    assert list(ref_i[0, :5]) == [0, 7, 14, 21, 28]        # ids ascending inside the tie
+
+
+def test_dense_empty_corpus_and_empty_batch(eng):
+    idx = eng.DenseIndex(16, "f16", "COSINE", DEV)
+    s, i, _ = idx.search(torch.zeros(2, 16), 3, mode=eng.DENSE_EXACT)
+    assert (i.cpu() == -1).all() and torch.isneginf(s.cpu()).all()
+    idx.add(torch.randn(10, 16))
+    s, i, _ = idx.search(torch.zeros(0, 16), 3, mode=eng.DENSE_EXACT)
+    assert s.shape == (0, 3)
+
+
+# ------------------------------------------------------------------------------------------------ merge
+def test_merge_topk_matches_oracle(eng, oracle_lib):
+    o = oracle_lib
+    rng = np.random.default_rng(9)
+    for b, m, k in [(1, 5, 6), (17, 800, 100), (4, 3000, 1000), (3, 1, 1)]:
+        sc = np.round(rng.standard_normal((b, m)), 1)                # coarse -> many ties
+        ids = np.stack([rng.permutation(m * 3)[:m] for _ in range(b)]).astype(np.int64) + (1 << 33)
+        ids[rng.random((b, m)) < 0.1] = -1
+        ref_s, ref_i = o.merge_topk(sc, ids, k)
+        s, i = eng.merge_topk(torch.from_numpy(sc).to(DEV), torch.from_numpy(ids).to(DEV), k)
+        assert np.array_equal(i.cpu().numpy(), ref_i)
+        assert np.array_equal(s.cpu().numpy(), ref_s)
+
+
+# ------------------------------------------------------------------------------------------------ sparse
+def _sparse_case(n_docs, vocab, n_q, seed, mean_len=60, n_terms=8, skip_top=20):
+    from b200rag import bm25, synth
+    dp, ti, tf = synth.zipf_corpus(n_docs, vocab, seed, mean_len=mean_len)
+    w = bm25.bm25_weights(dp, ti, tf, vocab)
+    qp, qt, qv = synth.zipf_queries(n_q, vocab, seed + 1, n_terms=n_terms, skip_top=skip_top)
+    return dp, ti, w, qp, qt, qv
+
+
+@pytest.mark.parametrize("n_docs,vocab,n_q,k,block", [(3000, 500, 16, 25, 1024), (100000, 30000, 32, 40, 32768),
+                                                       (70000, 2000, 8, 1000, 32768), (50, 40, 4, 10, 32)])
+def test_sparse_matches_oracle(eng, oracle_lib, n_docs, vocab, n_q, k, block):
+    from b200rag import synth
+    o = oracle_lib
+    dp, ti, w, qp, qt, qv = _sparse_case(n_docs, vocab, n_q, seed=n_docs)
+    qv = (qv * np.linspace(0.5, 2.0, qv.size)).astype(np.float32)       # general sparse IP, not only 1.0
+    tp, pd, pw = synth.doc_major_to_term_major(dp, ti, w, vocab)
+    ref_s, ref_i, ref_c = o.sparse_topk(tp, pd, pw, n_docs, qp, qt, qv, k, id_offset=7)
+    idx = eng.SparseIndex(dp, ti, w, vocab, DEV, block_docs=block, id_offset=7)
+    s, i, c = idx.search(qp, qt, qv, k)
+    assert np.array_equal(c.cpu().numpy(), ref_c)
+    assert np.array_equal(i.cpu().numpy(), ref_i)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), ref_s.view(np.uint32))      # bit exact fp32
+
+
+def test_sparse_edge_cases(eng, oracle_lib):
+    o = oracle_lib
+    # doc-major CSR: doc0 {t0:1}, doc1 {t1:2}, doc2 {t0:1, t2:.5}; term 3 unused
+    dp = np.array([0, 1, 2, 4], np.int64)
+    ti = np.array([0, 1, 0, 2], np.int64)
+    w = np.array([1.0, 2.0, 1.0, 0.5], np.float32)
+    idx = eng.SparseIndex(dp, ti, w, 4, DEV, block_docs=32)
+    qp = np.array([0, 0, 1, 3, 4], np.int64)
+    qt = np.array([3, 0, 2, 1], np.int32)
+    s, i, c = idx.search(qp, qt, np.ones(4, np.float32), 2)
+    assert c.cpu().tolist() == [0, 0, 2, 1]
+    assert i.cpu().tolist()[2] == [2, 0] and s.cpu().tolist()[2] == [1.5, 1.0]
+    assert i.cpu().tolist()[3] == [1, -1]
+    assert i.cpu().tolist()[0] == [-1, -1]
+
+
+# ------------------------------------------------------------------------------------------------ RRF / MMR
+def _run_rrf(eng, lists_per_query, weights_per_query, k_max):
+    nl = max(len(l) for l in lists_per_query)
+    b = len(lists_per_query)
+    ids = np.full((nl, b, k_max), -1, np.int64)
+    lens = np.zeros((nl, b), np.int32)
+    wts = np.zeros((b, nl), np.float64)
+    for q, (lists, w) in enumerate(zip(lists_per_query, weights_per_query)):
+        for l, lst in enumerate(lists):
+            ids[l, q, :len(lst)] = lst
+            lens[l, q] = len(lst)
+            wts[q, l] = w[l]
+    out = eng.rrf_fuse(torch.from_numpy(ids).to(DEV), torch.from_numpy(lens).to(DEV), torch.from_numpy(wts).to(DEV))
+    return out
+
+
+def test_rrf_matches_reference_golden(eng):
+    g = load_golden()
+    for c in g["rrf"]:
+        lists, w = golden_lists(c)
+        if len(lists) < 3:
+            w = w + [0.2]
+            lists = lists + [[]]
+        fwd, back = id_map(lists)
+        ilists = [[fwd[x] for x in l] for l in lists]
+        k_max = max(1, max(len(l) for l in lists))
+        out = _run_rrf(eng, [ilists], [w], k_max)
+        n = int(out.n[0])
+        assert [back[int(x)] for x in out.ids[0, :n].cpu()] == c["out_ids"]
+        assert [float(x).hex() for x in out.scores[0, :n].cpu()] == c["out_scores_hex"]
+        masks = out.mask[0, :n].cpu().tolist()
+        assert [sorted(METHOD_NAMES[i] for i in range(3) if m >> i & 1) for m in masks] == c["out_methods"]
+
+
+def test_rrf_batch_matches_oracle_random(eng):
+    from oracle import fusion
+    rng = np.random.default_rng(11)
+    b, k_max = 64, 500
+    lists_pq, w_pq = [], []
+    for q in range(b):
+        pool = rng.permutation(2000)[: rng.integers(1, 1200)] + (1 << 20)
+        lists = [list(rng.permutation(pool)[: rng.integers(0, min(k_max, pool.size) + 1)]) for _ in range(2)]
+        lists_pq.append(lists)
+        w_pq.append([float(rng.choice([0.7, 0.5, 0.1])), float(rng.choice([0.3, 0.5, 0.9]))])
+    out = _run_rrf(eng, lists_pq, w_pq, k_max)
+    for q in range(b):
+        ids, sc, mask = fusion.rrf_fuse(lists_pq[q], w_pq[q])
+        n = int(out.n[q])
+        assert n == len(ids)
+        assert out.ids[q, :n].cpu().tolist() == [int(x) for x in ids]
+        assert out.scores[q, :n].cpu().numpy().tobytes() == np.asarray(sc, np.float64).tobytes()
+        assert out.mask[q, :n].cpu().tolist() == mask
+        assert (out.ids[q, n:].cpu() == -1).all()
+
+
+def _mmr_inputs(contents_per_query, rel_per_query, lam, k, n_max):
+    from b200rag.bm25 import Bm25Encoder
+    enc = Bm25Encoder()
+    b = len(contents_per_query)
+    all_texts = [t for cs in contents_per_query for t in cs]
+    ptr, tok = enc.token_sets(all_texts)
+    cand_doc = np.zeros((b, n_max), np.int32)
+    rel = np.zeros((b, n_max), np.float64)
+    n = np.zeros(b, np.int32)
+    base = 0
+    for q, cs in enumerate(contents_per_query):
+        cand_doc[q, :len(cs)] = np.arange(base, base + len(cs))
+        rel[q, :len(cs)] = rel_per_query[q]
+        n[q] = len(cs)
+        base += len(cs)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return (t(cand_doc), t(rel), t(n), t(ptr), t(tok if tok.size else np.zeros(1, np.int32)), max(1, len(enc.vocab)),
+            t(np.asarray(lam, np.float64)), t(np.asarray(k, np.int32)))
+
+
+def test_mmr_matches_reference_golden(eng):
+    from oracle import fusion
+    g = load_golden()
+    for c in g["mmr"]:
+        lists, w = golden_lists(c)
+        ids, sc, _ = fusion.rrf_fuse(lists, w)                 # restatement already pinned to the reference
+        contents = [c["contents"][i] for i in ids]
+        n_max = max(1, len(ids))
+        args = _mmr_inputs([contents], [sc], [c["mmr_lambda"]], [c["top_k"]], n_max)
+        picks, n = eng.mmr_select(*args, k_max=max(1, c["top_k"]))
+        got = [ids[int(p)] for p in picks[0, : int(n[0])].cpu()]
+        assert got == c["out_ids"], (c["top_k"], c["mmr_lambda"])
+
+
+def test_mmr_batch_matches_oracle_random(eng):
+    from oracle import fusion
+    rng = np.random.default_rng(13)
+    b, n_max, k_max = 32, 200, 40
+    contents_pq, rel_pq, lam, k = [], [], [], []
+    for q in range(b):
+        n = int(rng.integers(1, n_max + 1))
+        vocab = int(rng.choice([8, 40, 400]))
+        contents_pq.append([" ".join(f"w{rng.integers(vocab)}" for _ in range(rng.integers(0, 30))) for _ in range(n)])
+        rel_pq.append(np.sort(rng.random(n) * 0.02)[::-1].copy())
+        lam.append(float(rng.choice([0.0, 0.5, 0.7, 0.8, 1.0])))
+        k.append(int(rng.integers(1, k_max + 1)))
+    args = _mmr_inputs(contents_pq, rel_pq, lam, k, n_max)
+    picks, n = eng.mmr_select(*args, k_max=k_max)
+    for q in range(b):
+        ref = fusion.mmr_select(list(rel_pq[q]), [fusion.tokens(t) for t in contents_pq[q]], k[q], lam[q])
+        assert picks[q, : int(n[q])].cpu().tolist() == ref, q
