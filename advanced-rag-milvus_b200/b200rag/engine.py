@@ -87,7 +87,8 @@ def prepare_rows(x_f32: torch.Tensor, dtype, normalize: bool, out: Optional[torc
 
 
 def dense_topk(corpus16: torch.Tensor, queries16: torch.Tensor, k: int, id_offset: int = 0, mode: int = DENSE_AUTO,
-               n_rows: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+               n_rows: Optional[int] = None, row_norm_bound: float = 1.001, out_err: Optional[torch.Tensor] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Exact top-k of stored rows.  Returns (scores f64 [B,k], ids i64 [B,k], flags i32 [B])."""
     _require_cuda(corpus16, "corpus")
     _require_cuda(queries16, "queries")
@@ -103,13 +104,18 @@ def dense_topk(corpus16: torch.Tensor, queries16: torch.Tensor, k: int, id_offse
     scores = torch.empty((b, k), dtype=torch.float64, device=dev)
     ids = torch.empty((b, k), dtype=torch.int64, device=dev)
     flags = torch.zeros((b,), dtype=torch.int32, device=dev)
+    if b == 0:
+        return scores, ids, flags
+    if out_err is not None and (out_err.dtype != torch.float32 or out_err.numel() < b or not out_err.is_cuda):
+        raise ValueError("out_err must be a CUDA float32 tensor with one entry per query")
     L = _lib.load()
     with torch.cuda.device(dev):
         nbytes = L.b200rag_dense_topk_workspace_bytes(n, dim, b, k, mode)
         ws = _WS.get(dev, nbytes)
         check(L.b200rag_dense_topk(corpus16.data_ptr(), n, dim, code, queries16.data_ptr(), b, k, id_offset,
-                                   scores.data_ptr(), ids.data_ptr(), flags.data_ptr(), ws.data_ptr(), ws.numel(),
-                                   mode, _stream_ptr(dev)))
+                                   scores.data_ptr(), ids.data_ptr(), flags.data_ptr(), float(row_norm_bound),
+                                   out_err.data_ptr() if out_err is not None else None,
+                                   ws.data_ptr(), ws.numel(), mode, _stream_ptr(dev)))
     return scores, ids, flags
 
 
@@ -203,6 +209,8 @@ class DenseIndex:
             raise ValueError("DenseIndex lives on a CUDA device (b200rag has no CPU path)")
         self._rows = torch.empty((max(capacity, 0), dim), dtype=_TORCH_DTYPE[self.code], device=self.device)
         self.n = 0
+        # upper bound on the stored rows' L2 norm (error margin of the tensor-core path's completeness proof)
+        self.row_norm_bound = 1.001 if metric == "COSINE" else 0.0
 
     @property
     def rows(self) -> torch.Tensor:
@@ -223,6 +231,9 @@ class DenseIndex:
         for s in range(0, rows_f32.shape[0], chunk):
             part = rows_f32[s: s + chunk].to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
             prepare_rows(part, self.code, self.metric == "COSINE", out=self._rows[self.n: self.n + part.shape[0]])
+            if self.metric != "COSINE" and part.shape[0]:
+                nb = float(self._rows[self.n: self.n + part.shape[0]].float().norm(dim=1).max()) * 1.001
+                self.row_norm_bound = max(self.row_norm_bound, nb)
             self.n += part.shape[0]
 
     def add_prepared(self, rows16: torch.Tensor) -> None:
@@ -231,6 +242,9 @@ class DenseIndex:
             raise ValueError("prepared rows have the wrong dtype or dim")
         self._reserve(self.n + rows16.shape[0])
         self._rows[self.n: self.n + rows16.shape[0]] = rows16.to(self.device)
+        if self.metric != "COSINE" and rows16.shape[0]:
+            nb = float(self._rows[self.n: self.n + rows16.shape[0]].float().norm(dim=1).max()) * 1.001
+            self.row_norm_bound = max(self.row_norm_bound, nb)
         self.n += rows16.shape[0]
 
     def prepare_queries(self, queries_f32: torch.Tensor) -> torch.Tensor:
@@ -239,13 +253,14 @@ class DenseIndex:
             q = q[None, :]
         return prepare_rows(q.contiguous(), self.code, self.metric == "COSINE")
 
-    def search(self, queries_f32: torch.Tensor, k: int, mode: int = DENSE_AUTO):
+    def search(self, queries_f32: torch.Tensor, k: int, mode: int = DENSE_AUTO, out_err: Optional[torch.Tensor] = None):
         """queries fp32 [B, dim] (host or device) -> (scores f64 [B,k], ids i64 [B,k], flags i32 [B]) on device."""
         q16 = self.prepare_queries(queries_f32)
-        return dense_topk(self._rows, q16, k, self.id_offset, mode, n_rows=self.n)
+        return self.search_prepared(q16, k, mode, out_err)
 
-    def search_prepared(self, queries16: torch.Tensor, k: int, mode: int = DENSE_AUTO):
-        return dense_topk(self._rows, queries16, k, self.id_offset, mode, n_rows=self.n)
+    def search_prepared(self, queries16: torch.Tensor, k: int, mode: int = DENSE_AUTO, out_err: Optional[torch.Tensor] = None):
+        return dense_topk(self._rows, queries16, k, self.id_offset, mode, n_rows=self.n,
+                          row_norm_bound=max(self.row_norm_bound, 1e-30), out_err=out_err)
 
 
 class SparseIndex:

@@ -9,8 +9,8 @@ int run_exact(const void* corpus16, int64_t n_rows, int dim, int dtype, const vo
               void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t tensor_workspace_bytes(int64_t n_rows, int dim, int n_q, int k);
 int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_q, int k,
-               int64_t id_offset, double* out_scores, int64_t* out_ids, int32_t* out_flags, int with_fallback,
-               void* workspace, size_t workspace_bytes, cudaStream_t st);
+               int64_t id_offset, double* out_scores, int64_t* out_ids, int32_t* out_flags, double row_norm_bound,
+               float* out_err, int with_fallback, void* workspace, size_t workspace_bytes, cudaStream_t st);
 }  // namespace b200rag
 
 using namespace b200rag;
@@ -26,6 +26,7 @@ size_t b200rag_dense_topk_workspace_bytes(int64_t n_rows, int32_t dim, int32_t n
 int b200rag_dense_topk(const void* corpus16, int64_t n_rows, int32_t dim, int32_t dtype,
                        const void* queries16, int32_t n_queries, int32_t k, int64_t id_offset,
                        double* out_scores, int64_t* out_ids, int32_t* out_flags,
+                       double row_norm_bound, float* out_err,
                        void* workspace, size_t workspace_bytes, int32_t mode, void* stream) {
     B200_REQUIRE(n_queries >= 0, "dense_topk: bad n_queries=%d", n_queries);
     if (n_queries == 0) return B200RAG_OK;
@@ -41,12 +42,15 @@ int b200rag_dense_topk(const void* corpus16, int64_t n_rows, int32_t dim, int32_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (mode == B200RAG_DENSE_EXACT) {
         if (out_flags) B200_CUDA_CHECK(cudaMemsetAsync(out_flags, 0, (size_t)n_queries * sizeof(int32_t), st));
+        if (out_err) B200_CUDA_CHECK(cudaMemsetAsync(out_err, 0, (size_t)n_queries * sizeof(float), st));
         return run_exact(corpus16, n_rows, dim, dtype, queries16, n_queries, nullptr, k, id_offset, out_scores, out_ids,
                          workspace, workspace_bytes, st);
     }
     if (mode == B200RAG_DENSE_AUTO || mode == B200RAG_DENSE_TENSOR) {
+        B200_REQUIRE(row_norm_bound > 0.0 && row_norm_bound < 1e30, "dense_topk: row_norm_bound must be positive (got %g)",
+                     row_norm_bound);
         return run_tensor(corpus16, n_rows, dim, dtype, queries16, n_queries, k, id_offset, out_scores, out_ids, out_flags,
-                          mode == B200RAG_DENSE_AUTO, workspace, workspace_bytes, st);
+                          row_norm_bound, out_err, mode == B200RAG_DENSE_AUTO, workspace, workspace_bytes, st);
     }
     set_error("dense_topk: unknown mode %d", mode);
     return B200RAG_E_INVALID;

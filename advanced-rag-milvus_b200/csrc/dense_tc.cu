@@ -1,10 +1,667 @@
-// dense_tc.cu -- placeholder until the tcgen05 scan lands (next commit).
+// dense_tc.cu -- the tensor-core flat scan with the top-k filter fused into the epilogue  (K1 + K2).
+//
+//   scan kernel (persistent, one CTA per SM, warp specialised, sm_100a only)
+//     warp 0      TMA producer: cp.async.bulk.tensor tiles of Q [128 x 64] and X [256 x 64] (SWIZZLE_128B) into a
+//                 4-stage shared-memory ring, mbarrier complete_tx signalling
+//     warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 (queries) x N=256 (corpus rows) x K=16,
+//                 fp32 accumulators double-buffered in TMEM (2 x 256 columns); tcgen05.commit frees smem stages and
+//                 publishes finished accumulators
+//     warps 2..5  epilogue: tcgen05.ld 32 columns at a time; a thread owns ONE query (TMEM lane), compares the 32 scores
+//                 against that query's running threshold (the k'-th best so far) and appends the rare survivors
+//                 (score, row) to a per-query candidate buffer in global memory; a warp-cooperative radix select
+//                 compacts a buffer back to k' entries and raises the threshold when it fills.  The score matrix never
+//                 leaves the SM.
+//     Work item = (query block of 128, chunk of consecutive corpus tiles); concurrently resident CTAs hold different
+//     query blocks of the same chunks so the corpus streams from HBM once and is re-served from L2.
+//
+//   finish kernel (one CTA per query)
+//     merges the per-chunk candidate lists to the k' best by tensor-core score, RE-SCORES them in the canonical fp64
+//     arithmetic (bit-identical to the oracle), sorts by (score desc, id asc) and PROVES completeness:
+//     every row outside the candidate set has tensor-core score <= m (the k'-th best), hence exact score <= m + eps;
+//     if the exact k-th score exceeds m + eps the exact top-k is inside the candidate set.  Otherwise the query is
+//     flagged and (AUTO mode) re-run on the exact CUDA-core path.  eps = 2 * dim * 2^-23 * |q| * row_norm_bound bounds
+//     the fp32 accumulation error of the tensor-core path (checked empirically in tests/test_gpu_dense_tc.py).
+#include <cuda.h>
+#include <cstdio>
+
 #include "common.cuh"
+#include "select.cuh"
+
 namespace b200rag {
-size_t tensor_workspace_bytes(int64_t, int, int, int) { return 256; }
-int run_tensor(const void*, int64_t, int, int, const void*, int, int, int64_t, double*, int64_t*, int32_t*, int, void*, size_t,
-               cudaStream_t) {
-    set_error("dense_topk: tensor-core path not built");
-    return B200RAG_E_UNSUPPORTED;
+
+size_t exact_workspace_bytes(int64_t n_rows, int dim, int n_q, int k);
+int run_exact(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_launch,
+              const int32_t* q_list, int k, int64_t id_offset, double* out_scores, int64_t* out_ids,
+              void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+// ----------------------------------------------------------------------------------------------- tile configuration
+constexpr int TC_BM = 128;             // queries per CTA tile (UMMA M, TMEM lanes)
+constexpr int TC_BN = 256;             // corpus rows per accumulator (UMMA N)
+constexpr int TC_BK = 64;              // K elements per stage = one 128-byte swizzle atom of 16-bit data
+constexpr int TC_STAGES = 4;
+constexpr int TC_Q_BYTES = TC_BM * TC_BK * 2;      // 16 KB
+constexpr int TC_X_BYTES = TC_BN * TC_BK * 2;      // 32 KB
+constexpr int TC_STAGE_BYTES = TC_Q_BYTES + TC_X_BYTES;
+constexpr int TC_THREADS = 192;        // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
+constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_MAX_C = 1280;         // candidate-buffer capacity limit (compaction scratch in smem)
+constexpr int TC_FALLBACK_BATCH = 32;
+
+__host__ __device__ inline int tc_kprime(int k) { int s = k / 4 > 28 ? k / 4 : 28; return (k + s + 31) / 32 * 32; }
+__host__ __device__ inline int tc_bufcap(int kp) { return 2 * kp; }
+
+// ----------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 6000000000ll) {     // ~3 s at 2 GHz
+            printf("b200rag: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor of a K-major, 128-byte-swizzled operand tile whose rows are 128 bytes apart and whose
+// 8-row groups are 1024 bytes apart (what TMA SWIZZLE_128B writes for a 64-element-wide 16-bit box).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);       // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                            // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: D=f32, A=B=dtype (0 f16 / 1 bf16), both K-major, N=256, M=128.
+__host__ __device__ inline uint32_t umma_idesc(int dtype) {
+    return (1u << 4) | ((uint32_t)dtype << 7) | ((uint32_t)dtype << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+           ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------------------------- scan kernel
+struct ScanParams {
+    int64_t n_rows;
+    int n_q;
+    int n_kblocks;       // ceil(dim / 64)
+    int n_tiles;         // ceil(n_rows / 256)
+    int nqb;             // query blocks
+    int n_chunks;
+    int n_items;         // nqb * n_chunks
+    int kprime;
+    int cap;             // candidate buffer capacity per (item, query lane)
+    uint32_t idesc;
+    unsigned long long* cand;   // [n_items][128][cap]  (score bits << 32 | local row)
+    int* cand_cnt;              // [n_items][128]
+};
+
+// Keep the kp greatest-score entries of buf[0..n) (in place), return the kp-th greatest score.  All 32 lanes call.
+__device__ __forceinline__ float warp_compact(unsigned long long* buf, int n, int kp, uint32_t* scratch, int lane) {
+    for (int j = lane; j < n; j += 32) scratch[j] = mono32(__uint_as_float((uint32_t)(buf[j] >> 32)));
+    __syncwarp();
+    uint32_t T = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = T | (1u << bit);
+        int c = 0;
+        for (int j = lane; j < n; j += 32) c += scratch[j] >= cand;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= kp) T = cand;
+    }
+    int gt = 0;
+    for (int j = lane; j < n; j += 32) gt += scratch[j] > T;
+    gt = __reduce_add_sync(0xffffffffu, gt);
+    const int allowed_eq = kp - gt;
+    int out = 0, eq_used = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        const bool valid = j < n;
+        unsigned long long e = 0;
+        uint32_t key = 0;
+        if (valid) { e = buf[j]; key = scratch[j]; }
+        const bool is_eq = valid && key == T;
+        const unsigned m_eq = __ballot_sync(0xffffffffu, is_eq);
+        const bool keep = (valid && key > T) || (is_eq && eq_used + __popc(m_eq & ((1u << lane) - 1)) < allowed_eq);
+        const unsigned m_keep = __ballot_sync(0xffffffffu, keep);
+        if (keep) buf[out + __popc(m_keep & ((1u << lane) - 1))] = e;
+        out += __popc(m_keep);
+        eq_used += __popc(m_eq);
+        __syncwarp();
+    }
+    return unmono32(T);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const ScanParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by SWIZZLE_128B; the dynamic smem base is only guaranteed 16-byte aligned
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;                                             // TC_STAGES * TC_STAGE_BYTES
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* full_bar = bars;                     // [TC_STAGES]
+    uint64_t* empty_bar = bars + TC_STAGES;        // [TC_STAGES]
+    uint64_t* tfull_bar = bars + 2 * TC_STAGES;    // [2]
+    uint64_t* tempty_bar = bars + 2 * TC_STAGES + 2;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+    uint32_t* scratch_all = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 6);   // [TC_EPI_WARPS][cap]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], TC_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer (one elected lane)
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int chunk = item / p.nqb, qb = item % p.nqb;
+                const int t0 = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
+                const int t1 = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
+                for (int tile = t0; tile < t1; ++tile) {
+                    for (int kb = 0; kb < p.n_kblocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sq = stage_base + stage * TC_STAGE_BYTES;
+                        uint8_t* sx = sq + TC_Q_BYTES;
+                        mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+                        tma_load_2d(sq, &map_q, kb * TC_BK, qb * TC_BM, &full_bar[stage]);
+                        tma_load_2d(sx, &map_x, kb * TC_BK, tile * TC_BN, &full_bar[stage]);
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        int stage = 0, astage = 0;
+        uint32_t phase = 0, aphase = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int chunk = item / p.nqb;
+            const int t0 = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
+            const int t1 = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
+            for (int tile = t0; tile < t1; ++tile) {
+                mbar_wait(&tempty_bar[astage], aphase ^ 1);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)astage * TC_BN;
+                for (int kb = 0; kb < p.n_kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t sq = smem_u32(stage_base + stage * TC_STAGE_BYTES);
+                        const uint32_t sx = sq + TC_Q_BYTES;
+#pragma unroll
+                        for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+                            umma_f16_ss(d_tmem, umma_desc_sw128(sq + k4 * 32), umma_desc_sw128(sx + k4 * 32), p.idesc,
+                                        (uint32_t)((kb | k4) != 0));
+                        }
+                        umma_commit(&empty_bar[stage]);          // smem stage reusable once these MMAs retire
+                        if (kb == p.n_kblocks - 1) umma_commit(&tfull_bar[astage]);   // accumulator complete
+                    }
+                    __syncwarp();
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++astage == 2) { astage = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ================================================================= epilogue: fused threshold filter
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int qlane = quarter * 32 + lane;        // query row inside the block == TMEM lane
+        uint32_t* scratch = scratch_all + (size_t)(warp - 2) * p.cap;
+        int astage = 0;
+        uint32_t aphase = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int chunk = item / p.nqb, qb = item % p.nqb;
+            const int t0 = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
+            const int t1 = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
+            const bool active = qb * TC_BM + qlane < p.n_q;
+            unsigned long long* buf = p.cand + ((size_t)item * TC_BM + qlane) * p.cap;
+            float thr = active ? -CUDART_INF_F : CUDART_INF_F;
+            int cnt = 0;
+            for (int tile = t0; tile < t1; ++tile) {
+                mbar_wait(&tfull_bar[astage], aphase);
+                tc_fence_after();
+                const int64_t row0 = (int64_t)tile * TC_BN;
+                const bool partial = row0 + TC_BN > p.n_rows;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)astage * TC_BN;
+#pragma unroll 1
+                for (int c = 0; c < TC_BN / 32; ++c) {
+                    // make room: a lane appends at most 32 entries per column group
+                    unsigned need = __ballot_sync(0xffffffffu, cnt > p.cap - 32);
+                    while (need) {
+                        const int L = __ffs(need) - 1;
+                        need &= need - 1;
+                        unsigned long long* b = reinterpret_cast<unsigned long long*>(
+                            __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), L));
+                        const int n = __shfl_sync(0xffffffffu, cnt, L);
+                        const float t = warp_compact(b, n, p.kprime, scratch, lane);
+                        if (lane == L) { cnt = p.kprime; thr = t; }
+                    }
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    if (partial) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (row0 + c * 32 + i >= p.n_rows) r[i] = 0xff800000u;      // -inf: never passes
+                    }
+                    bool any = false;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) any |= __uint_as_float(r[i]) > thr;
+                    if (any) {
+                        const uint32_t rbase = (uint32_t)(row0 + c * 32);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (__uint_as_float(r[i]) > thr) {
+                                buf[cnt] = ((unsigned long long)r[i] << 32) | (unsigned long long)(rbase + i);
+                                ++cnt;
+                            }
+                        }
+                    }
+                }
+                // accumulator drained: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[astage]);
+                if (++astage == 2) { astage = 0; aphase ^= 1; }
+            }
+            // end of item: leave at most k' entries per query
+            unsigned need = __ballot_sync(0xffffffffu, cnt > p.kprime);
+            while (need) {
+                const int L = __ffs(need) - 1;
+                need &= need - 1;
+                unsigned long long* b = reinterpret_cast<unsigned long long*>(
+                    __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), L));
+                const int n = __shfl_sync(0xffffffffu, cnt, L);
+                (void)warp_compact(b, n, p.kprime, scratch, lane);
+                if (lane == L) cnt = p.kprime;
+            }
+            p.cand_cnt[(size_t)item * TC_BM + qlane] = cnt;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- finish kernel
+constexpr int FN_THREADS = 256;
+
+struct FinishParams {
+    const uint16_t* corpus;
+    const uint16_t* queries;
+    int64_t n_rows;
+    int dim;
+    int n_q;
+    int k;
+    int kprime;
+    int cap;
+    int nqb;
+    int n_chunks;
+    int topk_cap;        // BlockTopK capacity
+    int64_t id_offset;
+    double row_norm_bound;
+    const unsigned long long* cand;
+    const int* cand_cnt;
+    double* out_scores;
+    int64_t* out_ids;
+    int32_t* out_flags;
+    int32_t* flag_list;   // compacted list of flagged queries
+    int32_t* n_flagged;
+    float* err_max;       // optional [n_q]: max |tensor score - exact score| over the re-scored candidates
+};
+
+template <int DTYPE>
+__global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishParams p) {
+    extern __shared__ __align__(16) char smem[];
+    const int tid = threadIdx.x;
+    const int q = blockIdx.x;
+    const int qb = q / TC_BM, ql = q % TC_BM;
+    double* qd = reinterpret_cast<double*>(smem);                   // [dim]
+    double* exact = qd + p.dim;                                     // [kprime]
+    uint32_t* rows = reinterpret_cast<uint32_t*>(exact + p.kprime);  // [kprime]
+    float* approx = reinterpret_cast<float*>(rows + p.kprime);      // [kprime]
+    int* rank_of = reinterpret_cast<int*>(approx + p.kprime);       // [kprime]
+    char* tkmem = reinterpret_cast<char*>(rank_of + p.kprime);
+    tkmem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tkmem) + 15) & ~uintptr_t(15));
+    __shared__ double s_q2;
+    __shared__ float s_err;
+
+    BlockTopK<FN_THREADS, uint32_t> tk;
+    tk.attach(tkmem, p.topk_cap, p.kprime, FN_THREADS, /*start_digit=*/BlockTopK<FN_THREADS, uint32_t>::NLO + 3);
+    tk.init();
+    for (int d = tid; d < p.dim; d += FN_THREADS) qd[d] = bits_to_double<DTYPE>(p.queries[(size_t)q * p.dim + d]);
+    if (tid == 0) s_err = 0.f;
+    __syncthreads();
+
+    // 1. k' best by tensor-core score over all chunks of this query
+    for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
+        const size_t slot = ((size_t)(chunk * p.nqb + qb)) * TC_BM + ql;
+        const int n = p.cand_cnt[slot];
+        const unsigned long long* b = p.cand + slot * p.cap;
+        for (int base = 0; base < n; base += FN_THREADS) {
+            const int i = base + tid;
+            const bool valid = i < n;
+            unsigned long long e = valid ? b[i] : 0ull;
+            tk.offer(valid, (uint64_t)mono32(__uint_as_float((uint32_t)(e >> 32))), ~(uint32_t)e);
+            tk.settle();
+        }
+    }
+    __syncthreads();
+    tk.finalize();
+    const int n = tk.count();
+    const uint64_t* oh = tk.out_hi();
+    const uint32_t* ol = tk.out_lo();
+    // m: every row outside the candidate set has tensor-core score <= m  (-inf if nothing was ever dropped)
+    const float m = (n >= p.kprime) ? unmono32((uint32_t)oh[n - 1]) : -CUDART_INF_F;
+
+    // 2. exact canonical re-score
+    for (int i = tid; i < n; i += FN_THREADS) {
+        const uint32_t row = ~ol[i];
+        rows[i] = row;
+        approx[i] = unmono32((uint32_t)oh[i]);
+        exact[i] = canonical_dot<DTYPE>(qd, reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim), p.dim);
+    }
+    if (tid == 0) {
+        double s = 0.0;
+        for (int d = 0; d < p.dim; ++d) s += qd[d] * qd[d];
+        s_q2 = s;
+    }
+    __syncthreads();
+    // 3. rank by (exact desc, row asc)
+    float my_err = 0.f;
+    for (int i = tid; i < n; i += FN_THREADS) {
+        const double e = exact[i];
+        const uint32_t r = rows[i];
+        int rk = 0;
+        for (int j = 0; j < n; ++j) rk += (exact[j] > e) || (exact[j] == e && rows[j] < r);
+        rank_of[i] = rk;
+        my_err = fmaxf(my_err, fabsf((float)((double)approx[i] - e)));
+    }
+    if (p.err_max) atomicMax(reinterpret_cast<int*>(&s_err), __float_as_int(my_err));   // non-negative floats order as ints
+    __syncthreads();
+    // 4. emit + completeness proof
+    const int kk = min(p.k, n);
+    __shared__ double s_ek;
+    if (tid == 0) s_ek = -CUDART_INF;
+    __syncthreads();
+    for (int i = tid; i < n; i += FN_THREADS) {
+        const int rk = rank_of[i];
+        if (rk < p.k) {
+            p.out_scores[(size_t)q * p.k + rk] = exact[i];
+            p.out_ids[(size_t)q * p.k + rk] = p.id_offset + (int64_t)rows[i];
+        }
+        if (rk == kk - 1) s_ek = exact[i];
+    }
+    for (int i = kk + tid; i < p.k; i += FN_THREADS) {
+        p.out_scores[(size_t)q * p.k + i] = -CUDART_INF;
+        p.out_ids[(size_t)q * p.k + i] = -1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double eps = 2.0 * (double)p.dim * 1.1920928955078125e-07 * sqrt(s_q2) * p.row_norm_bound;
+        // proven complete iff nothing was dropped (m = -inf) or the k-th exact score clears m + eps
+        const bool proven = (m == -CUDART_INF_F) || (n >= p.k && s_ek > (double)m + eps);
+        const int flag = proven ? 0 : 1;
+        if (p.out_flags) p.out_flags[q] = flag;
+        if (flag) p.flag_list[atomicAdd(p.n_flagged, 1)] = q;
+        if (p.err_max) p.err_max[q] = s_err;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int dtype, int box_rows) {
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
+        return B200RAG_E_CUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, dtype == B200RAG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld dim=%d)", (int)r, (long long)rows, dim);
+        return B200RAG_E_CUDA;
+    }
+    return B200RAG_OK;
+}
+
+struct TensorPlan {
+    int sm_count, nqb, n_tiles, n_chunks, n_items, kprime, cap, topk_cap;
+    size_t scan_smem, finish_smem;
+    size_t off_cand, off_cnt, off_flaglist, off_nflag, off_err, off_exact, total;
+};
+
+static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
+
+static int sm_count_cached() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
+    TensorPlan pl;
+    pl.sm_count = sm_count_cached();
+    pl.nqb = (n_q + TC_BM - 1) / TC_BM;
+    pl.n_tiles = (int)((n_rows + TC_BN - 1) / TC_BN);
+    int want = pl.sm_count / gcd_int(pl.nqb, pl.sm_count);        // smallest chunk count with n_items % sm_count == 0
+    pl.n_chunks = want < pl.n_tiles ? want : pl.n_tiles;
+    if (pl.n_chunks < 1) pl.n_chunks = 1;
+    pl.n_items = pl.nqb * pl.n_chunks;
+    pl.kprime = tc_kprime(k);
+    pl.cap = tc_bufcap(pl.kprime);
+    pl.topk_cap = BlockTopK<FN_THREADS, uint32_t>::capacity_for(pl.kprime, FN_THREADS);
+    pl.scan_smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 6) * 8 + (size_t)TC_EPI_WARPS * pl.cap * 4;
+    pl.finish_smem = (size_t)dim * 8 + (size_t)pl.kprime * (8 + 4 + 4 + 4) + 32 +
+                     BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.topk_cap) + 64;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { off = align_up(off, 256); size_t o = off; off += bytes; return o; };
+    pl.off_cand = take((size_t)pl.n_items * TC_BM * pl.cap * 8);
+    pl.off_cnt = take((size_t)pl.n_items * TC_BM * 4);
+    pl.off_flaglist = take((size_t)n_q * 4);
+    pl.off_nflag = take(256);
+    pl.off_err = take((size_t)n_q * 4);
+    pl.off_exact = take(exact_workspace_bytes(n_rows, dim, TC_FALLBACK_BATCH, k));
+    pl.total = align_up(off, 256);
+    return pl;
+}
+
+size_t tensor_workspace_bytes(int64_t n_rows, int dim, int n_q, int k) { return plan_tensor(n_rows, dim, n_q, k).total; }
+
+int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_q, int k,
+               int64_t id_offset, double* out_scores, int64_t* out_ids, int32_t* out_flags, double row_norm_bound,
+               float* out_err, int with_fallback, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    TensorPlan pl = plan_tensor(n_rows, dim, n_q, k);
+    if (pl.cap > TC_MAX_C || n_rows >= ((int64_t)1 << 32) - TC_BN) {
+        set_error("dense_topk(tensor): k=%d (k'=%d) or n_rows=%lld beyond the tensor-core path limits; use B200RAG_DENSE_EXACT",
+                  k, pl.kprime, (long long)n_rows);
+        return B200RAG_E_UNSUPPORTED;
+    }
+    if (workspace_bytes < pl.total) {
+        set_error("dense_topk(tensor): workspace too small (%zu < %zu)", workspace_bytes, pl.total);
+        return B200RAG_E_WORKSPACE;
+    }
+    char* ws = static_cast<char*>(workspace);
+    int32_t* flag_list = reinterpret_cast<int32_t*>(ws + pl.off_flaglist);
+    int32_t* n_flagged = reinterpret_cast<int32_t*>(ws + pl.off_nflag);
+    B200_CUDA_CHECK(cudaMemsetAsync(n_flagged, 0, sizeof(int32_t), st));
+
+    if (n_rows > 0) {
+        CUtensorMap map_q, map_x;
+        int rc = make_map(&map_q, queries16, n_q, dim, dtype, TC_BM);
+        if (rc) return rc;
+        rc = make_map(&map_x, corpus16, n_rows, dim, dtype, TC_BN);
+        if (rc) return rc;
+        ScanParams sp;
+        sp.n_rows = n_rows;
+        sp.n_q = n_q;
+        sp.n_kblocks = (dim + TC_BK - 1) / TC_BK;
+        sp.n_tiles = pl.n_tiles;
+        sp.nqb = pl.nqb;
+        sp.n_chunks = pl.n_chunks;
+        sp.n_items = pl.n_items;
+        sp.kprime = pl.kprime;
+        sp.cap = pl.cap;
+        sp.idesc = umma_idesc(dtype);
+        sp.cand = reinterpret_cast<unsigned long long*>(ws + pl.off_cand);
+        sp.cand_cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
+        B200_CUDA_CHECK(cudaFuncSetAttribute(dense_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.scan_smem));
+        int grid = pl.n_items < pl.sm_count ? pl.n_items : pl.sm_count;
+        dense_scan_kernel<<<grid, TC_THREADS, pl.scan_smem, st>>>(map_q, map_x, sp);
+        B200_CUDA_CHECK(cudaGetLastError());
+    } else {
+        B200_CUDA_CHECK(cudaMemsetAsync(ws + pl.off_cnt, 0, (size_t)pl.n_items * TC_BM * 4, st));
+    }
+
+    FinishParams fp;
+    fp.corpus = static_cast<const uint16_t*>(corpus16);
+    fp.queries = static_cast<const uint16_t*>(queries16);
+    fp.n_rows = n_rows;
+    fp.dim = dim;
+    fp.n_q = n_q;
+    fp.k = k;
+    fp.kprime = pl.kprime;
+    fp.cap = pl.cap;
+    fp.nqb = pl.nqb;
+    fp.n_chunks = n_rows > 0 ? pl.n_chunks : 0;
+    fp.topk_cap = pl.topk_cap;
+    fp.id_offset = id_offset;
+    fp.row_norm_bound = row_norm_bound;
+    fp.cand = reinterpret_cast<const unsigned long long*>(ws + pl.off_cand);
+    fp.cand_cnt = reinterpret_cast<const int*>(ws + pl.off_cnt);
+    fp.out_scores = out_scores;
+    fp.out_ids = out_ids;
+    fp.out_flags = out_flags;
+    fp.flag_list = flag_list;
+    fp.n_flagged = n_flagged;
+    fp.err_max = out_err;
+    if (dtype == B200RAG_F16) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(dense_finish_kernel<B200RAG_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.finish_smem));
+        dense_finish_kernel<B200RAG_F16><<<n_q, FN_THREADS, pl.finish_smem, st>>>(fp);
+    } else {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(dense_finish_kernel<B200RAG_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.finish_smem));
+        dense_finish_kernel<B200RAG_BF16><<<n_q, FN_THREADS, pl.finish_smem, st>>>(fp);
+    }
+    B200_CUDA_CHECK(cudaGetLastError());
+
+    if (with_fallback) {
+        // AUTO: results must be exact for every query, so learn how many queries could not be proven (4-byte read-back)
+        int32_t h_n = 0;
+        B200_CUDA_CHECK(cudaMemcpyAsync(&h_n, n_flagged, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int done = 0; done < h_n; done += TC_FALLBACK_BATCH) {
+            int nb = h_n - done < TC_FALLBACK_BATCH ? h_n - done : TC_FALLBACK_BATCH;
+            int rc = run_exact(corpus16, n_rows, dim, dtype, queries16, nb, flag_list + done, k, id_offset, out_scores, out_ids,
+                               ws + pl.off_exact, pl.total - pl.off_exact, st);
+            if (rc) return rc;
+        }
+    }
+    return B200RAG_OK;
+}
+
 }  // namespace b200rag

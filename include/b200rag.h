@@ -81,11 +81,16 @@ int b200rag_prepare_rows(const float* in_f32, void* out16, int64_t n_rows, int32
  *   out_flags  i32 [n_queries] or NULL: bit0 = the tensor-core candidate set could not be PROVEN complete for
  *              this query (near-ties beyond the slack); in AUTO mode such queries were re-run on the exact path,
  *              so results are always exact and the flag is informational.
+ *   row_norm_bound  upper bound on the L2 norm of any stored row (1.001 for rows prepared with normalize=1); it
+ *              sizes the error margin of the completeness proof of the tensor-core path.  Ignored in EXACT mode.
+ *   out_err    f32 [n_queries] or NULL: max |tensor-core score - canonical score| over the re-scored candidates
+ *              (diagnostic; lets callers verify the error bound the proof relies on).
  */
 size_t b200rag_dense_topk_workspace_bytes(int64_t n_rows, int32_t dim, int32_t n_queries, int32_t k, int32_t mode);
 int b200rag_dense_topk(const void* corpus16, int64_t n_rows, int32_t dim, int32_t dtype,
                        const void* queries16, int32_t n_queries, int32_t k, int64_t id_offset,
                        double* out_scores, int64_t* out_ids, int32_t* out_flags,
+                       double row_norm_bound, float* out_err,
                        void* workspace, size_t workspace_bytes, int32_t mode, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------

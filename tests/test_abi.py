@@ -36,7 +36,7 @@ def test_fails_loudly_without_gpu_or_with_bad_arguments():
     from b200rag import _lib, engine
     lib = _lib.load()
     # argument validation happens before any CUDA call
-    rc = lib.b200rag_dense_topk(None, 10, 7, 0, None, 1, 1, 0, None, None, None, None, 0, 1, None)
+    rc = lib.b200rag_dense_topk(None, 10, 7, 0, None, 1, 1, 0, None, None, None, 1.0, None, None, 0, 1, None)
     assert rc == _lib.E_INVALID and b"null" in lib.b200rag_last_error()
     rc = lib.b200rag_sparse_topk(None, None, None, 1, 1, 33, None, None, None, 1, 1, 0, None, None, None, None, 0, None)
     assert rc == _lib.E_INVALID

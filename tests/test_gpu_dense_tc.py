@@ -1,0 +1,96 @@
+"""GPU parity tests of the tensor-core scan (tcgen05 + TMA + fused top-k filter + exact re-score) against the CPU
+oracle: ids and fp64 scores must be bit exact, the completeness proof must hold, and the error bound the proof
+relies on must hold with margin."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from b200rag import engine
+    assert engine.device_info()[1] >= 10
+    return engine
+
+
+def _case(eng, o, n, d, b, k, dt, seed, metric="COSINE", mode=None):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((b, d)).astype(np.float32)
+    oc = o.F16 if dt == "f16" else o.BF16
+    if metric == "COSINE":
+        xb, qb = o.normalize_rows(x, oc), o.normalize_rows(q, oc)
+    else:
+        xb, qb = o.round_f32(x, oc), o.round_f32(q, oc)
+    ref_s, ref_i = o.dense_topk(xb, qb, k, oc, id_offset=5)
+    idx = eng.DenseIndex(d, dt, metric, DEV, id_offset=5)
+    idx.add(torch.from_numpy(x))
+    err = torch.zeros(b, dtype=torch.float32, device=DEV)
+    s, i, f = idx.search(torch.from_numpy(q), k, mode=eng.DENSE_TENSOR if mode is None else mode, out_err=err)
+    return (s.cpu().numpy(), i.cpu().numpy(), f.cpu().numpy(), err.cpu().numpy(), ref_s, ref_i,
+            o.bits_to_f32(qb, oc).astype(np.float64), idx.row_norm_bound)
+
+
+@pytest.mark.parametrize("n,d,b,k,dt", [
+    (256, 64, 128, 10, "f16"),        # one tile, one k-block
+    (300, 64, 5, 10, "f16"),          # partial second tile, partial query block
+    (100, 64, 3, 100, "f16"),         # fewer rows than k'
+    (1000, 768, 128, 100, "f16"),
+    (5000, 384, 300, 40, "f16"),      # 3 query blocks, last one partial
+    (40000, 200, 64, 1, "f16"),       # dim not a multiple of 64 (TMA zero fill), k = 1
+    (20000, 1024, 64, 100, "bf16"),   # config-4-like dtype/dim
+    (100000, 768, 256, 100, "f16"),
+    (60000, 384, 1024, 10, "f16"),    # 8 query blocks, config-5-like k
+    (30000, 128, 16, 500, "f16"),     # deep candidate list (config-4-like K)
+])
+def test_tensor_path_matches_oracle(eng, oracle_lib, n, d, b, k, dt):
+    s, i, f, err, ref_s, ref_i, qf, rnb = _case(eng, oracle_lib, n, d, b, k, dt, seed=n + d + b)
+    assert np.array_equal(i, ref_i)
+    assert np.array_equal(s.view(np.uint64), ref_s.view(np.uint64))     # canonical fp64 scores, bit exact
+    assert f.sum() == 0                                                  # every query proven complete
+    # the proof's error margin eps = 2*dim*2^-23*|q|*row_norm_bound must dominate the observed tensor-core error
+    eps = 2.0 * d * 2.0 ** -23 * np.sqrt((qf ** 2).sum(1)) * rnb
+    assert np.all(err <= eps / 4), (err.max(), eps.min())
+
+
+def test_tensor_path_ip_metric_unnormalised(eng, oracle_lib):
+    s, i, f, err, ref_s, ref_i, qf, rnb = _case(eng, oracle_lib, 50000, 256, 40, 20, "f16", seed=3, metric="IP")
+    assert np.array_equal(i, ref_i) and np.array_equal(s, ref_s)
+    eps = 2.0 * 256 * 2.0 ** -23 * np.sqrt((qf ** 2).sum(1)) * rnb
+    assert np.all(err <= eps / 4)
+
+
+def test_massive_ties_are_flagged_and_auto_mode_falls_back(eng, oracle_lib):
+    o = oracle_lib
+    rng = np.random.default_rng(21)
+    base = rng.standard_normal((9, 64)).astype(np.float32)
+    x = np.concatenate([base] * 400)                           # 400 exact copies of every row
+    q = base[:4]
+    xb, qb = o.normalize_rows(x, o.F16), o.normalize_rows(q, o.F16)
+    ref_s, ref_i = o.dense_topk(xb, qb, 100, o.F16)
+    idx = eng.DenseIndex(64, "f16", "COSINE", DEV)
+    idx.add(torch.from_numpy(x))
+    s, i, f = idx.search(torch.from_numpy(q), 100, mode=eng.DENSE_TENSOR)
+    assert f.cpu().numpy().all(), "400-way ties cannot be proven complete with k'=128 candidates"
+    s, i, f = idx.search(torch.from_numpy(q), 100, mode=eng.DENSE_AUTO)
+    assert np.array_equal(i.cpu().numpy(), ref_i) and np.array_equal(s.cpu().numpy(), ref_s)
+    assert f.cpu().numpy().all()                                # flags stay informational
+
+
+def test_auto_equals_exact_mode_at_one_million_rows(eng):
+    """Size-independent property at BASELINE config-2 scale (1M x 768, top-100): the tensor path and the CUDA-core
+    exact path (itself oracle-checked at small sizes) return identical ids and scores; lists are sorted."""
+    g = torch.Generator(device=DEV).manual_seed(0)
+    idx = eng.DenseIndex(768, "f16", "COSINE", DEV, capacity=1_000_000)
+    for _ in range(4):
+        idx.add(torch.randn(250_000, 768, generator=g, device=DEV))
+    q = torch.randn(16, 768, generator=g, device=DEV)
+    s1, i1, f1 = idx.search(q, 100, mode=eng.DENSE_AUTO)
+    s2, i2, _ = idx.search(q, 100, mode=eng.DENSE_EXACT)
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+    assert int(f1.sum()) == 0
+    assert bool((s1[:, 1:] <= s1[:, :-1]).all())
+    assert bool(((s1[:, 1:] < s1[:, :-1]) | (i1[:, 1:] > i1[:, :-1])).all())
