@@ -11,11 +11,17 @@ size_t tensor_workspace_bytes(int64_t n_rows, int dim, int n_q, int k);
 int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_q, int k,
                int64_t id_offset, double* out_scores, int64_t* out_ids, int32_t* out_flags, double row_norm_bound,
                float* out_err, int with_fallback, void* workspace, size_t workspace_bytes, cudaStream_t st);
+void profile_next_scan(void* a, void* b);
 }  // namespace b200rag
 
 using namespace b200rag;
 
 extern "C" {
+
+int b200rag_profile_next_scan(void* start_event, void* stop_event) {
+    profile_next_scan(start_event, stop_event);
+    return B200RAG_OK;
+}
 
 size_t b200rag_dense_topk_workspace_bytes(int64_t n_rows, int32_t dim, int32_t n_queries, int32_t k, int32_t mode) {
     if (n_rows < 0 || dim <= 0 || n_queries < 0 || k <= 0) return 0;

@@ -573,6 +573,9 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
 
 size_t tensor_workspace_bytes(int64_t n_rows, int dim, int n_q, int k) { return plan_tensor(n_rows, dim, n_q, k).total; }
 
+static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+void profile_next_scan(void* a, void* b) { g_prof_start = static_cast<cudaEvent_t>(a); g_prof_stop = static_cast<cudaEvent_t>(b); }
+
 int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_q, int k,
                int64_t id_offset, double* out_scores, int64_t* out_ids, int32_t* out_flags, double row_norm_bound,
                float* out_err, int with_fallback, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -612,8 +615,14 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
         sp.cand_cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
         B200_CUDA_CHECK(cudaFuncSetAttribute(dense_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.scan_smem));
         int grid = pl.n_items < pl.sm_count ? pl.n_items : pl.sm_count;
+        const bool prof = g_prof_start && g_prof_stop;
+        if (prof) B200_CUDA_CHECK(cudaEventRecord(g_prof_start, st));
         dense_scan_kernel<<<grid, TC_THREADS, pl.scan_smem, st>>>(map_q, map_x, sp);
         B200_CUDA_CHECK(cudaGetLastError());
+        if (prof) {
+            B200_CUDA_CHECK(cudaEventRecord(g_prof_stop, st));
+            g_prof_start = g_prof_stop = nullptr;
+        }
     } else {
         B200_CUDA_CHECK(cudaMemsetAsync(ws + pl.off_cnt, 0, (size_t)pl.n_items * TC_BM * 4, st));
     }

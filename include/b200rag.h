@@ -93,6 +93,12 @@ int b200rag_dense_topk(const void* corpus16, int64_t n_rows, int32_t dim, int32_
                        double row_norm_bound, float* out_err,
                        void* workspace, size_t workspace_bytes, int32_t mode, void* stream);
 
+/* Profiling hook (not part of the data path): when both handles are non-NULL cudaEvent_t values, the NEXT
+ * tensor-core b200rag_dense_topk call on this thread records `start` immediately before and `stop` immediately
+ * after its scan kernel on the call's stream, then clears the hook.  bench.py uses it to time the dominant kernel
+ * inside the timed region without a profiler. */
+int b200rag_profile_next_scan(void* start_event, void* stop_event);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Sparse inner-product top-k over doc-range-blocked postings (K3).  Replaces Collection.search on
  * "sparse_index" (reference indexing.py:472,487-498,505-523, reached from retrieval.py:367-395).
