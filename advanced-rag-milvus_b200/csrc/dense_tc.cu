@@ -21,10 +21,7 @@
 //     if the exact k-th score exceeds m + eps the exact top-k is inside the candidate set.  Otherwise the query is
 //     flagged and (AUTO mode) re-run on the exact CUDA-core path.  eps = 2 * dim * 2^-23 * |q| * row_norm_bound bounds
 //     the fp32 accumulation error of the tensor-core path (checked empirically in tests/test_gpu_dense_tc.py).
-#include <cuda.h>
-#include <cstdio>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 #include "select.cuh"
 
 namespace b200rag {
@@ -34,166 +31,7 @@ int run_exact(const void* corpus16, int64_t n_rows, int dim, int dtype, const vo
               const int32_t* q_list, int k, int64_t id_offset, double* out_scores, int64_t* out_ids,
               void* workspace, size_t workspace_bytes, cudaStream_t st);
 
-// ----------------------------------------------------------------------------------------------- tile configuration
-constexpr int TC_BM = 128;             // queries per CTA tile (UMMA M, TMEM lanes)
-constexpr int TC_BN = 256;             // corpus rows per accumulator (UMMA N)
-constexpr int TC_BK = 64;              // K elements per stage = one 128-byte swizzle atom of 16-bit data
-constexpr int TC_STAGES = 4;
-constexpr int TC_Q_BYTES = TC_BM * TC_BK * 2;      // 16 KB
-constexpr int TC_X_BYTES = TC_BN * TC_BK * 2;      // 32 KB
-constexpr int TC_STAGE_BYTES = TC_Q_BYTES + TC_X_BYTES;
-constexpr int TC_THREADS = 192;        // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
-constexpr int TC_EPI_WARPS = 4;
-constexpr int TC_TMEM_COLS = 512;
-constexpr int TC_MAX_C = 1280;         // candidate-buffer capacity limit (compaction scratch in smem)
-constexpr int TC_FALLBACK_BATCH = 32;
-
-__host__ __device__ inline int tc_kprime(int k) { int s = k / 4 > 28 ? k / 4 : 28; return (k + s + 31) / 32 * 32; }
-__host__ __device__ inline int tc_bufcap(int kp) { return 2 * kp; }
-
-// ----------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 6000000000ll) {     // ~3 s at 2 GHz
-            printf("b200rag: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "elect.sync _|P1, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P1;\n\t"
-        "}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// UMMA shared-memory descriptor of a K-major, 128-byte-swizzled operand tile whose rows are 128 bytes apart and whose
-// 8-row groups are 1024 bytes apart (what TMA SWIZZLE_128B writes for a 64-element-wide 16-bit box).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);       // start address, 16-byte units
-    d |= (uint64_t)1 << 16;                            // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
-    return d;
-}
-// Instruction descriptor: D=f32, A=B=dtype (0 f16 / 1 bf16), both K-major, N=256, M=128.
-__host__ __device__ inline uint32_t umma_idesc(int dtype) {
-    return (1u << 4) | ((uint32_t)dtype << 7) | ((uint32_t)dtype << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
-           ((uint32_t)(TC_BM >> 4) << 24);
-}
-
 // ----------------------------------------------------------------------------------------------- scan kernel
-struct ScanParams {
-    int64_t n_rows;
-    int n_q;
-    int n_kblocks;       // ceil(dim / 64)
-    int n_tiles;         // ceil(n_rows / 256)
-    int nqb;             // query blocks
-    int n_chunks;
-    int n_items;         // nqb * n_chunks
-    int kprime;
-    int cap;             // candidate buffer capacity per (item, query lane)
-    uint32_t idesc;
-    unsigned long long* cand;   // [n_items][128][cap]  (score bits << 32 | local row)
-    int* cand_cnt;              // [n_items][128]
-};
-
-// Keep the kp greatest-score entries of buf[0..n) (in place), return the kp-th greatest score.  All 32 lanes call.
-__device__ __forceinline__ float warp_compact(unsigned long long* buf, int n, int kp, uint32_t* scratch, int lane) {
-    for (int j = lane; j < n; j += 32) scratch[j] = mono32(__uint_as_float((uint32_t)(buf[j] >> 32)));
-    __syncwarp();
-    uint32_t T = 0;
-    for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t cand = T | (1u << bit);
-        int c = 0;
-        for (int j = lane; j < n; j += 32) c += scratch[j] >= cand;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c >= kp) T = cand;
-    }
-    int gt = 0;
-    for (int j = lane; j < n; j += 32) gt += scratch[j] > T;
-    gt = __reduce_add_sync(0xffffffffu, gt);
-    const int allowed_eq = kp - gt;
-    int out = 0, eq_used = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int j = base + lane;
-        const bool valid = j < n;
-        unsigned long long e = 0;
-        uint32_t key = 0;
-        if (valid) { e = buf[j]; key = scratch[j]; }
-        const bool is_eq = valid && key == T;
-        const unsigned m_eq = __ballot_sync(0xffffffffu, is_eq);
-        const bool keep = (valid && key > T) || (is_eq && eq_used + __popc(m_eq & ((1u << lane) - 1)) < allowed_eq);
-        const unsigned m_keep = __ballot_sync(0xffffffffu, keep);
-        if (keep) buf[out + __popc(m_keep & ((1u << lane) - 1))] = e;
-        out += __popc(m_keep);
-        eq_used += __popc(m_eq);
-        __syncwarp();
-    }
-    return unmono32(T);
-}
-
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const ScanParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -285,7 +123,7 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         // ================================================================= epilogue: fused threshold filter
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int qlane = quarter * 32 + lane;        // query row inside the block == TMEM lane
-        uint32_t* scratch = scratch_all + (size_t)(warp - 2) * p.cap;
+        const uint32_t scratch = smem_u32(scratch_all + (size_t)(warp - 2) * p.cap);
         int astage = 0;
         uint32_t aphase = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -294,9 +132,13 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             const int t1 = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
             const bool active = qb * TC_BM + qlane < p.n_q;
             unsigned long long* buf = p.cand + ((size_t)item * TC_BM + qlane) * p.cap;
-            float thr = active ? -CUDART_INF_F : CUDART_INF_F;
+            unsigned int* my_gthr = p.gthr + qb * TC_BM + qlane;
+            // start from the best threshold any CTA has established for this query so far (valid lower bound of the
+            // global k'-th best score; -inf while nobody has k' candidates yet)
+            float thr = active ? gthr_load(my_gthr) : CUDART_INF_F;
             int cnt = 0;
             for (int tile = t0; tile < t1; ++tile) {
+                if (active && ((tile - t0) & 3) == 3) thr = fmaxf(thr, gthr_load(my_gthr));
                 mbar_wait(&tfull_bar[astage], aphase);
                 tc_fence_after();
                 const int64_t row0 = (int64_t)tile * TC_BN;
@@ -312,8 +154,12 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         unsigned long long* b = reinterpret_cast<unsigned long long*>(
                             __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), L));
                         const int n = __shfl_sync(0xffffffffu, cnt, L);
-                        const float t = warp_compact(b, n, p.kprime, scratch, lane);
-                        if (lane == L) { cnt = p.kprime; thr = t; }
+                        const float t = warp_compact(b, n, p.kprime, p.cap, scratch, lane);
+                        if (lane == L) {
+                            cnt = p.kprime;
+                            thr = fmaxf(thr, t);
+                            atomicMax(my_gthr, mono32(t));
+                        }
                     }
                     uint32_t r[32];
                     tmem_ld32(taddr + c * 32, r);
@@ -350,8 +196,11 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 unsigned long long* b = reinterpret_cast<unsigned long long*>(
                     __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), L));
                 const int n = __shfl_sync(0xffffffffu, cnt, L);
-                (void)warp_compact(b, n, p.kprime, scratch, lane);
-                if (lane == L) cnt = p.kprime;
+                const float t = warp_compact(b, n, p.kprime, p.cap, scratch, lane);
+                if (lane == L) {
+                    cnt = p.kprime;
+                    atomicMax(my_gthr, mono32(t));
+                }
             }
             p.cand_cnt[(size_t)item * TC_BM + qlane] = cnt;
         }
@@ -383,6 +232,7 @@ struct FinishParams {
     double row_norm_bound;
     const unsigned long long* cand;
     const int* cand_cnt;
+    const unsigned int* gthr;
     double* out_scores;
     int64_t* out_ids;
     int32_t* out_flags;
@@ -433,7 +283,10 @@ __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishPa
     const uint64_t* oh = tk.out_hi();
     const uint32_t* ol = tk.out_lo();
     // m: every row outside the candidate set has tensor-core score <= m  (-inf if nothing was ever dropped)
-    const float m = (n >= p.kprime) ? unmono32((uint32_t)oh[n - 1]) : -CUDART_INF_F;
+    // (scan kernels drop a row only when its score is <= a threshold that was pushed to gthr; the merge above drops
+    //  rows <= the k'-th best of what was emitted)
+    const unsigned int gk = p.gthr[q];
+    const float m = fmaxf((n >= p.kprime) ? unmono32((uint32_t)oh[n - 1]) : -CUDART_INF_F, gk ? unmono32(gk) : -CUDART_INF_F);
 
     // 2. exact canonical re-score
     for (int i = tid; i < n; i += FN_THREADS) {
@@ -506,7 +359,8 @@ static PFN_tmapEncodeTiled get_encode() {
     return fn;
 }
 
-static int make_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int dtype, int box_rows) {
+// 2-D tensor map over a row-major [rows, dim] 16-bit matrix; box = 64 elements (one 128-byte swizzle atom) x box_rows.
+int make_tensor_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int dtype, int box_rows) {
     PFN_tmapEncodeTiled enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
@@ -526,10 +380,16 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int dim, i
     return B200RAG_OK;
 }
 
+bool scan2_supported(int dim);
+int scan2_tile_rows(int dim);
+size_t scan2_smem_bytes(int cap);
+int scan2_max_clusters(int dim, int cap, int cs, int sm_count);
+int launch_scan2(const void* corpus16, int dtype, const ScanParams& sp, int cs, int max_ctas, cudaStream_t st, int* grid_out);
+
 struct TensorPlan {
-    int sm_count, nqb, n_tiles, n_chunks, n_items, kprime, cap, topk_cap;
+    int sm_count, version, cs, tile_rows, nqb, n_tiles, n_chunks, n_items, kprime, cap, topk_cap, max_ctas;
     size_t scan_smem, finish_smem;
-    size_t off_cand, off_cnt, off_flaglist, off_nflag, off_err, off_exact, total;
+    size_t off_cand, off_cnt, off_gthr, off_flaglist, off_nflag, off_exact, total;
 };
 
 static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
@@ -544,28 +404,55 @@ static int sm_count_cached() {
     return n;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     TensorPlan pl;
     pl.sm_count = sm_count_cached();
     pl.nqb = (n_q + TC_BM - 1) / TC_BM;
-    pl.n_tiles = (int)((n_rows + TC_BN - 1) / TC_BN);
-    int want = pl.sm_count / gcd_int(pl.nqb, pl.sm_count);        // smallest chunk count with n_items % sm_count == 0
-    pl.n_chunks = want < pl.n_tiles ? want : pl.n_tiles;
-    if (pl.n_chunks < 1) pl.n_chunks = 1;
-    pl.n_items = pl.nqb * pl.n_chunks;
     pl.kprime = tc_kprime(k);
     pl.cap = tc_bufcap(pl.kprime);
+    // kernel generation: 2 (Q resident in TMEM + cluster multicast) whenever the query block fits TMEM
+    pl.version = scan2_supported(dim) ? 2 : 1;
+    int forced = env_int("B200RAG_SCAN_VERSION", 0);        // A/B testing hook
+    if (forced == 1 || (forced == 2 && scan2_supported(dim))) pl.version = forced;
+    int units;                                              // co-resident scheduling units (CTAs or clusters)
+    int qgroups;
+    if (pl.version == 2) {
+        pl.tile_rows = scan2_tile_rows(dim);
+        pl.cs = pl.nqb % 4 == 0 ? 4 : (pl.nqb % 2 == 0 ? 2 : 1);
+        int fcs = env_int("B200RAG_CLUSTER", 0);
+        if ((fcs == 1 || fcs == 2 || fcs == 4 || fcs == 8) && pl.nqb % fcs == 0) pl.cs = fcs;
+        units = scan2_max_clusters(dim, pl.cap, pl.cs, pl.sm_count);
+        qgroups = pl.nqb / pl.cs;
+        pl.max_ctas = units * pl.cs;
+        pl.scan_smem = scan2_smem_bytes(pl.cap);
+    } else {
+        pl.tile_rows = TC_BN;
+        pl.cs = 1;
+        units = pl.sm_count;
+        qgroups = pl.nqb;
+        pl.max_ctas = units;
+        pl.scan_smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 6) * 8 + (size_t)TC_EPI_WARPS * pl.cap * 4;
+    }
+    pl.n_tiles = (int)((n_rows + pl.tile_rows - 1) / pl.tile_rows);
+    int want = units / gcd_int(qgroups, units);             // smallest chunk count with n_items % units == 0
+    pl.n_chunks = want < pl.n_tiles ? want : pl.n_tiles;
+    if (pl.n_chunks < 1) pl.n_chunks = 1;
+    pl.n_items = qgroups * pl.n_chunks;
     pl.topk_cap = BlockTopK<FN_THREADS, uint32_t>::capacity_for(pl.kprime, FN_THREADS);
-    pl.scan_smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 6) * 8 + (size_t)TC_EPI_WARPS * pl.cap * 4;
     pl.finish_smem = (size_t)dim * 8 + (size_t)pl.kprime * (8 + 4 + 4 + 4) + 32 +
                      BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.topk_cap) + 64;
     size_t off = 0;
     auto take = [&](size_t bytes) { off = align_up(off, 256); size_t o = off; off += bytes; return o; };
-    pl.off_cand = take((size_t)pl.n_items * TC_BM * pl.cap * 8);
-    pl.off_cnt = take((size_t)pl.n_items * TC_BM * 4);
+    pl.off_cand = take((size_t)pl.n_chunks * pl.nqb * TC_BM * pl.cap * 8);
+    pl.off_cnt = take((size_t)pl.n_chunks * pl.nqb * TC_BM * 4);
+    pl.off_gthr = take((size_t)pl.nqb * TC_BM * 4);
     pl.off_flaglist = take((size_t)n_q * 4);
     pl.off_nflag = take(256);
-    pl.off_err = take((size_t)n_q * 4);
     pl.off_exact = take(exact_workspace_bytes(n_rows, dim, TC_FALLBACK_BATCH, k));
     pl.total = align_up(off, 256);
     return pl;
@@ -593,16 +480,13 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
     int32_t* flag_list = reinterpret_cast<int32_t*>(ws + pl.off_flaglist);
     int32_t* n_flagged = reinterpret_cast<int32_t*>(ws + pl.off_nflag);
     B200_CUDA_CHECK(cudaMemsetAsync(n_flagged, 0, sizeof(int32_t), st));
+    B200_CUDA_CHECK(cudaMemsetAsync(ws + pl.off_gthr, 0, (size_t)pl.nqb * TC_BM * 4, st));
 
     if (n_rows > 0) {
-        CUtensorMap map_q, map_x;
-        int rc = make_map(&map_q, queries16, n_q, dim, dtype, TC_BM);
-        if (rc) return rc;
-        rc = make_map(&map_x, corpus16, n_rows, dim, dtype, TC_BN);
-        if (rc) return rc;
         ScanParams sp;
         sp.n_rows = n_rows;
         sp.n_q = n_q;
+        sp.dim = dim;
         sp.n_kblocks = (dim + TC_BK - 1) / TC_BK;
         sp.n_tiles = pl.n_tiles;
         sp.nqb = pl.nqb;
@@ -610,21 +494,33 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
         sp.n_items = pl.n_items;
         sp.kprime = pl.kprime;
         sp.cap = pl.cap;
-        sp.idesc = umma_idesc(dtype);
+        sp.idesc = umma_idesc(dtype, pl.tile_rows);
         sp.cand = reinterpret_cast<unsigned long long*>(ws + pl.off_cand);
         sp.cand_cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
-        B200_CUDA_CHECK(cudaFuncSetAttribute(dense_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.scan_smem));
-        int grid = pl.n_items < pl.sm_count ? pl.n_items : pl.sm_count;
+        sp.gthr = reinterpret_cast<unsigned int*>(ws + pl.off_gthr);
+        sp.queries = static_cast<const uint16_t*>(queries16);
         const bool prof = g_prof_start && g_prof_stop;
         if (prof) B200_CUDA_CHECK(cudaEventRecord(g_prof_start, st));
-        dense_scan_kernel<<<grid, TC_THREADS, pl.scan_smem, st>>>(map_q, map_x, sp);
+        if (pl.version == 2) {
+            int rc = launch_scan2(corpus16, dtype, sp, pl.cs, pl.max_ctas, st, nullptr);
+            if (rc) return rc;
+        } else {
+            CUtensorMap map_q, map_x;
+            int rc = make_tensor_map(&map_q, queries16, n_q, dim, dtype, TC_BM);
+            if (rc) return rc;
+            rc = make_tensor_map(&map_x, corpus16, n_rows, dim, dtype, TC_BN);
+            if (rc) return rc;
+            B200_CUDA_CHECK(cudaFuncSetAttribute(dense_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.scan_smem));
+            int grid = pl.n_items < pl.sm_count ? pl.n_items : pl.sm_count;
+            dense_scan_kernel<<<grid, TC_THREADS, pl.scan_smem, st>>>(map_q, map_x, sp);
+        }
         B200_CUDA_CHECK(cudaGetLastError());
         if (prof) {
             B200_CUDA_CHECK(cudaEventRecord(g_prof_stop, st));
             g_prof_start = g_prof_stop = nullptr;
         }
     } else {
-        B200_CUDA_CHECK(cudaMemsetAsync(ws + pl.off_cnt, 0, (size_t)pl.n_items * TC_BM * 4, st));
+        B200_CUDA_CHECK(cudaMemsetAsync(ws + pl.off_cnt, 0, (size_t)pl.n_chunks * pl.nqb * TC_BM * 4, st));
     }
 
     FinishParams fp;
@@ -643,6 +539,7 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
     fp.row_norm_bound = row_norm_bound;
     fp.cand = reinterpret_cast<const unsigned long long*>(ws + pl.off_cand);
     fp.cand_cnt = reinterpret_cast<const int*>(ws + pl.off_cnt);
+    fp.gthr = reinterpret_cast<const unsigned int*>(ws + pl.off_gthr);
     fp.out_scores = out_scores;
     fp.out_ids = out_ids;
     fp.out_flags = out_flags;

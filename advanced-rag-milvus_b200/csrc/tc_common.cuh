@@ -1,0 +1,291 @@
+// tc_common.cuh -- constants, PTX wrappers and the warp-level candidate compaction shared by the tensor-core scan kernels.
+#pragma once
+#include <cuda.h>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace b200rag {
+
+// ----------------------------------------------------------------------------------------------- tile configuration
+constexpr int TC_BM = 128;             // queries per CTA tile (UMMA M, TMEM lanes)
+constexpr int TC_BN = 256;             // corpus rows per accumulator (UMMA N)
+constexpr int TC_BK = 64;              // K elements per stage = one 128-byte swizzle atom of 16-bit data
+constexpr int TC_STAGES = 4;
+constexpr int TC_Q_BYTES = TC_BM * TC_BK * 2;      // 16 KB
+constexpr int TC_X_BYTES = TC_BN * TC_BK * 2;      // 32 KB
+constexpr int TC_STAGE_BYTES = TC_Q_BYTES + TC_X_BYTES;
+constexpr int TC_THREADS = 192;        // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
+constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_MAX_C = 1280;         // candidate-buffer capacity limit (compaction scratch in smem)
+constexpr int TC_FALLBACK_BATCH = 32;
+
+__host__ __device__ inline int tc_kprime(int k) { int s = k / 4 > 28 ? k / 4 : 28; return (k + s + 31) / 32 * 32; }
+__host__ __device__ inline int tc_bufcap(int kp) { return 2 * kp; }
+
+// ----------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 6000000000ll) {     // ~3 s at 2 GHz
+            printf("b200rag: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor of a K-major, 128-byte-swizzled operand tile whose rows are 128 bytes apart and whose
+// 8-row groups are 1024 bytes apart (what TMA SWIZZLE_128B writes for a 64-element-wide 16-bit box).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);       // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                            // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: D=f32, A=B=dtype (0 f16 / 1 bf16), both K-major, N=n, M=128.
+__host__ __device__ inline uint32_t umma_idesc(int dtype, int n) {
+    return (1u << 4) | ((uint32_t)dtype << 7) | ((uint32_t)dtype << 10) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+
+// ----------------------------------------------------------------------------------------------- cluster helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// A operand from TMEM (K-major, 16-bit values packed two per 32-bit column), B from shared memory.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// ----------------------------------------------------------------------------------------------- candidate compaction
+// Candidate entry: (fp32 score bits << 32) | local row.  A query's buffer holds up to `cap` entries in global memory; when
+// it is nearly full the warp keeps the kp greatest scores and the kp-th greatest becomes the query's new threshold
+// (entries equal to the threshold are kept only as far as needed to reach kp).
+
+// Register-resident version: cap = 32*EPL entries, EPL per lane.  ~1.5k cycles instead of ~20k for the shared-memory one.
+template <int EPL>
+__device__ __forceinline__ float warp_compact_reg(unsigned long long* buf, int n, int kp, int lane) {
+    unsigned long long e[EPL];
+    uint32_t key[EPL];
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+        const int j = t * 32 + lane;
+        e[t] = j < n ? buf[j] : 0ull;
+        key[t] = j < n ? mono32(__uint_as_float((uint32_t)(e[t] >> 32))) : 0u;      // 0 sorts below every real key
+    }
+    uint32_t T = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = T | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int t = 0; t < EPL; ++t) c += key[t] >= cand;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= kp) T = cand;
+    }
+    int gt = 0;
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) gt += key[t] > T;
+    gt = __reduce_add_sync(0xffffffffu, gt);
+    const int allowed_eq = kp - gt;
+    int out = 0, eq_used = 0;
+    const unsigned below = (1u << lane) - 1;
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+        const bool is_eq = key[t] == T && T != 0;
+        const unsigned m_eq = __ballot_sync(0xffffffffu, is_eq);
+        const bool keep = key[t] > T || (is_eq && eq_used + __popc(m_eq & below) < allowed_eq);
+        const unsigned m_keep = __ballot_sync(0xffffffffu, keep);
+        if (keep) buf[out + __popc(m_keep & below)] = e[t];
+        out += __popc(m_keep);
+        eq_used += __popc(m_eq);
+    }
+    __syncwarp();
+    return unmono32(T);
+}
+
+// Generic version for large buffers: keys staged in a per-warp shared-memory scratch (32-bit shared address).
+__device__ __forceinline__ float warp_compact_smem(unsigned long long* buf, int n, int kp, uint32_t scratch_addr, int lane) {
+    for (int j = lane; j < n; j += 32) sts_u32(scratch_addr + 4 * j, mono32(__uint_as_float((uint32_t)(buf[j] >> 32))));
+    __syncwarp();
+    uint32_t T = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = T | (1u << bit);
+        int c = 0;
+        for (int j = lane; j < n; j += 32) c += lds_u32(scratch_addr + 4 * j) >= cand;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= kp) T = cand;
+    }
+    int gt = 0;
+    for (int j = lane; j < n; j += 32) gt += lds_u32(scratch_addr + 4 * j) > T;
+    gt = __reduce_add_sync(0xffffffffu, gt);
+    const int allowed_eq = kp - gt;
+    int out = 0, eq_used = 0;
+    const unsigned below = (1u << lane) - 1;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        const bool valid = j < n;
+        unsigned long long e = 0;
+        uint32_t key = 0;
+        if (valid) { e = buf[j]; key = lds_u32(scratch_addr + 4 * j); }
+        const bool is_eq = valid && key == T;
+        const unsigned m_eq = __ballot_sync(0xffffffffu, is_eq);
+        const bool keep = (valid && key > T) || (is_eq && eq_used + __popc(m_eq & below) < allowed_eq);
+        const unsigned m_keep = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) buf[out + __popc(m_keep & below)] = e;
+        out += __popc(m_keep);
+        eq_used += __popc(m_eq);
+        __syncwarp();
+    }
+    return unmono32(T);
+}
+
+__device__ __forceinline__ float warp_compact(unsigned long long* buf, int n, int kp, int cap, uint32_t scratch_addr, int lane) {
+    switch (cap) {
+        case 64: return warp_compact_reg<2>(buf, n, kp, lane);
+        case 128: return warp_compact_reg<4>(buf, n, kp, lane);
+        case 192: return warp_compact_reg<6>(buf, n, kp, lane);
+        case 256: return warp_compact_reg<8>(buf, n, kp, lane);
+        case 320: return warp_compact_reg<10>(buf, n, kp, lane);
+        case 384: return warp_compact_reg<12>(buf, n, kp, lane);
+        case 512: return warp_compact_reg<16>(buf, n, kp, lane);
+        default: return warp_compact_smem(buf, n, kp, scratch_addr, lane);
+    }
+}
+
+// Shared per-query threshold: key 0 means "nobody has k' candidates yet" (-inf).
+__device__ __forceinline__ float gthr_load(const unsigned int* p) {
+    unsigned int k;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(k) : "l"(p) : "memory");
+    return k ? unmono32(k) : -CUDART_INF_F;
+}
+
+// Scan-kernel parameters shared by both kernels.
+struct ScanParams {
+    int64_t n_rows;
+    int n_q;
+    int dim;
+    int n_kblocks;       // ceil(dim / 64)
+    int n_tiles;         // ceil(n_rows / tile rows)
+    int nqb;             // query blocks (padded to a multiple of the cluster size in v2)
+    int n_chunks;
+    int n_items;
+    int kprime;
+    int cap;             // candidate buffer capacity per (chunk, query)
+    uint32_t idesc;
+    unsigned long long* cand;   // [n_chunks][nqb][128][cap]  (score bits << 32 | local row)
+    int* cand_cnt;              // [n_chunks][nqb][128]
+    unsigned int* gthr;         // [nqb*128] shared per-query threshold keys (mono32), monotone via atomicMax
+    const uint16_t* queries;    // v2 loads Q rows itself
+};
+
+}  // namespace b200rag

@@ -37,11 +37,13 @@ def case(n, d, b, k, dt="f16", seed=0, mode=engine.DENSE_TENSOR):
 
 
 if __name__ == "__main__":
-    print(torch.cuda.get_device_name(0), engine.device_info(), flush=True)
+    print(torch.cuda.get_device_name(0), engine.device_info(), "SCAN_VERSION", os.environ.get("B200RAG_SCAN_VERSION"),
+          "CLUSTER", os.environ.get("B200RAG_CLUSTER"), flush=True)
     ok = True
     for args in [(256, 64, 128, 10), (256, 128, 128, 10), (300, 64, 5, 10), (1000, 768, 128, 100), (5000, 384, 300, 40),
-                 (100000, 768, 256, 100)]:
+                 (100000, 768, 256, 100), (60000, 384, 1024, 10), (50000, 768, 512, 100)]:
         ok &= case(*args)
     ok &= case(20000, 1024, 64, 100, dt="bf16")
+    ok &= case(30000, 512, 256, 40, dt="bf16")
     print("ALL OK" if ok else "FAILURES")
     sys.exit(0 if ok else 1)
