@@ -70,37 +70,51 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            long long st_wait = 0;
+            ST_T0(st_begin);
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const int chunk = item / p.nqb, qb = item % p.nqb;
                 const int t0 = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
                 const int t1 = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
                 for (int tile = t0; tile < t1; ++tile) {
                     for (int kb = 0; kb < p.n_kblocks; ++kb) {
+                        ST_T0(tw);
                         mbar_wait(&empty_bar[stage], phase ^ 1);
+                        ST_ADD(st_wait, tw);
                         uint8_t* sq = stage_base + stage * TC_STAGE_BYTES;
                         uint8_t* sx = sq + TC_Q_BYTES;
                         mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
                         tma_load_2d(sq, &map_q, kb * TC_BK, qb * TC_BM, &full_bar[stage]);
-                        tma_load_2d(sx, &map_x, kb * TC_BK, tile * TC_BN, &full_bar[stage]);
+                        tma_load_2d(sx, &map_x, kb * TC_BK, tile * p.tile_stride * TC_BN, &full_bar[stage]);
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
+            }
+            if (p.stats) {
+                p.stats[blockIdx.x * ST_N + ST_PROD_TOTAL] = clock64() - st_begin;
+                p.stats[blockIdx.x * ST_N + ST_PROD_WAIT_EMPTY] = st_wait;
             }
         }
     } else if (warp == 1) {
         // ================================================================= MMA issuer
         int stage = 0, astage = 0;
         uint32_t phase = 0, aphase = 0;
+        long long st_wfull = 0, st_wtempty = 0, st_wq = 0;
+        ST_T0(st_begin);
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const int chunk = item / p.nqb;
             const int t0 = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
             const int t1 = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
             for (int tile = t0; tile < t1; ++tile) {
+                ST_T0(te);
                 mbar_wait(&tempty_bar[astage], aphase ^ 1);      // epilogue has drained this accumulator
+                ST_ADD(st_wtempty, te);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)astage * TC_BN;
                 for (int kb = 0; kb < p.n_kblocks; ++kb) {
+                    ST_T0(tf);
                     mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
+                    ST_ADD(st_wfull, tf);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t sq = smem_u32(stage_base + stage * TC_STAGE_BYTES);
@@ -119,6 +133,12 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 if (++astage == 2) { astage = 0; aphase ^= 1; }
             }
         }
+        if (p.stats && lane == 0) {
+            p.stats[blockIdx.x * ST_N + ST_MMA_TOTAL] = clock64() - st_begin;
+            p.stats[blockIdx.x * ST_N + ST_MMA_WAIT_FULL] = st_wfull;
+            p.stats[blockIdx.x * ST_N + ST_MMA_WAIT_TEMPTY] = st_wtempty;
+            p.stats[blockIdx.x * ST_N + ST_MMA_WAIT_Q] = st_wq;
+        }
     } else {
         // ================================================================= epilogue: fused threshold filter
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
@@ -126,6 +146,8 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const uint32_t scratch = smem_u32(scratch_all + (size_t)(warp - 2) * p.cap);
         int astage = 0;
         uint32_t aphase = 0;
+        long long st_wtfull = 0, st_compact = 0, st_qload = 0, st_ncompact = 0, st_nslow = 0;
+        ST_T0(st_begin);
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const int chunk = item / p.nqb, qb = item % p.nqb;
             const int t0 = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
@@ -139,15 +161,19 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             int cnt = 0;
             for (int tile = t0; tile < t1; ++tile) {
                 if (active && ((tile - t0) & 3) == 3) thr = fmaxf(thr, gthr_load(my_gthr));
+                ST_T0(tt);
                 mbar_wait(&tfull_bar[astage], aphase);
+                ST_ADD(st_wtfull, tt);
                 tc_fence_after();
-                const int64_t row0 = (int64_t)tile * TC_BN;
+                const int64_t row0 = (int64_t)tile * p.tile_stride * TC_BN;
                 const bool partial = row0 + TC_BN > p.n_rows;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)astage * TC_BN;
 #pragma unroll 1
                 for (int c = 0; c < TC_BN / 32; ++c) {
                     // make room: a lane appends at most 32 entries per column group
                     unsigned need = __ballot_sync(0xffffffffu, cnt > p.cap - 32);
+                    ST_T0(tc0);
+                    st_ncompact += __popc(need);
                     while (need) {
                         const int L = __ffs(need) - 1;
                         need &= need - 1;
@@ -161,6 +187,7 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                             atomicMax(my_gthr, mono32(t));
                         }
                     }
+                    ST_ADD(st_compact, tc0);
                     uint32_t r[32];
                     tmem_ld32(taddr + c * 32, r);
                     if (partial) {
@@ -172,6 +199,7 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 32; ++i) any |= __uint_as_float(r[i]) > thr;
                     if (any) {
+                        ++st_nslow;
                         const uint32_t rbase = (uint32_t)(row0 + c * 32);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
@@ -203,6 +231,14 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 }
             }
             p.cand_cnt[(size_t)item * TC_BM + qlane] = cnt;
+        }
+        if (p.stats && warp == 2 && lane == 0) {
+            p.stats[blockIdx.x * ST_N + ST_EPI_TOTAL] = clock64() - st_begin;
+            p.stats[blockIdx.x * ST_N + ST_EPI_WAIT_TFULL] = st_wtfull;
+            p.stats[blockIdx.x * ST_N + ST_EPI_COMPACT] = st_compact;
+            p.stats[blockIdx.x * ST_N + ST_EPI_QLOAD] = st_qload;
+            p.stats[blockIdx.x * ST_N + ST_EPI_NCOMPACT] = st_ncompact;
+            p.stats[blockIdx.x * ST_N + ST_EPI_NSLOW] = st_nslow;
         }
     }
 
@@ -342,6 +378,40 @@ __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishPa
     }
 }
 
+// ----------------------------------------------------------------------------------------------- sample threshold
+// After the strided SAMPLE pass: the r-th best tensor-core score among a query's sample candidates becomes its
+// starting threshold for the full scan.  With a sample of 1/stride of the rows, about r*stride rows of the whole
+// corpus beat it, so r is chosen to leave ~6 k' survivors: enough to contain the top-k' with overwhelming probability,
+// few enough that the epilogue's append path and the compaction are rare.  A threshold that turns out too high only
+// costs speed (the query fails the completeness proof and is re-run exactly), never correctness.
+__global__ void __launch_bounds__(FN_THREADS)
+sample_threshold_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int cap, int nqb,
+                        int n_chunks, int rank, int topk_cap, unsigned int* __restrict__ gthr) {
+    extern __shared__ __align__(16) char smem[];
+    const int tid = threadIdx.x;
+    const int q = blockIdx.x;
+    const int qb = q / TC_BM, ql = q % TC_BM;
+    BlockTopK<FN_THREADS, uint32_t> tk;
+    tk.attach(smem, topk_cap, rank, FN_THREADS, BlockTopK<FN_THREADS, uint32_t>::NLO + 3);
+    tk.init();
+    __syncthreads();
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        const size_t slot = ((size_t)(chunk * nqb + qb)) * TC_BM + ql;
+        const int n = cand_cnt[slot];
+        const unsigned long long* b = cand + slot * cap;
+        for (int base = 0; base < n; base += FN_THREADS) {
+            const int i = base + tid;
+            const bool valid = i < n;
+            unsigned long long e = valid ? b[i] : 0ull;
+            tk.offer(valid, (uint64_t)mono32(__uint_as_float((uint32_t)(e >> 32))), ~(uint32_t)e);
+            tk.settle();
+        }
+    }
+    __syncthreads();
+    tk.finalize();
+    if (tid == 0) gthr[q] = tk.count() >= rank ? (unsigned int)tk.out_hi()[rank - 1] : 0u;
+}
+
 // ----------------------------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -388,8 +458,9 @@ int launch_scan2(const void* corpus16, int dtype, const ScanParams& sp, int cs, 
 
 struct TensorPlan {
     int sm_count, version, cs, tile_rows, nqb, n_tiles, n_chunks, n_items, kprime, cap, topk_cap, max_ctas;
+    int sample, s_stride, s_tiles, s_chunks, s_items, s_kprime, s_cap, s_rank, s_topk_cap;   // strided sample pass
     size_t scan_smem, finish_smem;
-    size_t off_cand, off_cnt, off_gthr, off_flaglist, off_nflag, off_exact, total;
+    size_t off_cand, off_cnt, off_gthr, off_flaglist, off_nflag, off_stats, off_exact, total;
 };
 
 static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
@@ -443,22 +514,47 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     pl.n_chunks = want < pl.n_tiles ? want : pl.n_tiles;
     if (pl.n_chunks < 1) pl.n_chunks = 1;
     pl.n_items = qgroups * pl.n_chunks;
+    // strided sample pass that seeds the per-query thresholds (large corpora only)
+    pl.s_stride = 64;
+    pl.s_tiles = pl.n_tiles / pl.s_stride;
+    pl.sample = pl.s_tiles >= 64 && env_int("B200RAG_NO_SAMPLE", 0) == 0;
+    pl.s_chunks = want < pl.s_tiles ? want : (pl.s_tiles > 0 ? pl.s_tiles : 1);
+    pl.s_items = qgroups * pl.s_chunks;
+    pl.s_kprime = 32;
+    pl.s_cap = 64;
+    pl.s_rank = (6 * pl.kprime + pl.s_stride - 1) / pl.s_stride;
+    if (pl.s_rank < 8) pl.s_rank = 8;
+    if (pl.s_rank > 32) pl.s_rank = 32;
+    pl.s_topk_cap = BlockTopK<FN_THREADS, uint32_t>::capacity_for(pl.s_rank, FN_THREADS);
     pl.topk_cap = BlockTopK<FN_THREADS, uint32_t>::capacity_for(pl.kprime, FN_THREADS);
     pl.finish_smem = (size_t)dim * 8 + (size_t)pl.kprime * (8 + 4 + 4 + 4) + 32 +
                      BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.topk_cap) + 64;
     size_t off = 0;
     auto take = [&](size_t bytes) { off = align_up(off, 256); size_t o = off; off += bytes; return o; };
-    pl.off_cand = take((size_t)pl.n_chunks * pl.nqb * TC_BM * pl.cap * 8);
-    pl.off_cnt = take((size_t)pl.n_chunks * pl.nqb * TC_BM * 4);
+    const int max_chunks = pl.n_chunks > pl.s_chunks ? pl.n_chunks : pl.s_chunks;
+    pl.off_cand = take((size_t)max_chunks * pl.nqb * TC_BM * pl.cap * 8);
+    pl.off_cnt = take((size_t)max_chunks * pl.nqb * TC_BM * 4);
     pl.off_gthr = take((size_t)pl.nqb * TC_BM * 4);
     pl.off_flaglist = take((size_t)n_q * 4);
     pl.off_nflag = take(256);
+    pl.off_stats = take((size_t)256 * ST_N * 8);
     pl.off_exact = take(exact_workspace_bytes(n_rows, dim, TC_FALLBACK_BATCH, k));
     pl.total = align_up(off, 256);
     return pl;
 }
 
 size_t tensor_workspace_bytes(int64_t n_rows, int dim, int n_q, int k) { return plan_tensor(n_rows, dim, n_q, k).total; }
+
+static bool g_stats_enabled = false;
+static unsigned long long* g_stats_last = nullptr;
+int scan_stats(int enable, unsigned long long* out_host, int max_ctas) {
+    g_stats_enabled = enable != 0;
+    if (out_host && g_stats_last && max_ctas > 0) {
+        if (max_ctas > 256) max_ctas = 256;
+        B200_CUDA_CHECK(cudaMemcpy(out_host, g_stats_last, (size_t)max_ctas * ST_N * 8, cudaMemcpyDeviceToHost));
+    }
+    return B200RAG_OK;
+}
 
 static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
 void profile_next_scan(void* a, void* b) { g_prof_start = static_cast<cudaEvent_t>(a); g_prof_stop = static_cast<cudaEvent_t>(b); }
@@ -488,33 +584,59 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
         sp.n_q = n_q;
         sp.dim = dim;
         sp.n_kblocks = (dim + TC_BK - 1) / TC_BK;
-        sp.n_tiles = pl.n_tiles;
         sp.nqb = pl.nqb;
-        sp.n_chunks = pl.n_chunks;
-        sp.n_items = pl.n_items;
-        sp.kprime = pl.kprime;
-        sp.cap = pl.cap;
         sp.idesc = umma_idesc(dtype, pl.tile_rows);
         sp.cand = reinterpret_cast<unsigned long long*>(ws + pl.off_cand);
         sp.cand_cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
         sp.gthr = reinterpret_cast<unsigned int*>(ws + pl.off_gthr);
         sp.queries = static_cast<const uint16_t*>(queries16);
-        const bool prof = g_prof_start && g_prof_stop;
-        if (prof) B200_CUDA_CHECK(cudaEventRecord(g_prof_start, st));
-        if (pl.version == 2) {
-            int rc = launch_scan2(corpus16, dtype, sp, pl.cs, pl.max_ctas, st, nullptr);
-            if (rc) return rc;
-        } else {
-            CUtensorMap map_q, map_x;
+        sp.stats = g_stats_enabled ? reinterpret_cast<unsigned long long*>(ws + pl.off_stats) : nullptr;
+        if (g_stats_enabled) {
+            B200_CUDA_CHECK(cudaMemsetAsync(sp.stats, 0, (size_t)256 * ST_N * 8, st));
+            g_stats_last = sp.stats;
+        }
+        CUtensorMap map_q, map_x;
+        if (pl.version == 1) {
             int rc = make_tensor_map(&map_q, queries16, n_q, dim, dtype, TC_BM);
             if (rc) return rc;
             rc = make_tensor_map(&map_x, corpus16, n_rows, dim, dtype, TC_BN);
             if (rc) return rc;
             B200_CUDA_CHECK(cudaFuncSetAttribute(dense_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.scan_smem));
-            int grid = pl.n_items < pl.sm_count ? pl.n_items : pl.sm_count;
-            dense_scan_kernel<<<grid, TC_THREADS, pl.scan_smem, st>>>(map_q, map_x, sp);
         }
-        B200_CUDA_CHECK(cudaGetLastError());
+        auto launch = [&](const ScanParams& spx) -> int {
+            if (pl.version == 2) return launch_scan2(corpus16, dtype, spx, pl.cs, pl.max_ctas, st, nullptr);
+            int grid = spx.n_items < pl.sm_count ? spx.n_items : pl.sm_count;
+            dense_scan_kernel<<<grid, TC_THREADS, pl.scan_smem, st>>>(map_q, map_x, spx);
+            B200_CUDA_CHECK(cudaGetLastError());
+            return B200RAG_OK;
+        };
+        const bool prof = g_prof_start && g_prof_stop;
+        if (prof) B200_CUDA_CHECK(cudaEventRecord(g_prof_start, st));
+        if (pl.sample) {
+            // pass 0: every s_stride-th tile, tiny k'; its r-th best score per query seeds the thresholds
+            ScanParams s0 = sp;
+            s0.stats = nullptr;
+            s0.n_tiles = pl.s_tiles;
+            s0.tile_stride = pl.s_stride;
+            s0.n_chunks = pl.s_chunks;
+            s0.n_items = pl.s_items;
+            s0.kprime = pl.s_kprime;
+            s0.cap = pl.s_cap;
+            int rc = launch(s0);
+            if (rc) return rc;
+            size_t tsm = BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.s_topk_cap) + 64;
+            sample_threshold_kernel<<<pl.nqb * TC_BM, FN_THREADS, tsm, st>>>(s0.cand, s0.cand_cnt, s0.cap, pl.nqb, pl.s_chunks,
+                                                                            pl.s_rank, pl.s_topk_cap, sp.gthr);
+            B200_CUDA_CHECK(cudaGetLastError());
+        }
+        sp.n_tiles = pl.n_tiles;
+        sp.tile_stride = 1;
+        sp.n_chunks = pl.n_chunks;
+        sp.n_items = pl.n_items;
+        sp.kprime = pl.kprime;
+        sp.cap = pl.cap;
+        int rc = launch(sp);
+        if (rc) return rc;
         if (prof) {
             B200_CUDA_CHECK(cudaEventRecord(g_prof_stop, st));
             g_prof_start = g_prof_stop = nullptr;

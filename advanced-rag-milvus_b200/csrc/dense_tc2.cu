@@ -80,6 +80,8 @@ dense_scan2_kernel(const __grid_constant__ CUtensorMap map_x, const ScanParams p
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            long long st_wait = 0;
+            ST_T0(st_begin);
             for (int item = cluster_id; item < p.n_items; item += n_clusters) {
                 const int chunk = item / qgroups;
                 const int t0 = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
@@ -88,20 +90,26 @@ dense_scan2_kernel(const __grid_constant__ CUtensorMap map_x, const ScanParams p
                     for (int sg = 0; sg < stages_per_tile; ++sg) {
                         const int kb0 = sg * Cfg::KPS;
                         const int nkb = min(Cfg::KPS, p.n_kblocks - kb0);
-                        mbar_wait(&empty_bar[stage], phase ^ 1);      // slot free in EVERY CTA of the cluster
+                        ST_T0(tw);
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        ST_ADD(st_wait, tw);      // slot free in EVERY CTA of the cluster
                         uint8_t* sx = stage_base + stage * Cfg::STAGE_BYTES;
                         mbar_expect_tx(&full_bar[stage], (uint32_t)(nkb * Cfg::KB_BYTES));
                         for (int j = 0; j < nkb; ++j) {
                             const int kb = kb0 + j;
                             if (cs == 1) {
-                                tma_load_2d(sx + j * Cfg::KB_BYTES, &map_x, kb * TC_BK, tile * N_ACC, &full_bar[stage]);
+                                tma_load_2d(sx + j * Cfg::KB_BYTES, &map_x, kb * TC_BK, tile * p.tile_stride * N_ACC, &full_bar[stage]);
                             } else if (kb % cs == rank) {
-                                tma_load_2d_mc(sx + j * Cfg::KB_BYTES, &map_x, kb * TC_BK, tile * N_ACC, &full_bar[stage], mc_mask);
+                                tma_load_2d_mc(sx + j * Cfg::KB_BYTES, &map_x, kb * TC_BK, tile * p.tile_stride * N_ACC, &full_bar[stage], mc_mask);
                             }
                         }
                         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
+            }
+            if (p.stats) {
+                p.stats[blockIdx.x * ST_N + ST_PROD_TOTAL] = clock64() - st_begin;
+                p.stats[blockIdx.x * ST_N + ST_PROD_WAIT_EMPTY] = st_wait;
             }
         }
     } else if (warp == 1) {
@@ -109,30 +117,45 @@ dense_scan2_kernel(const __grid_constant__ CUtensorMap map_x, const ScanParams p
         int stage = 0, astage = 0;
         uint32_t phase = 0, aphase = 0, qphase = 0;
         const uint32_t idesc = p.idesc;
+        long long st_wfull = 0, st_wtempty = 0, st_wq = 0;
+        ST_T0(st_begin);
         for (int item = cluster_id; item < p.n_items; item += n_clusters) {
             const int chunk = item / qgroups;
             const int t0 = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
             const int t1 = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
+            ST_T0(tq);
             mbar_wait(qready_bar, qphase);                 // this item's query block is in TMEM
+            ST_ADD(st_wq, tq);
             qphase ^= 1;
             tc_fence_after();
             for (int tile = t0; tile < t1; ++tile) {
+                ST_T0(te);
                 mbar_wait(&tempty_bar[astage], aphase ^ 1);
+                ST_ADD(st_wtempty, te);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(Cfg::ACC_COL0 + astage * N_ACC);
                 for (int sg = 0; sg < stages_per_tile; ++sg) {
                     const int kb0 = sg * Cfg::KPS;
                     const int nkb = min(Cfg::KPS, p.n_kblocks - kb0);
+                    ST_T0(tf);
                     mbar_wait(&full_bar[stage], phase);
+                    ST_ADD(st_wfull, tf);
                     tc_fence_after();
                     if (elect_one()) {
+                        // descriptors differ only in the 14-bit start-address field: one add per MMA
                         const uint32_t sx = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
-                        for (int j = 0; j < nkb; ++j) {
+                        const uint32_t desc_lo0 = ((sx & 0x3FFFF) >> 4) | (1u << 16);
+                        const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+                        const uint32_t a0 = tmem_base + (uint32_t)(kb0 * 32);
 #pragma unroll
-                            for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
-                                const int kstep = (kb0 + j) * (TC_BK / 16) + k4;
-                                umma_f16_ts(d_tmem, tmem_base + (uint32_t)(kstep * 8),
-                                            umma_desc_sw128(sx + j * Cfg::KB_BYTES + k4 * 32), idesc, (uint32_t)(kstep != 0));
+                        for (int j = 0; j < Cfg::KPS; ++j) {
+                            if (j < nkb) {
+#pragma unroll
+                                for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+                                    const uint32_t acc = (j | k4) != 0 ? 1u : (uint32_t)(sg != 0);
+                                    umma_f16_ts(d_tmem, a0 + (uint32_t)((j * 4 + k4) * 8),
+                                                desc_hi | (uint64_t)(desc_lo0 + (uint32_t)((j * Cfg::KB_BYTES + k4 * 32) >> 4)), idesc, acc);
+                                }
                             }
                         }
                         if (cs == 1) umma_commit(&empty_bar[stage]);
@@ -145,6 +168,12 @@ dense_scan2_kernel(const __grid_constant__ CUtensorMap map_x, const ScanParams p
                 if (++astage == 2) { astage = 0; aphase ^= 1; }
             }
         }
+        if (p.stats && lane == 0) {
+            p.stats[blockIdx.x * ST_N + ST_MMA_TOTAL] = clock64() - st_begin;
+            p.stats[blockIdx.x * ST_N + ST_MMA_WAIT_FULL] = st_wfull;
+            p.stats[blockIdx.x * ST_N + ST_MMA_WAIT_TEMPTY] = st_wtempty;
+            p.stats[blockIdx.x * ST_N + ST_MMA_WAIT_Q] = st_wq;
+        }
     } else {
         // ================================================================= epilogue
         const int quarter = warp & 3;
@@ -153,6 +182,8 @@ dense_scan2_kernel(const __grid_constant__ CUtensorMap map_x, const ScanParams p
         const uint32_t scratch = smem_u32(scratch_all + (size_t)(warp - 2) * p.cap);
         int astage = 0;
         uint32_t aphase = 0;
+        long long st_wtfull = 0, st_compact = 0, st_qload = 0, st_ncompact = 0, st_nslow = 0;
+        ST_T0(st_begin);
         for (int item = cluster_id; item < p.n_items; item += n_clusters) {
             const int chunk = item / qgroups, qg = item % qgroups;
             const int qb = qg * cs + rank;
@@ -161,6 +192,7 @@ dense_scan2_kernel(const __grid_constant__ CUtensorMap map_x, const ScanParams p
             const int q = qb * TC_BM + qlane;
             const bool active = q < p.n_q;
             // ---- query block -> TMEM.  The previous item's MMAs have all retired (its last tfull was observed).
+            ST_T0(tql);
             {
                 const uint4* qrow = reinterpret_cast<const uint4*>(p.queries + (size_t)(active ? q : 0) * p.dim);
                 const int n_vec = p.dim / 8;                              // 16-byte vectors in the row
@@ -180,20 +212,25 @@ dense_scan2_kernel(const __grid_constant__ CUtensorMap map_x, const ScanParams p
                 __syncwarp();
                 if (lane == 0) mbar_arrive(qready_bar);
             }
+            ST_ADD(st_qload, tql);
             unsigned long long* buf = p.cand + ((size_t)(chunk * p.nqb + qb) * TC_BM + qlane) * p.cap;
             unsigned int* my_gthr = p.gthr + q;
             float thr = active ? gthr_load(my_gthr) : CUDART_INF_F;
             int cnt = 0;
             for (int tile = t0; tile < t1; ++tile) {
                 if (active && ((tile - t0) & 15) == 15) thr = fmaxf(thr, gthr_load(my_gthr));
+                ST_T0(tt);
                 mbar_wait(&tfull_bar[astage], aphase);
+                ST_ADD(st_wtfull, tt);
                 tc_fence_after();
-                const int64_t row0 = (int64_t)tile * N_ACC;
+                const int64_t row0 = (int64_t)tile * p.tile_stride * N_ACC;
                 const bool partial = row0 + N_ACC > p.n_rows;
                 const uint32_t taddr = lane_taddr + (uint32_t)(Cfg::ACC_COL0 + astage * N_ACC);
 #pragma unroll 1
                 for (int c = 0; c < N_ACC / 32; ++c) {
                     unsigned need = __ballot_sync(0xffffffffu, cnt > p.cap - 32);
+                    ST_T0(tc0);
+                    st_ncompact += __popc(need);
                     while (need) {
                         const int L = __ffs(need) - 1;
                         need &= need - 1;
@@ -207,6 +244,7 @@ dense_scan2_kernel(const __grid_constant__ CUtensorMap map_x, const ScanParams p
                             atomicMax(my_gthr, mono32(t));
                         }
                     }
+                    ST_ADD(st_compact, tc0);
                     uint32_t r[32];
                     tmem_ld32(taddr + c * 32, r);
                     if (partial) {
@@ -218,6 +256,7 @@ dense_scan2_kernel(const __grid_constant__ CUtensorMap map_x, const ScanParams p
 #pragma unroll
                     for (int i = 0; i < 32; ++i) any |= __uint_as_float(r[i]) > thr;
                     if (any) {
+                        ++st_nslow;
                         const uint32_t rbase = (uint32_t)(row0 + c * 32);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
@@ -247,6 +286,14 @@ dense_scan2_kernel(const __grid_constant__ CUtensorMap map_x, const ScanParams p
                 }
             }
             p.cand_cnt[(size_t)(chunk * p.nqb + qb) * TC_BM + qlane] = cnt;
+        }
+        if (p.stats && warp == 2 && lane == 0) {
+            p.stats[blockIdx.x * ST_N + ST_EPI_TOTAL] = clock64() - st_begin;
+            p.stats[blockIdx.x * ST_N + ST_EPI_WAIT_TFULL] = st_wtfull;
+            p.stats[blockIdx.x * ST_N + ST_EPI_COMPACT] = st_compact;
+            p.stats[blockIdx.x * ST_N + ST_EPI_QLOAD] = st_qload;
+            p.stats[blockIdx.x * ST_N + ST_EPI_NCOMPACT] = st_ncompact;
+            p.stats[blockIdx.x * ST_N + ST_EPI_NSLOW] = st_nslow;
         }
     }
 

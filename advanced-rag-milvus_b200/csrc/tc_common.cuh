@@ -269,13 +269,20 @@ __device__ __forceinline__ float gthr_load(const unsigned int* p) {
     return k ? unmono32(k) : -CUDART_INF_F;
 }
 
+// Cycle-counter slots written per CTA when ScanParams::stats is set (one elected lane per role).
+enum { ST_MMA_TOTAL = 0, ST_MMA_WAIT_FULL, ST_MMA_WAIT_TEMPTY, ST_MMA_WAIT_Q, ST_PROD_TOTAL, ST_PROD_WAIT_EMPTY,
+       ST_EPI_TOTAL, ST_EPI_WAIT_TFULL, ST_EPI_COMPACT, ST_EPI_QLOAD, ST_EPI_NCOMPACT, ST_EPI_NSLOW, ST_N = 16 };
+#define ST_T0(var) long long var = clock64()
+#define ST_ADD(acc, var) acc += clock64() - var
+
 // Scan-kernel parameters shared by both kernels.
 struct ScanParams {
     int64_t n_rows;
     int n_q;
     int dim;
     int n_kblocks;       // ceil(dim / 64)
-    int n_tiles;         // ceil(n_rows / tile rows)
+    int n_tiles;         // tiles this launch visits (ceil(n_rows / tile rows) for a full scan)
+    int tile_stride;     // visited tile t is corpus tile t * tile_stride (1 = full scan, >1 = strided sample pass)
     int nqb;             // query blocks (padded to a multiple of the cluster size in v2)
     int n_chunks;
     int n_items;
@@ -286,6 +293,7 @@ struct ScanParams {
     int* cand_cnt;              // [n_chunks][nqb][128]
     unsigned int* gthr;         // [nqb*128] shared per-query threshold keys (mono32), monotone via atomicMax
     const uint16_t* queries;    // v2 loads Q rows itself
+    unsigned long long* stats;  // optional [gridDim.x][16] cycle counters (debug/profiling), may be NULL
 };
 
 }  // namespace b200rag

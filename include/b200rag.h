@@ -98,6 +98,11 @@ int b200rag_dense_topk(const void* corpus16, int64_t n_rows, int32_t dim, int32_
  * after its scan kernel on the call's stream, then clears the hook.  bench.py uses it to time the dominant kernel
  * inside the timed region without a profiler. */
 int b200rag_profile_next_scan(void* start_event, void* stop_event);
+/* Debug/profiling: enable per-CTA cycle counters in the tensor-core scan kernels (16 u64 slots per CTA: MMA total,
+ * MMA wait-for-data, MMA wait-for-epilogue, MMA wait-for-queries, producer total, producer wait-for-slot, epilogue
+ * total, epilogue wait-for-accumulator, epilogue compaction, epilogue query load, #compactions, #slow-path groups).
+ * With out_host != NULL the counters of the last scan are copied to host memory (synchronous). */
+int b200rag_debug_scan_stats(int32_t enable, uint64_t* out_host, int32_t max_ctas);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Sparse inner-product top-k over doc-range-blocked postings (K3).  Replaces Collection.search on
