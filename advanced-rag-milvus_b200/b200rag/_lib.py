@@ -27,6 +27,7 @@ class B200RagError(RuntimeError):
 SIGNATURES = {
     "b200rag_last_error": (ctypes.c_char_p, []),
     "b200rag_abi_version": (ctypes.c_int, []),
+    "b200rag_kernel_launch_count": (ctypes.c_uint64, []),
     "b200rag_device_info": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
     "b200rag_prepare_rows": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p]),
     "b200rag_dense_topk_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32, c_int32]),

@@ -1,4 +1,5 @@
 // api.cu -- error plumbing, device info and row preparation for libb200rag.so.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -15,6 +16,10 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
@@ -82,6 +87,7 @@ extern "C" {
 const char* b200rag_last_error(void) { return g_err; }
 
 int b200rag_abi_version(void) { return B200RAG_ABI_VERSION; }
+uint64_t b200rag_kernel_launch_count(void) { return b200rag::launch_count(); }
 
 int b200rag_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;
@@ -106,10 +112,10 @@ int b200rag_prepare_rows(const float* in_f32, void* out16, int64_t n_rows, int32
     B200_REQUIRE(blocks < (int64_t)1 << 31, "prepare_rows: too many rows for one call");
     if (dtype == B200RAG_F16) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(prepare_rows_kernel<B200RAG_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prepare_rows_kernel<B200RAG_F16><<<(unsigned)blocks, PREP_THREADS, smem, st>>>(in_f32, (uint16_t*)out16, n_rows, dim, normalize);
+        prepare_rows_kernel<B200RAG_F16><<<(unsigned)blocks, PREP_THREADS, smem, st>>>(in_f32, (uint16_t*)out16, n_rows, dim, normalize); count_launch();
     } else {
         B200_CUDA_CHECK(cudaFuncSetAttribute(prepare_rows_kernel<B200RAG_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prepare_rows_kernel<B200RAG_BF16><<<(unsigned)blocks, PREP_THREADS, smem, st>>>(in_f32, (uint16_t*)out16, n_rows, dim, normalize);
+        prepare_rows_kernel<B200RAG_BF16><<<(unsigned)blocks, PREP_THREADS, smem, st>>>(in_f32, (uint16_t*)out16, n_rows, dim, normalize); count_launch();
     }
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;

@@ -13,6 +13,7 @@ namespace b200rag {
 // --------------------------------------------------------------------------- error plumbing (api.cu)
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void count_launch();   // bumps the process-wide kernel-launch counter (b200rag_kernel_launch_count)
 
 #define B200_CUDA_CHECK(expr)                                            \
     do {                                                                 \

@@ -203,11 +203,11 @@ int launch_merge(const double* cand_scores, const int64_t* cand_ids, int n_launc
     if (out_scores_f64) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(merge_topk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         merge_topk_kernel<double><<<n_launch, MG_THREADS, smem, st>>>(cand_scores, cand_ids, n_cand, k, cap, q_list,
-                                                                     out_scores_f64, out_ids, out_counts);
+                                                                     out_scores_f64, out_ids, out_counts); count_launch();
     } else {
         B200_CUDA_CHECK(cudaFuncSetAttribute(merge_topk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         merge_topk_kernel<float><<<n_launch, MG_THREADS, smem, st>>>(cand_scores, cand_ids, n_cand, k, cap, q_list,
-                                                                    out_scores_f32, out_ids, out_counts);
+                                                                    out_scores_f32, out_ids, out_counts); count_launch();
     }
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;
@@ -237,11 +237,11 @@ int run_exact(const void* corpus16, int64_t n_rows, int dim, int dtype, const vo
     if (dtype == B200RAG_F16) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(dense_exact_kernel<B200RAG_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         dense_exact_kernel<B200RAG_F16><<<grid, EX_THREADS, pl.smem, st>>>(c, n_rows, dim, q, n_launch, q_list, k, pl.cap,
-                                                                         pl.rows_per_chunk, pl.n_chunks, id_offset, part_scores, part_ids);
+                                                                         pl.rows_per_chunk, pl.n_chunks, id_offset, part_scores, part_ids); count_launch();
     } else {
         B200_CUDA_CHECK(cudaFuncSetAttribute(dense_exact_kernel<B200RAG_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         dense_exact_kernel<B200RAG_BF16><<<grid, EX_THREADS, pl.smem, st>>>(c, n_rows, dim, q, n_launch, q_list, k, pl.cap,
-                                                                          pl.rows_per_chunk, pl.n_chunks, id_offset, part_scores, part_ids);
+                                                                          pl.rows_per_chunk, pl.n_chunks, id_offset, part_scores, part_ids); count_launch();
     }
     B200_CUDA_CHECK(cudaGetLastError());
     return launch_merge(part_scores, part_ids, n_launch, q_list, pl.n_chunks * k, k, out_scores, nullptr, out_ids, nullptr, st);

@@ -455,6 +455,9 @@ int scan2_tile_rows(int dim);
 size_t scan2_smem_bytes(int cap);
 int scan2_max_clusters(int dim, int cap, int cs, int sm_count);
 int launch_scan2(const void* corpus16, int dtype, const ScanParams& sp, int cs, int max_ctas, cudaStream_t st, int* grid_out);
+size_t scan3_smem_bytes(int cap);
+int scan3_max_clusters(int cap, int sm_count);
+int launch_scan3(const void* corpus16, int dtype, const ScanParams& sp, int max_clusters, cudaStream_t st);
 
 struct TensorPlan {
     int sm_count, version, cs, tile_rows, nqb, n_tiles, n_chunks, n_items, kprime, cap, topk_cap, max_ctas;
@@ -486,13 +489,22 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     pl.nqb = (n_q + TC_BM - 1) / TC_BM;
     pl.kprime = tc_kprime(k);
     pl.cap = tc_bufcap(pl.kprime);
-    // kernel generation: 2 (Q resident in TMEM + cluster multicast) whenever the query block fits TMEM
-    pl.version = scan2_supported(dim) ? 2 : 1;
-    int forced = env_int("B200RAG_SCAN_VERSION", 0);        // A/B testing hook
-    if (forced == 1 || (forced == 2 && scan2_supported(dim))) pl.version = forced;
+    // kernel generation: 3 = CTA pairs (tcgen05 cta_group::2, dense_tc3.cu) is the product path; 1 (single CTA, this file)
+    // and 2 (query block in TMEM + multicast, dense_tc2.cu) are kept selectable for A/B measurements.
+    pl.version = pl.nqb >= 2 ? 3 : 1;     // a single query block cannot fill a pair's M = 256
+    int forced = env_int("B200RAG_SCAN_VERSION", 0);
+    if (forced == 1 || forced == 3 || (forced == 2 && scan2_supported(dim))) pl.version = forced;
     int units;                                              // co-resident scheduling units (CTAs or clusters)
     int qgroups;
-    if (pl.version == 2) {
+    if (pl.version == 3) {
+        pl.tile_rows = 256;
+        pl.cs = 2;
+        qgroups = (pl.nqb + 1) / 2;
+        pl.nqb = qgroups * 2;                               // candidate / threshold buffers cover the padded block too
+        units = scan3_max_clusters(pl.cap, pl.sm_count);
+        pl.max_ctas = units * 2;
+        pl.scan_smem = scan3_smem_bytes(pl.cap);
+    } else if (pl.version == 2) {
         pl.tile_rows = scan2_tile_rows(dim);
         pl.cs = pl.nqb % 4 == 0 ? 4 : (pl.nqb % 2 == 0 ? 2 : 1);
         int fcs = env_int("B200RAG_CLUSTER", 0);
@@ -585,7 +597,7 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
         sp.dim = dim;
         sp.n_kblocks = (dim + TC_BK - 1) / TC_BK;
         sp.nqb = pl.nqb;
-        sp.idesc = umma_idesc(dtype, pl.tile_rows);
+        sp.idesc = pl.version == 3 ? umma_idesc_mn(dtype, 2 * TC_BM, pl.tile_rows) : umma_idesc(dtype, pl.tile_rows);
         sp.cand = reinterpret_cast<unsigned long long*>(ws + pl.off_cand);
         sp.cand_cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
         sp.gthr = reinterpret_cast<unsigned int*>(ws + pl.off_gthr);
@@ -604,9 +616,10 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
             B200_CUDA_CHECK(cudaFuncSetAttribute(dense_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.scan_smem));
         }
         auto launch = [&](const ScanParams& spx) -> int {
+            if (pl.version == 3) return launch_scan3(corpus16, dtype, spx, pl.max_ctas / 2, st);
             if (pl.version == 2) return launch_scan2(corpus16, dtype, spx, pl.cs, pl.max_ctas, st, nullptr);
             int grid = spx.n_items < pl.sm_count ? spx.n_items : pl.sm_count;
-            dense_scan_kernel<<<grid, TC_THREADS, pl.scan_smem, st>>>(map_q, map_x, spx);
+            dense_scan_kernel<<<grid, TC_THREADS, pl.scan_smem, st>>>(map_q, map_x, spx); count_launch();
             B200_CUDA_CHECK(cudaGetLastError());
             return B200RAG_OK;
         };
@@ -626,7 +639,7 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
             if (rc) return rc;
             size_t tsm = BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.s_topk_cap) + 64;
             sample_threshold_kernel<<<pl.nqb * TC_BM, FN_THREADS, tsm, st>>>(s0.cand, s0.cand_cnt, s0.cap, pl.nqb, pl.s_chunks,
-                                                                            pl.s_rank, pl.s_topk_cap, sp.gthr);
+                                                                            pl.s_rank, pl.s_topk_cap, sp.gthr); count_launch();
             B200_CUDA_CHECK(cudaGetLastError());
         }
         sp.n_tiles = pl.n_tiles;
@@ -670,10 +683,10 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
     fp.err_max = out_err;
     if (dtype == B200RAG_F16) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(dense_finish_kernel<B200RAG_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.finish_smem));
-        dense_finish_kernel<B200RAG_F16><<<n_q, FN_THREADS, pl.finish_smem, st>>>(fp);
+        dense_finish_kernel<B200RAG_F16><<<n_q, FN_THREADS, pl.finish_smem, st>>>(fp); count_launch();
     } else {
         B200_CUDA_CHECK(cudaFuncSetAttribute(dense_finish_kernel<B200RAG_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.finish_smem));
-        dense_finish_kernel<B200RAG_BF16><<<n_q, FN_THREADS, pl.finish_smem, st>>>(fp);
+        dense_finish_kernel<B200RAG_BF16><<<n_q, FN_THREADS, pl.finish_smem, st>>>(fp); count_launch();
     }
     B200_CUDA_CHECK(cudaGetLastError());
 

@@ -343,6 +343,7 @@ static int launch_scan2_t(const void* corpus16, int dtype, const ScanParams& sp,
     cfg.gridDim = dim3(n_clusters * cs);
     if (grid_out) *grid_out = n_clusters * cs;
     B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, map_x, sp, cs));
+    count_launch();
     return B200RAG_OK;
 }
 

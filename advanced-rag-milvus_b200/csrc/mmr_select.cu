@@ -142,7 +142,7 @@ int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     B200_CUDA_CHECK(cudaFuncSetAttribute(mmr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mmr_select_kernel<<<n_queries, MMR_THREADS, smem, st>>>(cand_doc, cand_rel, cand_n, n_max, doc_tok_ptr, doc_tok_ids,
-                                                           vocab_words, lambda, k_sel, k_max, out_pick, out_n);
+                                                           vocab_words, lambda, k_sel, k_max, out_pick, out_n); count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;
 }

@@ -195,7 +195,7 @@ int b200rag_rrf_fuse(const int64_t* list_ids, const int32_t* list_len, int32_t n
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     B200_CUDA_CHECK(cudaFuncSetAttribute(rrf_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rrf_fuse_kernel<<<n_queries, RRF_THREADS, smem, st>>>(list_ids, list_len, n_lists, n_queries, k_max, weights, rrf_k,
-                                                         table_size, sort_cap, out_ids, out_scores, out_mask, out_first, out_n);
+                                                         table_size, sort_cap, out_ids, out_scores, out_mask, out_first, out_n); count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;
 }

@@ -142,7 +142,7 @@ int b200rag_sparse_topk(const int64_t* blk_term_ptr, const uint16_t* post_doc, c
     dim3 grid((unsigned)n_blocks, (unsigned)n_queries);
     sparse_block_kernel<<<grid, SP_THREADS, smem, st>>>(blk_term_ptr, post_doc, post_w, n_docs, n_terms, block_docs,
                                                        (int)n_blocks, q_ptr, q_terms, q_vals, k, cap, id_offset,
-                                                       part_scores, part_ids);
+                                                       part_scores, part_ids); count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return launch_merge(part_scores, part_ids, n_queries, nullptr, (int)(n_blocks * k), k, nullptr, out_scores, out_ids,
                         out_counts, st);

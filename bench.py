@@ -66,48 +66,62 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region, in-process through NVML (pynvml).
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+    (Spawning `nvidia-smi -lms` next to the timed loop costs several ms per step while it initialises; an NVML handle
+    opened before the warm-up does not disturb the GPU.)"""
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("hw_power_brake_slowdown", 0x80), ("sw_power_cap", 0x4))
+
+    def __init__(self, gpu_index: int, period_s: float = 0.02):
+        self.period = period_s
+        self.samples, self.reasons, self.power = [], set(), []
+        self._stop = threading.Event()
+        self._thread = None
+        self.h = None
+        self.smax = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                      # noqa: BLE001 - NVML missing is reported, not fatal
+            self.err = repr(e)
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for name, bit in self.REASONS:
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:                       # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.h is None:
+            return
+        self.samples, self.reasons, self.power = [], set(), []
+        self._stop.clear()
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                smax = float(parts[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self._stop.set()
+        self._thread.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w": statistics.median(self.power) if self.power else None}
 
 
 # ------------------------------------------------------------------------------------------------- reference / CPU arm
@@ -222,20 +236,23 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local_rank)
+    flags_total = torch.zeros((), dtype=torch.int64, device=device)
     for it in range(args.warmup):
-        search(q_dev[it % POOL])
+        s, i, f = search(q_dev[it % POOL])
+        flags_total += f.sum()        # also warms torch's own reduce/add kernels (first use costs ~100 ms of module load)
     barrier()
 
     # ---------------- timed region 1: device-resident inputs -------------------------------------
-    sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in scan_ev:          # torch creates the cudaEvent lazily on the first record(); the hook needs live handles
         a.record()
         b.record()
-    flags_total = torch.zeros((), dtype=torch.int64, device=device)
+    flags_total.zero_()
     barrier()
+    launches0 = int(lib.b200rag_kernel_launch_count())
     ev0.record()
     for it in range(args.steps):
         lib.b200rag_profile_next_scan(scan_ev[it][0].cuda_event, scan_ev[it][1].cuda_event)
@@ -243,6 +260,7 @@ def main():
         flags_total += f.sum()
     ev1.record()
     barrier()
+    launches = int(lib.b200rag_kernel_launch_count()) - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop()
     scan_ms = [a.elapsed_time(b) for a, b in scan_ev]
@@ -299,6 +317,8 @@ def main():
                     traffic = json.load(fh).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        scan_kernel = {"1": "dense_scan_kernel", "2": "dense_scan2_kernel"}.get(os.environ.get("B200RAG_SCAN_VERSION", ""),
+                                                                                  "dense_scan3_kernel")
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -309,9 +329,9 @@ def main():
                        "flagged_queries_in_timed_region": int(flags_total.item())},
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * K * 16,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)),
+            "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "dense_scan_kernel", "bound": "tensor", "achieved": achieved_tf,
+            "roofline": {"kernel": scan_kernel, "bound": "tensor", "achieved": achieved_tf,
                          "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops_sustained"],
                          "peak_kind": f"bf16 cuBLAS sustained, {peaks['source']} (burst {peaks['tflops_burst']})",
                          "frac_of_burst": achieved_tf / peaks["tflops_burst"],

@@ -59,6 +59,9 @@ enum {
 /* Thread-local description of the last error on this thread ("" if none). */
 const char* b200rag_last_error(void);
 int b200rag_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process so far (bench.py reports the difference over its
+ * timed region as gpu_launches). */
+uint64_t b200rag_kernel_launch_count(void);
 /* Fills SM count and compute capability of the current device. */
 int b200rag_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -173,3 +173,30 @@ def test_merge_topk(oracle_lib):
     ids = np.array([[7, 3, 2, -1, 1]], np.int64)
     s, i = o.merge_topk(sc, ids, 6)
     assert list(i[0]) == [1, 3, 2, 7, -1, -1]
+
+
+def test_pipeline_restatement_matches_reference_e2e_golden():
+    """oracle/pipeline.py (the chain the GPU tests check against) == the unmodified reference HybridRetriever.retrieve
+    over the in-memory index, on the committed golden queries (tests/golden/e2e_golden.json)."""
+    import json
+    import os
+    from oracle import e2e_corpus, inmem_index, pipeline
+    with open(os.path.join(os.path.dirname(__file__), "golden", "e2e_golden.json")) as f:
+        golden = json.load(f)
+    c = e2e_corpus.build()
+    gen = inmem_index.HashEmbeddingGenerator(e2e_corpus.SEM_DIM, e2e_corpus.DOM_DIM, c["vocab"])
+    corpus = pipeline.ArrayCorpus(c["semantic"], c["domain"], c["sp_ptr"], c["sp_idx"], c["sp_val"], e2e_corpus.VOCAB,
+                                  c["contents"])
+    assert len(golden["cases"]) == len(e2e_corpus.queries())
+    n_mmr = 0
+    for case, (text, kw) in zip(golden["cases"], e2e_corpus.queries()):
+        assert case["query"] == text
+        prof = pipeline.PROFILES_TOPK20[case["profile"]]
+        n_mmr += prof["enable_mmr"]
+        dom_q = gen.encode_domain(text, kw["domain"]) if kw.get("use_domain_index") else None
+        ids, scores, masks = pipeline.retrieve(corpus, gen.encode_semantic(text), gen.encode_sparse(text), dom_q, **prof)
+        assert [c["ids"][i] for i in ids] == case["ids"], text
+        assert [float(s).hex() for s in scores] == case["scores_hex"], text
+        names = ["semantic", "sparse", "domain"]
+        assert [sorted(n for b, n in enumerate(names) if m >> b & 1) for m in masks] == case["methods"], text
+    assert n_mmr >= 5

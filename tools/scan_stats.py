@@ -19,15 +19,17 @@ ap.add_argument("--rows", type=int, default=4_000_000)
 ap.add_argument("--dim", type=int, default=768)
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--k", type=int, default=100)
+ap.add_argument("--dtype", default="f16")
+ap.add_argument("--reps", type=int, default=1)
 args = ap.parse_args()
 dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(0)
-idx = engine.DenseIndex(args.dim, "f16", "COSINE", dev, capacity=args.rows)
+idx = engine.DenseIndex(args.dim, args.dtype, "COSINE", dev, capacity=args.rows)
 for s in range(0, args.rows, 250_000):
     idx.add(torch.randn(min(250_000, args.rows - s), args.dim, generator=g, device=dev))
 q = torch.randn(args.batch, args.dim, generator=g, device=dev)
 lib = _lib.load()
-for _ in range(3):
+for _ in range(3 + args.reps):
     idx.search(q, args.k, engine.DENSE_TENSOR)
 torch.cuda.synchronize()
 lib.b200rag_debug_scan_stats(1, None, 0)
@@ -40,7 +42,7 @@ buf = np.zeros((256, 16), dtype=np.uint64)
 lib.b200rag_debug_scan_stats(0, buf.ctypes.data_as(ctypes.c_void_p), 256)
 used = buf[buf[:, 0] > 0]
 ms = e0.elapsed_time(e1)
-print(f"v={os.environ.get('B200RAG_SCAN_VERSION')} cs={os.environ.get('B200RAG_CLUSTER')} rows={args.rows} dim={args.dim} "
+print(f"v={os.environ.get('B200RAG_SCAN_VERSION')} cs={os.environ.get('B200RAG_CLUSTER')} {args.dtype} rows={args.rows} dim={args.dim} "
       f"B={args.batch}: scan {ms:.2f} ms, {2.0 * args.batch * args.rows * args.dim / ms / 1e9:.0f} TFLOP/s, CTAs={len(used)}")
 mean = used.astype(np.float64).mean(0)
 for i, nm in enumerate(NAMES):
