@@ -154,7 +154,8 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const uint32_t tempty_leader = mapa_u32(smem_u32(tempty_bar), 0);
         int astage = 0;
         uint32_t aphase = 0;
-        long long st_wtfull = 0, st_compact = 0, st_ncompact = 0, st_nslow = 0;
+        long long st_wtfull = 0;
+        EpiCounters ec;
         ST_T0(st_begin);
         for (int item = cluster_id; item < p.n_items; item += n_clusters) {
             const int chunk = item / qgroups, qb = (item % qgroups) * 2 + rank;
@@ -167,85 +168,39 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             unsigned int* my_gthr = p.gthr + q;       // gthr has nqb*128 entries, padded blocks included
             float thr = active ? gthr_load(my_gthr) : CUDART_INF_F;
             int cnt = 0;
+            float top[TC_SAMPLE_R];
+#pragma unroll
+            for (int i = 0; i < TC_SAMPLE_R; ++i) top[i] = -CUDART_INF_F;
             for (int tile = t0; tile < t1; ++tile) {
-                if (active && ((tile - t0) & 3) == 3) thr = fmaxf(thr, gthr_load(my_gthr));
+                if (!p.sample && active && ((tile - t0) & 3) == 3) thr = fmaxf(thr, gthr_load(my_gthr));
                 ST_T0(tt);
                 mbar_wait(&tfull_bar[astage], aphase);
                 ST_ADD(st_wtfull, tt);
                 tc_fence_after();
                 const int64_t row0 = (int64_t)tile * p.tile_stride * T3_BN;
-                const bool partial = row0 + T3_BN > p.n_rows;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)astage * T3_BN;
-#pragma unroll 1
-                for (int c = 0; c < T3_BN / 32; ++c) {
-                    // make room: a lane appends at most 32 entries per column group
-                    unsigned need = __ballot_sync(0xffffffffu, cnt > p.cap - 32);
-                    ST_T0(tc0);
-                    st_ncompact += __popc(need);
-                    while (need) {
-                        const int L = __ffs(need) - 1;
-                        need &= need - 1;
-                        unsigned long long* b = reinterpret_cast<unsigned long long*>(
-                            __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), L));
-                        const int n = __shfl_sync(0xffffffffu, cnt, L);
-                        const float t = warp_compact(b, n, p.kprime, p.cap, scratch, lane);
-                        if (lane == L) {
-                            cnt = p.kprime;
-                            thr = fmaxf(thr, t);
-                            atomicMax(my_gthr, mono32(t));
-                        }
-                    }
-                    ST_ADD(st_compact, tc0);
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c * 32, r);
-                    if (partial) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (row0 + c * 32 + i >= p.n_rows) r[i] = 0xff800000u;      // -inf: never passes
-                    }
-                    bool any = false;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) any |= __uint_as_float(r[i]) > thr;
-                    if (any) {
-                        ++st_nslow;
-                        const uint32_t rbase = (uint32_t)(row0 + c * 32);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (__uint_as_float(r[i]) > thr) {
-                                buf[cnt] = ((unsigned long long)r[i] << 32) | (unsigned long long)(rbase + i);
-                                ++cnt;
-                            }
-                        }
-                    }
-                }
+                if (p.sample) epi_sample_tile(taddr, T3_BN / 32, row0, p.n_rows, top);
+                else epi_filter_tile(taddr, T3_BN / 32, row0, p.n_rows, thr, cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane, ec);
                 // accumulator drained: hand it back to the leader's MMA warp
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tempty_leader + astage * 8);
                 if (++astage == 2) { astage = 0; aphase ^= 1; }
             }
-            // end of item: leave at most k' entries per query
-            unsigned need = __ballot_sync(0xffffffffu, cnt > p.kprime);
-            while (need) {
-                const int L = __ffs(need) - 1;
-                need &= need - 1;
-                unsigned long long* b = reinterpret_cast<unsigned long long*>(
-                    __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), L));
-                const int n = __shfl_sync(0xffffffffu, cnt, L);
-                const float t = warp_compact(b, n, p.kprime, p.cap, scratch, lane);
-                if (lane == L) {
-                    cnt = p.kprime;
-                    atomicMax(my_gthr, mono32(t));
-                }
+            if (p.sample) {
+                epi_sample_finish(top, buf);
+                cnt = TC_SAMPLE_R;
+            } else {
+                epi_filter_finish(cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane);
             }
             p.cand_cnt[slot] = cnt;
         }
         if (p.stats && warp == 2 && lane == 0) {
             p.stats[blockIdx.x * ST_N + ST_EPI_TOTAL] = clock64() - st_begin;
             p.stats[blockIdx.x * ST_N + ST_EPI_WAIT_TFULL] = st_wtfull;
-            p.stats[blockIdx.x * ST_N + ST_EPI_COMPACT] = st_compact;
-            p.stats[blockIdx.x * ST_N + ST_EPI_NCOMPACT] = st_ncompact;
-            p.stats[blockIdx.x * ST_N + ST_EPI_NSLOW] = st_nslow;
+            p.stats[blockIdx.x * ST_N + ST_EPI_COMPACT] = ec.compact;
+            p.stats[blockIdx.x * ST_N + ST_EPI_NCOMPACT] = ec.ncompact;
+            p.stats[blockIdx.x * ST_N + ST_EPI_NSLOW] = ec.nslow;
         }
     }
 

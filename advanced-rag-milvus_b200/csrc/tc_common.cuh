@@ -332,6 +332,116 @@ enum { ST_MMA_TOTAL = 0, ST_MMA_WAIT_FULL, ST_MMA_WAIT_TEMPTY, ST_MMA_WAIT_Q, ST
 #define ST_T0(var) long long var = clock64()
 #define ST_ADD(acc, var) acc += clock64() - var
 
+// ----------------------------------------------------------------------------------------------- epilogue building blocks
+// One accumulator (n_groups * 32 columns) of the FULL scan: a thread owns one query (TMEM lane), compares 32 scores at a
+// time against the query's running threshold and appends the rare survivors to its candidate buffer; when a buffer is
+// nearly full the warp compacts it to kp entries and raises the threshold.
+struct EpiCounters { long long compact = 0, ncompact = 0, nslow = 0; };
+
+__device__ __forceinline__ void epi_filter_tile(uint32_t taddr, int n_groups, int64_t row0, int64_t n_rows, float& thr, int& cnt,
+                                                unsigned long long* buf, unsigned int* my_gthr, int kp, int cap,
+                                                uint32_t scratch, int lane, EpiCounters& ec) {
+    const bool partial = row0 + n_groups * 32 > n_rows;
+#pragma unroll 1
+    for (int c = 0; c < n_groups; ++c) {
+        // make room: a lane appends at most 32 entries per column group
+        unsigned need = __ballot_sync(0xffffffffu, cnt > cap - 32);
+        if (need) {
+            ST_T0(tc0);
+            ec.ncompact += __popc(need);
+            while (need) {
+                const int L = __ffs(need) - 1;
+                need &= need - 1;
+                unsigned long long* b = reinterpret_cast<unsigned long long*>(
+                    __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), L));
+                const int n = __shfl_sync(0xffffffffu, cnt, L);
+                const float t = warp_compact(b, n, kp, cap, scratch, lane);
+                if (lane == L) {
+                    cnt = kp;
+                    thr = fmaxf(thr, t);
+                    atomicMax(my_gthr, mono32(t));
+                }
+            }
+            ST_ADD(ec.compact, tc0);
+        }
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        if (partial) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (row0 + c * 32 + i >= n_rows) r[i] = 0xff800000u;      // -inf: never passes
+        }
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) any |= __uint_as_float(r[i]) > thr;
+        if (any) {
+            ++ec.nslow;
+            const uint32_t rbase = (uint32_t)(row0 + c * 32);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (__uint_as_float(r[i]) > thr) {
+                    buf[cnt] = ((unsigned long long)r[i] << 32) | (unsigned long long)(rbase + i);
+                    ++cnt;
+                }
+            }
+        }
+    }
+}
+
+// End of a work item of the full scan: leave at most kp entries per query and publish the threshold.
+__device__ __forceinline__ void epi_filter_finish(int& cnt, unsigned long long* buf, unsigned int* my_gthr, int kp, int cap,
+                                                  uint32_t scratch, int lane) {
+    unsigned need = __ballot_sync(0xffffffffu, cnt > kp);
+    while (need) {
+        const int L = __ffs(need) - 1;
+        need &= need - 1;
+        unsigned long long* b = reinterpret_cast<unsigned long long*>(
+            __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), L));
+        const int n = __shfl_sync(0xffffffffu, cnt, L);
+        const float t = warp_compact(b, n, kp, cap, scratch, lane);
+        if (lane == L) {
+            cnt = kp;
+            atomicMax(my_gthr, mono32(t));
+        }
+    }
+}
+
+// SAMPLE pass: no buffers, no compaction.  Each thread keeps, in registers, the TC_SAMPLE_R greatest 32-row GROUP
+// MAXIMA it has seen, sorted descending.  The r-th greatest group maximum is a lower bound of the r-th greatest score
+// (r distinct rows reach it), and equals it unless two of the top r rows share a group -- so the threshold derived
+// from it is never too high because of the grouping, at worst a little low (a few more survivors in the full scan).
+constexpr int TC_SAMPLE_R = 16;
+
+__device__ __forceinline__ void epi_sample_tile(uint32_t taddr, int n_groups, int64_t row0, int64_t n_rows,
+                                                float (&top)[TC_SAMPLE_R]) {
+    const bool partial = row0 + n_groups * 32 > n_rows;
+#pragma unroll 1
+    for (int c = 0; c < n_groups; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        if (partial) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (row0 + c * 32 + i >= n_rows) r[i] = 0xff800000u;
+        }
+        float m = __uint_as_float(r[0]);
+#pragma unroll
+        for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+        if (m > top[TC_SAMPLE_R - 1]) {
+#pragma unroll
+            for (int i = 0; i < TC_SAMPLE_R; ++i) {
+                const float hi = fmaxf(top[i], m);
+                m = fminf(top[i], m);
+                top[i] = hi;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void epi_sample_finish(const float (&top)[TC_SAMPLE_R], unsigned long long* buf) {
+#pragma unroll
+    for (int i = 0; i < TC_SAMPLE_R; ++i) buf[i] = (unsigned long long)__float_as_uint(top[i]) << 32;
+}
+
 // Scan-kernel parameters shared by both kernels.
 struct ScanParams {
     int64_t n_rows;
@@ -345,6 +455,7 @@ struct ScanParams {
     int n_items;
     int kprime;
     int cap;             // candidate buffer capacity per (chunk, query)
+    int sample;          // 1 = strided SAMPLE pass: the epilogue keeps only the TC_SAMPLE_R best 32-row group maxima per query
     uint32_t idesc;
     unsigned long long* cand;   // [n_chunks][nqb][128][cap]  (score bits << 32 | local row)
     int* cand_cnt;              // [n_chunks][nqb][128]

@@ -1,0 +1,73 @@
+"""A/B the tensor-core scan generations in ONE process on one resident index, in steady state (power-capped clocks).
+
+For each (B200RAG_SCAN_VERSION, B200RAG_CLUSTER) setting: `reps` back-to-back searches; the b200rag_profile_next_scan hook
+times the FULL scan kernel alone, CUDA events time the whole search (prepare + sample pass + scan + finish), and the
+per-role cycle counters of the last scan give the effective SM clock (mma_total cycles / scan time).
+"""
+import argparse
+import ctypes
+import os
+import statistics
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "advanced-rag-milvus_b200")]
+from b200rag import _lib, engine  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rows", type=int, default=10_000_000)
+ap.add_argument("--dim", type=int, default=768)
+ap.add_argument("--batch", type=int, default=1024)
+ap.add_argument("--k", type=int, default=100)
+ap.add_argument("--dtype", default="f16")
+ap.add_argument("--reps", type=int, default=60)
+ap.add_argument("--configs", default="3:0,1:0,2:4,2:2,3:0")
+ap.add_argument("--mode", default="auto", choices=["auto", "tensor"])
+args = ap.parse_args()
+dev = "cuda:0"
+g = torch.Generator(device=dev).manual_seed(0)
+idx = engine.DenseIndex(args.dim, args.dtype, "COSINE", dev, capacity=args.rows)
+for s in range(0, args.rows, 250_000):
+    idx.add(torch.randn(min(250_000, args.rows - s), args.dim, generator=g, device=dev))
+qs = [torch.randn(args.batch, args.dim, generator=g, device=dev) for _ in range(8)]
+lib = _lib.load()
+mode = engine.DENSE_AUTO if args.mode == "auto" else engine.DENSE_TENSOR
+flops = 2.0 * args.batch * args.rows * args.dim
+print(f"{args.dtype} rows={args.rows} dim={args.dim} B={args.batch} k={args.k} reps={args.reps} mode={args.mode}")
+for cfg in args.configs.split(","):
+    ver, cs = cfg.split(":")
+    os.environ["B200RAG_SCAN_VERSION"] = ver
+    os.environ["B200RAG_CLUSTER"] = cs
+    for i in range(3):
+        idx.search(qs[i], args.k, mode)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.reps)]
+    tot = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.reps)]
+    for a, b in evs:
+        a.record(); b.record()
+    torch.cuda.synchronize()
+    flagged = 0
+    for it in range(args.reps):
+        if it == args.reps - 1:
+            lib.b200rag_debug_scan_stats(1, None, 0)
+        lib.b200rag_profile_next_scan(evs[it][0].cuda_event, evs[it][1].cuda_event)
+        tot[it][0].record()
+        s_, i_, f_ = idx.search(qs[it % 8], args.k, mode)
+        tot[it][1].record()
+    torch.cuda.synchronize()
+    flagged = int(f_.sum())
+    buf = np.zeros((256, 16), dtype=np.uint64)
+    lib.b200rag_debug_scan_stats(0, buf.ctypes.data_as(ctypes.c_void_p), 256)
+    used = buf[buf[:, 0] > 0].astype(np.float64)
+    scan = [a.elapsed_time(b) for a, b in evs][5:]
+    step = [a.elapsed_time(b) for a, b in tot][5:]
+    sm, st = statistics.median(scan), statistics.median(step)
+    last_scan = evs[-1][0].elapsed_time(evs[-1][1])
+    mma_total = used[:, 0].mean() if len(used) else float("nan")
+    mma_busy = 1.0 - (used[:, 1].mean() + used[:, 2].mean() + used[:, 3].mean()) / mma_total if len(used) else float("nan")
+    print(f"v{ver} cs={cs}: scan median {sm:6.2f} ms = {flops / sm / 1e9:5.0f} TFLOP/s (min {min(scan):.2f} max {max(scan):.2f}); "
+          f"search {st:6.2f} ms = {args.batch / st * 1e3:7.0f} QPS; clock ~{mma_total / last_scan / 1e6:.3f} GHz, "
+          f"MMA issue busy {100 * mma_busy:.0f}%, CTAs with MMA {len(used)}, flagged(last) {flagged}")
