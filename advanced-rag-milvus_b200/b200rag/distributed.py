@@ -44,9 +44,10 @@ def gather_and_merge(scores: torch.Tensor, ids: torch.Tensor, k: int,
     if world == 1:
         return scores, ids
     msg = pack_candidates(scores, ids)
-    out = torch.empty((world,) + tuple(msg.shape), dtype=msg.dtype, device=msg.device)
+    # concatenated (not stacked) output layout: the one form both NCCL and gloo accept
+    out = torch.empty((world * msg.shape[0], msg.shape[1]), dtype=msg.dtype, device=msg.device)
     dist.all_gather_into_tensor(out, msg, group=group)
-    cs, ci = unpack_gathered(out, k)
+    cs, ci = unpack_gathered(out.view(world, msg.shape[0], msg.shape[1]), k)
     return merge_fn(cs, ci, k)
 
 
