@@ -219,8 +219,17 @@ size_t scan3_smem_bytes(int cap) {
     return 1024 + (size_t)T3_STAGES * T3_STAGE_BYTES + (T3_N_BARS + 2) * 8 + (size_t)T3_EPI_WARPS * cap * 4 + 64;
 }
 
+int scan3_max_clusters_query(int cap, int sm_count);
 // Number of CTA pairs that can be co-resident (the kernel is persistent: every pair must be resident at once).
 int scan3_max_clusters(int cap, int sm_count) {
+    static int cached_cap = -1, cached_sm = -1, cached_val = 0;      // the occupancy query costs tens of microseconds per call
+    if (cap == cached_cap && sm_count == cached_sm) return cached_val;
+    const int val = scan3_max_clusters_query(cap, sm_count);
+    cached_cap = cap; cached_sm = sm_count; cached_val = val;
+    return val;
+}
+
+int scan3_max_clusters_query(int cap, int sm_count) {
     const size_t smem = scan3_smem_bytes(cap);
     if (cudaFuncSetAttribute(dense_scan3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
@@ -240,7 +249,7 @@ int scan3_max_clusters(int cap, int sm_count) {
 
 int launch_scan3(const void* corpus16, int dtype, const ScanParams& sp, int max_clusters, cudaStream_t st) {
     CUtensorMap map_q, map_x;
-    int rc = make_tensor_map(&map_q, sp.queries, sp.n_q, sp.dim, dtype, TC_BM);
+    int rc = make_tensor_map(&map_q, sp.queries, (int64_t)sp.nqb * TC_BM, sp.dim, dtype, TC_BM);   // whole blocks (padded by run_tensor)
     if (rc) return rc;
     rc = make_tensor_map(&map_x, corpus16, sp.n_rows, sp.dim, dtype, T3_HALF);
     if (rc) return rc;
