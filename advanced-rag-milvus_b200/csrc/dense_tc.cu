@@ -425,7 +425,7 @@ int scan3_max_clusters(int cap, int sm_count);
 int launch_scan3(const void* corpus16, int dtype, const ScanParams& sp, int max_clusters, cudaStream_t st);
 
 struct TensorPlan {
-    int sm_count, version, cs, tile_rows, nqb, n_tiles, n_chunks, n_items, kprime, cap, topk_cap, max_ctas;
+    int sm_count, version, cs, tile_rows, nqb, n_tiles, n_chunks, n_items, kprime, cap, topk_cap, max_ctas, qg_span;
     int sample, s_stride, s_tiles, s_chunks, s_items, s_kprime, s_cap, s_rank, s_topk_cap;   // strided sample pass
     size_t scan_smem, finish_smem;
     size_t off_cand, off_cnt, off_gthr, off_flaglist, off_nflag, off_stats, off_qpad, off_exact, total;
@@ -487,10 +487,19 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
         pl.scan_smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 6) * 8 + (size_t)TC_EPI_WARPS * pl.cap * 4;
     }
     pl.n_tiles = (int)((n_rows + pl.tile_rows - 1) / pl.tile_rows);
-    int want = units / gcd_int(qgroups, units);             // smallest chunk count with n_items % units == 0
-    pl.n_chunks = want < pl.n_tiles ? want : pl.n_tiles;
+    const int want = units / gcd_int(qgroups, units);       // smallest chunk count with n_items % units == 0 (span 1)
+    // v3 runs tile-major: one work item covers a span of query-block pairs for every tile of its chunk
+    pl.qg_span = 1;
+    if (pl.version == 3) {
+        pl.qg_span = qgroups < TC_QG_SPAN_MAX ? qgroups : TC_QG_SPAN_MAX;
+        int fs = env_int("B200RAG_QG_SPAN", 0);
+        if (fs >= 1 && fs <= TC_QG_SPAN_MAX) pl.qg_span = fs < qgroups ? fs : qgroups;
+    }
+    const int n_spans = (qgroups + pl.qg_span - 1) / pl.qg_span;
+    const int want_main = units / gcd_int(n_spans, units);
+    pl.n_chunks = want_main < pl.n_tiles ? want_main : pl.n_tiles;
     if (pl.n_chunks < 1) pl.n_chunks = 1;
-    pl.n_items = qgroups * pl.n_chunks;
+    pl.n_items = n_spans * pl.n_chunks;
     // strided SAMPLE pass that seeds the per-query thresholds: every s_stride-th tile is scored, the epilogue keeps the
     // TC_SAMPLE_R best 32-row group maxima per (chunk, query) in registers, and the s_rank-th best over all chunks becomes
     // the query's starting threshold.  About s_rank * s_stride rows of the whole corpus beat it; that product is held
@@ -608,6 +617,7 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
         };
         const bool prof = g_prof_start && g_prof_stop;
         sp.sample = 0;
+        sp.qg_span = 1;
         if (pl.sample) {
             // pass 0: every s_stride-th tile, tiny k'; its r-th best score per query seeds the thresholds
             ScanParams s0 = sp;
@@ -619,6 +629,7 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
             s0.kprime = pl.s_kprime;
             s0.cap = pl.s_cap;
             s0.sample = 1;
+            s0.qg_span = 1;
             int rc = launch(s0);
             if (rc) return rc;
             size_t tsm = BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.s_topk_cap) + 64;
@@ -632,6 +643,7 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
         sp.n_items = pl.n_items;
         sp.kprime = pl.kprime;
         sp.cap = pl.cap;
+        sp.qg_span = pl.qg_span;
         if (prof) B200_CUDA_CHECK(cudaEventRecord(g_prof_start, st));     // the hook brackets the FULL scan kernel only
         int rc = launch(sp);
         if (rc) return rc;

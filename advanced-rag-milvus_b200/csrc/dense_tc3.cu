@@ -8,7 +8,10 @@
 // Per CTA and k-block that is 16 KB + 16 KB instead of 16 KB + 32 KB for the same amount of math: one third less
 // L2->SM traffic and shared-memory fill, one third less operand fetch per MMA.
 //
-//   cluster = 2 CTAs (rank 0 = leader).  Work item = (chunk of consecutive corpus tiles, PAIR of query blocks).
+//   cluster = 2 CTAs (rank 0 = leader).  Work item = (chunk of consecutive corpus tiles, SPAN of query-block pairs).
+//   Tile-major order: for every corpus tile of its chunk the cluster runs ALL pairs of the span back to back, so the
+//   tile comes from HBM once and is re-served from L2 microseconds later for the other pairs (r1d profile: with one pair
+//   per item the 4 clusters sharing a chunk drifted apart and HBM saw the corpus 2.0 times).
 //   warp 0      TMA producer in BOTH CTAs: Q tile [128 x 64] of the CTA's own query block + X half tile [128 x 64]
 //               (rows tile*256 + rank*128 ...), 6-stage ring of 32 KB; every load credits its bytes to the LEADER's
 //               full barrier (cp.async.bulk.tensor ... .cta_group::2)
@@ -43,6 +46,8 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     uint64_t* tempty_bar = bars + 2 * T3_STAGES + 2;    // [2]       leader: 8 arrivals (epilogue warps of both CTAs)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + T3_N_BARS);
     uint32_t* scratch_all = reinterpret_cast<uint32_t*>(bars + T3_N_BARS + 2);   // [4][cap] (large-k compaction)
+    float* st_thr = reinterpret_cast<float*>(scratch_all + (size_t)T3_EPI_WARPS * p.cap);   // [qg_span][128] running thresholds
+    int* st_cnt = reinterpret_cast<int*>(st_thr + (size_t)p.qg_span * TC_BM);                // [qg_span][128] buffer fill
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -51,6 +56,7 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int cluster_id = blockIdx.x >> 1;
     const int n_clusters = gridDim.x >> 1;
     const int qgroups = p.nqb >> 1;                     // nqb is padded to an even number of query blocks
+    const int n_spans = (qgroups + p.qg_span - 1) / p.qg_span;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
@@ -78,21 +84,25 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             long long st_wait = 0;
             ST_T0(st_begin);
             for (int item = cluster_id; item < p.n_items; item += n_clusters) {
-                const int chunk = item / qgroups, qb = (item % qgroups) * 2 + rank;
+                const int chunk = item / n_spans, qg0 = (item % n_spans) * p.qg_span;
+                const int qg1 = min(qg0 + p.qg_span, qgroups);
                 const int t0 = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
                 const int t1 = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
                 for (int tile = t0; tile < t1; ++tile) {
                     const int xrow = tile * p.tile_stride * T3_BN + rank * T3_HALF;
-                    for (int kb = 0; kb < p.n_kblocks; ++kb) {
-                        ST_T0(tw);
-                        mbar_wait(&empty_bar[stage], phase ^ 1);          // the pair's MMAs have drained OUR copy of the slot
-                        ST_ADD(st_wait, tw);
-                        uint8_t* sq = stage_base + stage * T3_STAGE_BYTES;
-                        uint8_t* sx = sq + T3_Q_BYTES;
-                        if (leader) mbar_expect_tx(&full_bar[stage], 2 * T3_STAGE_BYTES);
-                        tma_load_2d_pair(sq, &map_q, kb * TC_BK, qb * TC_BM, full_leader + stage * 8);
-                        tma_load_2d_pair(sx, &map_x, kb * TC_BK, xrow, full_leader + stage * 8);
-                        if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
+                    for (int qg = qg0; qg < qg1; ++qg) {
+                        const int qrow = (qg * 2 + rank) * TC_BM;
+                        for (int kb = 0; kb < p.n_kblocks; ++kb) {
+                            ST_T0(tw);
+                            mbar_wait(&empty_bar[stage], phase ^ 1);      // the pair's MMAs have drained OUR copy of the slot
+                            ST_ADD(st_wait, tw);
+                            uint8_t* sq = stage_base + stage * T3_STAGE_BYTES;
+                            uint8_t* sx = sq + T3_Q_BYTES;
+                            if (leader) mbar_expect_tx(&full_bar[stage], 2 * T3_STAGE_BYTES);
+                            tma_load_2d_pair(sq, &map_q, kb * TC_BK, qrow, full_leader + stage * 8);
+                            tma_load_2d_pair(sx, &map_x, kb * TC_BK, xrow, full_leader + stage * 8);
+                            if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
+                        }
                     }
                 }
             }
@@ -109,10 +119,10 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             long long st_wfull = 0, st_wtempty = 0;
             ST_T0(st_begin);
             for (int item = cluster_id; item < p.n_items; item += n_clusters) {
-                const int chunk = item / qgroups;
-                const int t0 = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
-                const int t1 = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
-                for (int tile = t0; tile < t1; ++tile) {
+                const int chunk = item / n_spans, qg0 = (item % n_spans) * p.qg_span;
+                const int n_acc = (min(qg0 + p.qg_span, qgroups) - qg0) *
+                                  ((int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks) - (int)((int64_t)chunk * p.n_tiles / p.n_chunks));
+                for (int acc = 0; acc < n_acc; ++acc) {       // one accumulator per (tile, pair of query blocks)
                     ST_T0(te);
                     mbar_wait_cluster(&tempty_bar[astage], aphase ^ 1);   // both epilogues have drained this accumulator
                     ST_ADD(st_wtempty, te);
@@ -158,42 +168,75 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         EpiCounters ec;
         ST_T0(st_begin);
         for (int item = cluster_id; item < p.n_items; item += n_clusters) {
-            const int chunk = item / qgroups, qb = (item % qgroups) * 2 + rank;
+            const int chunk = item / n_spans, qg0 = (item % n_spans) * p.qg_span;
+            const int qg1 = min(qg0 + p.qg_span, qgroups);
             const int t0 = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
             const int t1 = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
-            const int q = qb * TC_BM + qlane;
-            const bool active = q < p.n_q;
-            const size_t slot = (size_t)(chunk * p.nqb + qb) * TC_BM + qlane;
-            unsigned long long* buf = p.cand + slot * p.cap;
-            unsigned int* my_gthr = p.gthr + q;       // gthr has nqb*128 entries, padded blocks included
-            float thr = active ? gthr_load(my_gthr) : CUDART_INF_F;
-            int cnt = 0;
-            float top[TC_SAMPLE_R];
-#pragma unroll
-            for (int i = 0; i < TC_SAMPLE_R; ++i) top[i] = -CUDART_INF_F;
-            for (int tile = t0; tile < t1; ++tile) {
-                if (!p.sample && active && ((tile - t0) & 3) == 3) thr = fmaxf(thr, gthr_load(my_gthr));
-                ST_T0(tt);
-                mbar_wait(&tfull_bar[astage], aphase);
-                ST_ADD(st_wtfull, tt);
-                tc_fence_after();
-                const int64_t row0 = (int64_t)tile * p.tile_stride * T3_BN;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)astage * T3_BN;
-                if (p.sample) epi_sample_tile(taddr, T3_BN / 32, row0, p.n_rows, top);
-                else epi_filter_tile(taddr, T3_BN / 32, row0, p.n_rows, thr, cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane, ec);
-                // accumulator drained: hand it back to the leader's MMA warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(tempty_leader + astage * 8);
-                if (++astage == 2) { astage = 0; aphase ^= 1; }
-            }
             if (p.sample) {
-                epi_sample_finish(top, buf);
-                cnt = TC_SAMPLE_R;
-            } else {
-                epi_filter_finish(cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane);
+                // ---- SAMPLE pass (qg_span == 1): best group maxima in registers
+                const int qb = qg0 * 2 + rank;
+                const size_t slot = (size_t)(chunk * p.nqb + qb) * TC_BM + qlane;
+                float top[TC_SAMPLE_R];
+#pragma unroll
+                for (int i = 0; i < TC_SAMPLE_R; ++i) top[i] = -CUDART_INF_F;
+                for (int tile = t0; tile < t1; ++tile) {
+                    ST_T0(tt);
+                    mbar_wait(&tfull_bar[astage], aphase);
+                    ST_ADD(st_wtfull, tt);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)astage * T3_BN;
+                    epi_sample_tile(taddr, T3_BN / 32, (int64_t)tile * p.tile_stride * T3_BN, p.n_rows, top);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty_leader + astage * 8);
+                    if (++astage == 2) { astage = 0; aphase ^= 1; }
+                }
+                epi_sample_finish(top, p.cand + slot * p.cap);
+                p.cand_cnt[slot] = TC_SAMPLE_R;
+                continue;
             }
-            p.cand_cnt[slot] = cnt;
+            // ---- FULL scan: per-query state of every pair of the span lives in shared memory (a thread only ever touches
+            //      its own slots, so no synchronisation is needed)
+            for (int qg = qg0; qg < qg1; ++qg) {
+                const int q = (qg * 2 + rank) * TC_BM + qlane;
+                // start from the best threshold any CTA has established for this query so far (valid lower bound of the
+                // global k'-th best score; -inf while nobody has k' candidates yet); padding lanes never pass
+                st_thr[(qg - qg0) * TC_BM + qlane] = q < p.n_q ? gthr_load(p.gthr + q) : CUDART_INF_F;
+                st_cnt[(qg - qg0) * TC_BM + qlane] = 0;
+            }
+            for (int tile = t0; tile < t1; ++tile) {
+                const int64_t row0 = (int64_t)tile * p.tile_stride * T3_BN;
+                for (int qg = qg0; qg < qg1; ++qg) {
+                    const int qb = qg * 2 + rank;
+                    const int q = qb * TC_BM + qlane;
+                    const int si = (qg - qg0) * TC_BM + qlane;
+                    unsigned long long* buf = p.cand + ((size_t)(chunk * p.nqb + qb) * TC_BM + qlane) * p.cap;
+                    unsigned int* my_gthr = p.gthr + q;       // gthr has nqb*128 entries, padded blocks included
+                    float thr = st_thr[si];
+                    int cnt = st_cnt[si];
+                    if (((tile - t0) & 7) == 7 && q < p.n_q) thr = fmaxf(thr, gthr_load(my_gthr));
+                    ST_T0(tt);
+                    mbar_wait(&tfull_bar[astage], aphase);
+                    ST_ADD(st_wtfull, tt);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)astage * T3_BN;
+                    epi_filter_tile(taddr, T3_BN / 32, row0, p.n_rows, thr, cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane, ec);
+                    // accumulator drained: hand it back to the leader's MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty_leader + astage * 8);
+                    if (++astage == 2) { astage = 0; aphase ^= 1; }
+                    st_thr[si] = thr;
+                    st_cnt[si] = cnt;
+                }
+            }
+            for (int qg = qg0; qg < qg1; ++qg) {
+                const int qb = qg * 2 + rank;
+                const size_t slot = (size_t)(chunk * p.nqb + qb) * TC_BM + qlane;
+                int cnt = st_cnt[(qg - qg0) * TC_BM + qlane];
+                epi_filter_finish(cnt, p.cand + slot * p.cap, p.gthr + qb * TC_BM + qlane, p.kprime, p.cap, scratch, lane);
+                p.cand_cnt[slot] = cnt;
+            }
         }
         if (p.stats && warp == 2 && lane == 0) {
             p.stats[blockIdx.x * ST_N + ST_EPI_TOTAL] = clock64() - st_begin;
@@ -215,8 +258,9 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 // ----------------------------------------------------------------------------------------------- host side
 int make_tensor_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int dtype, int box_rows);
 
-size_t scan3_smem_bytes(int cap) {
-    return 1024 + (size_t)T3_STAGES * T3_STAGE_BYTES + (T3_N_BARS + 2) * 8 + (size_t)T3_EPI_WARPS * cap * 4 + 64;
+size_t scan3_smem_bytes(int cap) {      // sized for the widest span so that occupancy does not depend on the batch
+    return 1024 + (size_t)T3_STAGES * T3_STAGE_BYTES + (T3_N_BARS + 2) * 8 + (size_t)T3_EPI_WARPS * cap * 4 +
+           (size_t)TC_QG_SPAN_MAX * TC_BM * 8 + 64;
 }
 
 int scan3_max_clusters_query(int cap, int sm_count);

@@ -20,6 +20,7 @@ constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_MAX_C = 1280;         // candidate-buffer capacity limit (compaction scratch in smem)
 constexpr int TC_FALLBACK_BATCH = 32;
+constexpr int TC_QG_SPAN_MAX = 16;     // v3 tile-major order: per-query epilogue state of up to 16 block pairs lives in shared memory
 
 __host__ __device__ inline int tc_kprime(int k) { int s = k / 4 > 28 ? k / 4 : 28; return (k + s + 31) / 32 * 32; }
 __host__ __device__ inline int tc_bufcap(int kp) { return 2 * kp; }
@@ -453,6 +454,7 @@ struct ScanParams {
     int nqb;             // query blocks (padded to a multiple of the cluster size in v2)
     int n_chunks;
     int n_items;
+    int qg_span;         // v3: query-block PAIRS one work item covers back to back for every corpus tile (1 = one pair per item)
     int kprime;
     int cap;             // candidate buffer capacity per (chunk, query)
     int sample;          // 1 = strided SAMPLE pass: the epilogue keeps only the TC_SAMPLE_R best 32-row group maxima per query

@@ -24,7 +24,7 @@ ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--k", type=int, default=100)
 ap.add_argument("--dtype", default="f16")
 ap.add_argument("--reps", type=int, default=60)
-ap.add_argument("--configs", default="3:0,1:0,2:4,2:2,3:0")
+ap.add_argument("--configs", default="3:0:0,3:0:1,3:0:2,1:0:0,3:0:0")
 ap.add_argument("--mode", default="auto", choices=["auto", "tensor"])
 args = ap.parse_args()
 dev = "cuda:0"
@@ -38,9 +38,10 @@ mode = engine.DENSE_AUTO if args.mode == "auto" else engine.DENSE_TENSOR
 flops = 2.0 * args.batch * args.rows * args.dim
 print(f"{args.dtype} rows={args.rows} dim={args.dim} B={args.batch} k={args.k} reps={args.reps} mode={args.mode}")
 for cfg in args.configs.split(","):
-    ver, cs = cfg.split(":")
+    ver, cs, span = (cfg.split(":") + ["0"])[:3]
     os.environ["B200RAG_SCAN_VERSION"] = ver
     os.environ["B200RAG_CLUSTER"] = cs
+    os.environ["B200RAG_QG_SPAN"] = span
     for i in range(3):
         idx.search(qs[i], args.k, mode)
     torch.cuda.synchronize()
@@ -68,6 +69,6 @@ for cfg in args.configs.split(","):
     last_scan = evs[-1][0].elapsed_time(evs[-1][1])
     mma_total = used[:, 0].mean() if len(used) else float("nan")
     mma_busy = 1.0 - (used[:, 1].mean() + used[:, 2].mean() + used[:, 3].mean()) / mma_total if len(used) else float("nan")
-    print(f"v{ver} cs={cs}: scan median {sm:6.2f} ms = {flops / sm / 1e9:5.0f} TFLOP/s (min {min(scan):.2f} max {max(scan):.2f}); "
+    print(f"v{ver} cs={cs} span={span}: scan median {sm:6.2f} ms = {flops / sm / 1e9:5.0f} TFLOP/s (min {min(scan):.2f} max {max(scan):.2f}); "
           f"search {st:6.2f} ms = {args.batch / st * 1e3:7.0f} QPS; clock ~{mma_total / last_scan / 1e6:.3f} GHz, "
           f"MMA issue busy {100 * mma_busy:.0f}%, CTAs with MMA {len(used)}, flagged(last) {flagged}")
