@@ -314,7 +314,10 @@ def main():
         if os.path.exists(tpath):
             try:
                 with open(tpath) as fh:
-                    traffic = json.load(fh).get("dram_bytes_per_launch")
+                    tj = json.load(fh)
+                # the ncu capture is of ONE workload; report it only for the same per-GPU shard and batch
+                if (tj.get("rows"), tj.get("dim"), tj.get("batch")) == (n_local, D, B):
+                    traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         scan_kernel = {"1": "dense_scan_kernel", "2": "dense_scan2_kernel"}.get(os.environ.get("B200RAG_SCAN_VERSION", ""),
