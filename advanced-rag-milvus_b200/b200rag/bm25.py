@@ -47,6 +47,27 @@ def bm25_weights(doc_ptr: np.ndarray, term_ids: np.ndarray, tf: np.ndarray, n_te
     return w.astype(np.float32)
 
 
+def bm25_weights_device(doc_ptr, term_ids, tf, n_terms: int, k1: float = K1, b: float = B):
+    """bm25_weights for CSR arrays that already live on a CUDA device (torch tensors): same fp64 operation order, so
+    the fp32 result is bit-identical to the numpy version (idf, the only transcendental, is evaluated on the host for
+    the n_terms vocabulary entries; +, *, / are correctly rounded on both sides)."""
+    import torch
+    dev = term_ids.device
+    n_docs = doc_ptr.numel() - 1
+    if term_ids.numel() == 0:
+        return torch.zeros(0, dtype=torch.float32, device=dev)
+    counts = (doc_ptr[1:] - doc_ptr[:-1]).to(dev)
+    doc_of = torch.repeat_interleave(torch.arange(n_docs, device=dev), counts, output_size=term_ids.numel())
+    tf64 = tf.to(torch.float64)
+    doc_len = torch.zeros(n_docs, dtype=torch.float64, device=dev).index_add_(0, doc_of, tf64)   # integers: exact in fp64
+    avgdl = float(doc_len.sum().item()) / n_docs
+    df = torch.bincount(term_ids, minlength=n_terms).cpu().numpy()
+    idf = torch.as_tensor(bm25_idf(n_docs, df)).to(dev)
+    norm = k1 * (1.0 - b + b * doc_len[doc_of] / avgdl)
+    w = idf[term_ids] * tf64 * (k1 + 1.0) / (tf64 + norm)
+    return w.to(torch.float32)
+
+
 def tokenize(text) -> List[str]:
     return (text or "").lower().split()
 

@@ -278,15 +278,18 @@ class SparseIndex:
             raise ValueError("SparseIndex lives on a CUDA device (b200rag has no CPU path)")
         if block_docs % 32 or not 0 < block_docs <= 65536:
             raise ValueError("block_docs must be a multiple of 32 in (0, 65536]")
-        doc_ptr = torch.as_tensor(np.asarray(doc_ptr, dtype=np.int64))
+        def _t(a, np_dtype, t_dtype):           # numpy / list / torch (any device) -> torch tensor of the wanted dtype
+            return a.to(t_dtype) if torch.is_tensor(a) else torch.as_tensor(np.asarray(a, dtype=np_dtype))
+
+        doc_ptr = _t(doc_ptr, np.int64, torch.int64).cpu()
         self.n_docs = int(doc_ptr.numel() - 1)
         self.n_terms = int(n_terms)
         self.block_docs = int(block_docs)
         self.id_offset = int(id_offset)
         self.n_blocks = max(1, -(-self.n_docs // block_docs))
         dev = self.device
-        t = torch.as_tensor(np.asarray(term_ids, dtype=np.int64)).to(dev)
-        w = torch.as_tensor(np.asarray(weights, dtype=np.float32)).to(dev)
+        t = _t(term_ids, np.int64, torch.int64).to(dev)
+        w = _t(weights, np.float32, torch.float32).to(dev)
         nnz = t.numel()
         counts = (doc_ptr[1:] - doc_ptr[:-1]).to(dev)
         d = torch.repeat_interleave(torch.arange(self.n_docs, device=dev, dtype=torch.int64), counts, output_size=nnz)

@@ -420,9 +420,9 @@ int scan2_tile_rows(int dim);
 size_t scan2_smem_bytes(int cap);
 int scan2_max_clusters(int dim, int cap, int cs, int sm_count);
 int launch_scan2(const void* corpus16, int dtype, const ScanParams& sp, int cs, int max_ctas, cudaStream_t st, int* grid_out);
-size_t scan3_smem_bytes(int cap);
-int scan3_max_clusters(int cap, int sm_count);
-int launch_scan3(const void* corpus16, int dtype, const ScanParams& sp, int max_clusters, cudaStream_t st);
+size_t scan3_smem_bytes(int cap, int span);
+int scan3_max_clusters(int cap, int span, int sm_count);
+int launch_scan3(const void* corpus16, int dtype, const ScanParams& sp, int max_clusters, int span_cap, int span_max, cudaStream_t st);
 
 struct TensorPlan {
     int sm_count, version, cs, tile_rows, nqb, n_tiles, n_chunks, n_items, kprime, cap, topk_cap, max_ctas, qg_span;
@@ -466,9 +466,14 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
         pl.cs = 2;
         qgroups = (pl.nqb + 1) / 2;
         pl.nqb = qgroups * 2;                               // candidate / threshold buffers cover the padded block too
-        units = scan3_max_clusters(pl.cap, pl.sm_count);
+        // tile-major span: as many query-block pairs per work item as fit next to the stage ring in shared memory
+        pl.qg_span = qgroups < TC_QG_SPAN_MAX ? qgroups : TC_QG_SPAN_MAX;
+        int fs = env_int("B200RAG_QG_SPAN", 0);
+        if (fs >= 1 && fs <= TC_QG_SPAN_MAX) pl.qg_span = fs < qgroups ? fs : qgroups;
+        while (pl.qg_span > 1 && scan3_smem_bytes(pl.cap, pl.qg_span) > TC_SMEM_LIMIT) --pl.qg_span;
+        units = scan3_max_clusters(pl.cap, pl.qg_span, pl.sm_count);
         pl.max_ctas = units * 2;
-        pl.scan_smem = scan3_smem_bytes(pl.cap);
+        pl.scan_smem = scan3_smem_bytes(pl.cap, pl.qg_span);
     } else if (pl.version == 2) {
         pl.tile_rows = scan2_tile_rows(dim);
         pl.cs = pl.nqb % 4 == 0 ? 4 : (pl.nqb % 2 == 0 ? 2 : 1);
@@ -489,12 +494,7 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     pl.n_tiles = (int)((n_rows + pl.tile_rows - 1) / pl.tile_rows);
     const int want = units / gcd_int(qgroups, units);       // smallest chunk count with n_items % units == 0 (span 1)
     // v3 runs tile-major: one work item covers a span of query-block pairs for every tile of its chunk
-    pl.qg_span = 1;
-    if (pl.version == 3) {
-        pl.qg_span = qgroups < TC_QG_SPAN_MAX ? qgroups : TC_QG_SPAN_MAX;
-        int fs = env_int("B200RAG_QG_SPAN", 0);
-        if (fs >= 1 && fs <= TC_QG_SPAN_MAX) pl.qg_span = fs < qgroups ? fs : qgroups;
-    }
+    if (pl.version != 3) pl.qg_span = 1;
     const int n_spans = (qgroups + pl.qg_span - 1) / pl.qg_span;
     const int want_main = units / gcd_int(n_spans, units);
     pl.n_chunks = want_main < pl.n_tiles ? want_main : pl.n_tiles;
@@ -555,7 +555,7 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
                int64_t id_offset, double* out_scores, int64_t* out_ids, int32_t* out_flags, double row_norm_bound,
                float* out_err, int with_fallback, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     TensorPlan pl = plan_tensor(n_rows, dim, n_q, k);
-    if (pl.cap > TC_MAX_C || n_rows >= ((int64_t)1 << 32) - TC_BN) {
+    if (pl.cap > TC_MAX_C || pl.scan_smem > TC_SMEM_LIMIT || n_rows >= ((int64_t)1 << 32) - TC_BN) {
         set_error("dense_topk(tensor): k=%d (k'=%d) or n_rows=%lld beyond the tensor-core path limits; use B200RAG_DENSE_EXACT",
                   k, pl.kprime, (long long)n_rows);
         return B200RAG_E_UNSUPPORTED;
@@ -608,7 +608,7 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
             B200_CUDA_CHECK(cudaFuncSetAttribute(dense_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.scan_smem));
         }
         auto launch = [&](const ScanParams& spx) -> int {
-            if (pl.version == 3) return launch_scan3(corpus16, dtype, spx, pl.max_ctas / 2, st);
+            if (pl.version == 3) return launch_scan3(corpus16, dtype, spx, pl.max_ctas / 2, pl.cap, pl.qg_span, st);
             if (pl.version == 2) return launch_scan2(corpus16, dtype, spx, pl.cs, pl.max_ctas, st, nullptr);
             int grid = spx.n_items < pl.sm_count ? spx.n_items : pl.sm_count;
             dense_scan_kernel<<<grid, TC_THREADS, pl.scan_smem, st>>>(map_q, map_x, spx); count_launch();

@@ -258,23 +258,23 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 // ----------------------------------------------------------------------------------------------- host side
 int make_tensor_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int dtype, int box_rows);
 
-size_t scan3_smem_bytes(int cap) {      // sized for the widest span so that occupancy does not depend on the batch
+size_t scan3_smem_bytes(int cap, int span) {
     return 1024 + (size_t)T3_STAGES * T3_STAGE_BYTES + (T3_N_BARS + 2) * 8 + (size_t)T3_EPI_WARPS * cap * 4 +
-           (size_t)TC_QG_SPAN_MAX * TC_BM * 8 + 64;
+           (size_t)span * TC_BM * 8 + 64;
 }
 
-int scan3_max_clusters_query(int cap, int sm_count);
+int scan3_max_clusters_query(int cap, int span, int sm_count);
 // Number of CTA pairs that can be co-resident (the kernel is persistent: every pair must be resident at once).
-int scan3_max_clusters(int cap, int sm_count) {
-    static int cached_cap = -1, cached_sm = -1, cached_val = 0;      // the occupancy query costs tens of microseconds per call
-    if (cap == cached_cap && sm_count == cached_sm) return cached_val;
-    const int val = scan3_max_clusters_query(cap, sm_count);
-    cached_cap = cap; cached_sm = sm_count; cached_val = val;
+int scan3_max_clusters(int cap, int span, int sm_count) {
+    static int cached_cap = -1, cached_span = -1, cached_sm = -1, cached_val = 0;      // the occupancy query costs tens of microseconds per call
+    if (cap == cached_cap && span == cached_span && sm_count == cached_sm) return cached_val;
+    const int val = scan3_max_clusters_query(cap, span, sm_count);
+    cached_cap = cap; cached_span = span; cached_sm = sm_count; cached_val = val;
     return val;
 }
 
-int scan3_max_clusters_query(int cap, int sm_count) {
-    const size_t smem = scan3_smem_bytes(cap);
+int scan3_max_clusters_query(int cap, int span, int sm_count) {
+    const size_t smem = scan3_smem_bytes(cap, span);
     if (cudaFuncSetAttribute(dense_scan3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return sm_count / 2;
@@ -291,13 +291,15 @@ int scan3_max_clusters_query(int cap, int sm_count) {
     return max_active < sm_count / 2 ? max_active : sm_count / 2;
 }
 
-int launch_scan3(const void* corpus16, int dtype, const ScanParams& sp, int max_clusters, cudaStream_t st) {
+int launch_scan3(const void* corpus16, int dtype, const ScanParams& sp, int max_clusters, int span_cap, int span_max, cudaStream_t st) {
+    // span_cap / span_max: the FULL scan's buffer capacity and span, so that the sample pass is launched with the same
+    // shared-memory size (and therefore the same co-residency) as the full scan
     CUtensorMap map_q, map_x;
     int rc = make_tensor_map(&map_q, sp.queries, (int64_t)sp.nqb * TC_BM, sp.dim, dtype, TC_BM);   // whole blocks (padded by run_tensor)
     if (rc) return rc;
     rc = make_tensor_map(&map_x, corpus16, sp.n_rows, sp.dim, dtype, T3_HALF);
     if (rc) return rc;
-    const size_t smem = scan3_smem_bytes(sp.cap);
+    const size_t smem = scan3_smem_bytes(sp.cap > span_cap ? sp.cap : span_cap, span_max);
     B200_CUDA_CHECK(cudaFuncSetAttribute(dense_scan3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int n_clusters = sp.n_items < max_clusters ? sp.n_items : max_clusters;
     if (n_clusters < 1) n_clusters = 1;

@@ -7,29 +7,44 @@
 // kept incrementally (max is order independent), turning the reference's O(k^2 n) set rebuilds into O(k n)
 // intersections.
 //
-// One CTA per query.  Token sets are rows of a CSR (sorted unique token ids per document).  Per pick: the picked
-// document's tokens are raised in a shared-memory bitset over the vocabulary, every thread intersects its
-// candidates against the bitset, the bitset is cleared again.
+// One CTA per query, up to 1024 threads.  Token sets are rows of a CSR (sorted unique token ids per document).  Per pick:
+//   1. argmax over the alive candidates (thread-strided, warp shuffle + one cross-warp step; "earliest wins" on ties)
+//   2. the picked document's tokens are raised in a shared-memory bitset over the vocabulary
+//   3. every WARP intersects whole candidates against the bitset: the 32 lanes read 32 consecutive tokens of the
+//      candidate's list (one coalesced 128-byte load), probe the bitset, and the counts are summed with one warp
+//      reduction.  (Round 1 had one THREAD per candidate walking its list token by token: 26.7 ms for 256 queries x 1000
+//      candidates x 100 picks; this form: see profiles/r1_hybrid_c4.md.)
+//   4. the bitset is cleared again (only the picked document's words).
+// Work = picks x candidates x tokens per candidate bitset probes; the shared-memory bank conflicts of the random probes
+// (~3.5 wavefronts per 32 probes) are the bound.
 #include "common.cuh"
 
 namespace b200rag {
 
-constexpr int MMR_THREADS = 256;
+constexpr int MMR_MAX_THREADS = 1024;
+constexpr unsigned FULL = 0xffffffffu;
 
-__global__ void __launch_bounds__(MMR_THREADS)
+__device__ __forceinline__ bool mmr_better(double ob, int oi, double b, int bi) {
+    return oi != 0x7fffffff && (bi == 0x7fffffff || ob > b || (ob == b && oi < bi));
+}
+
+__global__ void __launch_bounds__(MMR_MAX_THREADS)
 mmr_select_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict__ cand_rel, const int32_t* __restrict__ cand_n,
                   int n_max, const int64_t* __restrict__ doc_tok_ptr, const int32_t* __restrict__ doc_tok_ids, int vocab_words,
                   const double* __restrict__ lambda, const int32_t* __restrict__ k_sel, int k_max,
                   int32_t* __restrict__ out_pick, int32_t* __restrict__ out_n) {
     extern __shared__ __align__(16) char smem[];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     const int q = blockIdx.x;
     double* rel = reinterpret_cast<double*>(smem);                 // [n_max]
     double* max_sim = rel + n_max;                                 // [n_max]
-    int* alive = reinterpret_cast<int*>(max_sim + n_max);          // [n_max]
+    int64_t* tok_begin = reinterpret_cast<int64_t*>(max_sim + n_max);   // [n_max] start of the candidate's token list
+    int* tok_len = reinterpret_cast<int*>(tok_begin + n_max);      // [n_max]
+    int* alive = tok_len + n_max;                                  // [n_max]
     uint32_t* bits = reinterpret_cast<uint32_t*>(alive + n_max);   // [vocab_words]
-    __shared__ double s_best[MMR_THREADS / 32];
-    __shared__ int s_best_idx[MMR_THREADS / 32];
+    __shared__ double s_best[MMR_MAX_THREADS / 32];
+    __shared__ int s_best_idx[MMR_MAX_THREADS / 32];
     __shared__ int s_pick;
     __shared__ int s_done;
 
@@ -38,82 +53,90 @@ mmr_select_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict
     const double lam = lambda[q];
     const double one_minus = __dsub_rn(1.0, lam);
     const int32_t* docs = cand_doc + (size_t)q * n_max;
-    for (int i = tid; i < n; i += MMR_THREADS) {
+    for (int i = tid; i < n; i += nthreads) {
         rel[i] = cand_rel[(size_t)q * n_max + i];
         max_sim[i] = 0.0;
         alive[i] = 1;
+        const int64_t b0 = doc_tok_ptr[docs[i]];
+        tok_begin[i] = b0;
+        tok_len[i] = (int)(doc_tok_ptr[docs[i] + 1] - b0);
     }
-    for (int i = tid; i < vocab_words; i += MMR_THREADS) bits[i] = 0u;
+    for (int i = tid; i < vocab_words; i += nthreads) bits[i] = 0u;
     if (tid == 0) s_done = 0;
     __syncthreads();
 
     for (int step = 0; step < k; ++step) {
-        // ---- argmax with "earliest wins" --------------------------------------------------------
+        // ---- 1. argmax with "earliest wins" -------------------------------------------------------
         double best = -1e9;
         int best_i = 0x7fffffff;
-        for (int c = tid; c < n; c += MMR_THREADS) {
+        for (int c = tid; c < n; c += nthreads) {
             if (!alive[c]) continue;
             double s = step == 0 ? rel[c] : __dsub_rn(__dmul_rn(lam, rel[c]), __dmul_rn(one_minus, max_sim[c]));
             if (s > best) { best = s; best_i = c; }   // per-thread candidates come in increasing c
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
-            double ob = __shfl_down_sync(0xffffffffu, best, off);
-            int oi = __shfl_down_sync(0xffffffffu, best_i, off);
-            if (oi != 0x7fffffff && (best_i == 0x7fffffff || ob > best || (ob == best && oi < best_i))) { best = ob; best_i = oi; }
+            double ob = __shfl_down_sync(FULL, best, off);
+            int oi = __shfl_down_sync(FULL, best_i, off);
+            if (mmr_better(ob, oi, best, best_i)) { best = ob; best_i = oi; }
         }
-        if ((tid & 31) == 0) { s_best[tid >> 5] = best; s_best_idx[tid >> 5] = best_i; }
+        if (lane == 0) { s_best[warp] = best; s_best_idx[warp] = best_i; }
         __syncthreads();
-        if (tid == 0) {
-            double b = s_best[0];
-            int bi = s_best_idx[0];
-            for (int w = 1; w < MMR_THREADS / 32; ++w) {
-                double ob = s_best[w];
-                int oi = s_best_idx[w];
-                if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > b || (ob == b && oi < bi))) { b = ob; bi = oi; }
+        if (warp == 0) {
+            double b = lane < nwarps ? s_best[lane] : -1e9;
+            int bi = lane < nwarps ? s_best_idx[lane] : 0x7fffffff;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                double ob = __shfl_down_sync(FULL, b, off);
+                int oi = __shfl_down_sync(FULL, bi, off);
+                if (mmr_better(ob, oi, b, bi)) { b = ob; bi = oi; }
             }
-            s_pick = bi;
-            if (bi != 0x7fffffff) {
-                out_pick[(size_t)q * k_max + step] = bi;
-                alive[bi] = 0;
-                s_done = step + 1;
+            if (lane == 0) {
+                s_pick = bi;
+                if (bi != 0x7fffffff) {
+                    out_pick[(size_t)q * k_max + step] = bi;
+                    alive[bi] = 0;
+                    s_done = step + 1;
+                }
             }
         }
         __syncthreads();
         const int pick = s_pick;
         if (pick == 0x7fffffff) break;           // nothing beat -1e9 (the reference would fail here too)
         if (step + 1 == k) break;
-        // ---- raise the picked document's tokens, intersect, clear --------------------------------
-        const int64_t ps = doc_tok_ptr[docs[pick]], pe = doc_tok_ptr[docs[pick] + 1];
-        const int len_p = (int)(pe - ps);
-        for (int64_t i = ps + tid; i < pe; i += MMR_THREADS) {
-            int t = doc_tok_ids[i];
+        // ---- 2. raise the picked document's tokens -------------------------------------------------
+        const int64_t ps = tok_begin[pick];
+        const int len_p = tok_len[pick];
+        for (int i = tid; i < len_p; i += nthreads) {
+            int t = doc_tok_ids[ps + i];
             atomicOr(&bits[t >> 5], 1u << (t & 31));
         }
         __syncthreads();
-        for (int c = tid; c < n; c += MMR_THREADS) {
-            if (!alive[c]) continue;
-            const int64_t cs = doc_tok_ptr[docs[c]], ce = doc_tok_ptr[docs[c] + 1];
+        // ---- 3. warp per candidate: |tokens(c) & tokens(pick)| -------------------------------------
+        for (int c = warp; c < n; c += nwarps) {
+            if (!alive[c]) continue;              // warp-uniform
+            const int32_t* toks = doc_tok_ids + tok_begin[c];
+            const int len_c = tok_len[c];
             int inter = 0;
-            for (int64_t i = cs; i < ce; ++i) {
-                int t = __ldg(doc_tok_ids + i);
+            for (int i = lane; i < len_c; i += 32) {
+                const int t = __ldg(toks + i);
                 inter += (bits[t >> 5] >> (t & 31)) & 1u;
             }
-            int uni = (int)(ce - cs) + len_p - inter;
-            double j = __ddiv_rn((double)inter, (double)(uni ? uni : 1));
-            if (j > max_sim[c]) max_sim[c] = j;
+            inter = __reduce_add_sync(FULL, inter);
+            if (lane == 0) {
+                const int uni = len_c + len_p - inter;
+                const double j = __ddiv_rn((double)inter, (double)(uni ? uni : 1));
+                if (j > max_sim[c]) max_sim[c] = j;
+            }
         }
         __syncthreads();
-        for (int64_t i = ps + tid; i < pe; i += MMR_THREADS) {
-            int t = doc_tok_ids[i];
-            bits[t >> 5] = 0u;
-        }
-        __syncthreads();
+        // ---- 4. clear (the next raise happens two barriers later) ----------------------------------
+        for (int i = tid; i < len_p; i += nthreads) bits[doc_tok_ids[ps + i] >> 5] = 0u;
     }
     __syncthreads();
     const int done = s_done;
     if (tid == 0) out_n[q] = done;
-    for (int i = done + tid; i < k_max; i += MMR_THREADS) out_pick[(size_t)q * k_max + i] = -1;
+    for (int i = done + tid; i < k_max; i += nthreads) out_pick[(size_t)q * k_max + i] = -1;
 }
 
 }  // namespace b200rag
@@ -134,14 +157,16 @@ int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const in
     B200_REQUIRE(n_queries >= 0 && n_max >= 1 && vocab_size >= 1 && k_max >= 1, "mmr_select: bad sizes");
     if (n_queries == 0) return B200RAG_OK;
     int vocab_words = (vocab_size + 31) / 32;
-    size_t smem = (size_t)n_max * (8 + 8 + 4) + (size_t)vocab_words * 4 + 64;
+    size_t smem = (size_t)n_max * (8 + 8 + 8 + 4 + 4) + (size_t)vocab_words * 4 + 64;
     if (smem > 225 * 1024) {
         set_error("mmr_select: n_max=%d vocab=%d needs %zu bytes of shared memory", n_max, vocab_size, smem);
         return B200RAG_E_UNSUPPORTED;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     B200_CUDA_CHECK(cudaFuncSetAttribute(mmr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mmr_select_kernel<<<n_queries, MMR_THREADS, smem, st>>>(cand_doc, cand_rel, cand_n, n_max, doc_tok_ptr, doc_tok_ids,
+    // one warp per candidate in the intersection phase: as many warps as there are candidates, up to 32
+    const int threads = n_max >= 32 ? MMR_MAX_THREADS : (n_max >= 8 ? 256 : 128);
+    mmr_select_kernel<<<n_queries, threads, smem, st>>>(cand_doc, cand_rel, cand_n, n_max, doc_tok_ptr, doc_tok_ids,
                                                            vocab_words, lambda, k_sel, k_max, out_pick, out_n); count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;

@@ -95,6 +95,10 @@ struct BlockTopK {
             }
         }
     }
+    // Would offer() accept this key?  (Lets callers skip losers before spending one of their `reserve` offers.)
+    __device__ __forceinline__ bool passes(uint64_t h, LoT l) const {
+        return !st->has_thr || key_gt<LoT>(h, l, st->thr_hi, (LoT)st->thr_lo);
+    }
     // Barrier + (when the next round could overflow) compaction.  All threads must call.  Ends synchronised.
     __device__ __forceinline__ void settle() {
         __syncthreads();

@@ -1,14 +1,20 @@
 // sparse_bm25.cu -- sparse inner-product (BM25-weighted) top-k over doc-range-blocked postings  (K3).
 //
-// One CTA owns one (query, document block) pair.  The block's per-document accumulators live in shared memory
-// (fp32, block_docs <= 65536 -> <= 256 KB is too much, so block_docs is capped by the shared memory left after the
-// selection buffers; the index builder uses 32768 by default = 128 KB).  Query terms are processed in ascending
-// term id with a barrier between terms, so every document's accumulator sees  acc = fmaf(qv, w, acc)  in the
-// canonical order (bit-identical to oracle/exact_scan.c:orc_sparse_topk).  Within one term the postings touch
-// distinct documents, so no atomics are needed on the accumulators; postings are read with coalesced loads
-// (u16 doc + f32 weight, 6 bytes per posting = the algorithmic HBM traffic).  A touched-bitmap marks candidate
-// documents; the final pass streams the touched documents into the block-level top-k (select.cuh) and writes a
-// sorted partial list per (query, block); merge_topk_kernel reduces the blocks.
+// One CTA (1024 threads) owns one QUERY and walks the document blocks of its slice one after the other:
+//   * the block's per-document accumulators live in shared memory (fp32, block_docs <= 32768 -> 128 KB) and are zeroed
+//     once per CTA; collecting a block's candidates puts them back to zero;
+//   * the postings of up to 8 query terms inside the block are fetched TOGETHER (one coalesced u16 doc + f32 weight per
+//     thread and term, a single exposed memory latency per block instead of one per term) and then applied in ascending
+//     term id with a barrier between terms, so every document sees  acc = fmaf(qv, w, acc)  in the canonical order
+//     (bit-identical to oracle/exact_scan.c:orc_sparse_topk).  Postings of one term hit distinct documents: no atomics
+//     on the accumulators; a touched-bitmap marks the candidates;
+//   * candidates are collected from the bitmap (a thread owns one or two 32-document words), losers against the running
+//     k-th best are dropped on the spot, survivors go to the block-level streaming top-k (select.cuh), which lives for
+//     the whole walk, so later blocks are filtered by the threshold earlier blocks established.
+// Algorithmic HBM traffic = 6 bytes per posting of the query's terms.  grid = (queries, slices): with fewer queries
+// than SMs the blocks are split into slices; merge_topk_kernel reduces the slices.
+// (Round 1 first ran one CTA per (query, block) that re-scanned all 32768 documents of the block: 4.1 ms for 256
+// queries over 1M documents = 0.8 % of the HBM roofline; see profiles/r1_hybrid_c4.md for this version.)
 #include "common.cuh"
 #include "select.cuh"
 
@@ -17,70 +23,108 @@ namespace b200rag {
 int launch_merge(const double* cand_scores, const int64_t* cand_ids, int n_launch, const int32_t* q_list, int n_cand, int k,
                  double* out_scores_f64, float* out_scores_f32, int64_t* out_ids, int32_t* out_counts, cudaStream_t st);
 
-constexpr int SP_THREADS = 256;
-constexpr int SP_ITEMS = 4;   // documents examined per thread between two settle() calls
+constexpr int SP_THREADS = 1024;
+constexpr int SP_TG = 8;       // query terms fetched together (one register pair per term and thread)
 
-__global__ void __launch_bounds__(SP_THREADS)
-sparse_block_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __restrict__ post_doc,
-                    const float* __restrict__ post_w, int64_t n_docs, int n_terms, int block_docs, int n_blocks,
+__global__ void __launch_bounds__(SP_THREADS, 1)
+sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __restrict__ post_doc,
+                    const float* __restrict__ post_w, int64_t n_docs, int n_terms, int block_docs, int n_blocks, int n_slices,
                     const int64_t* __restrict__ q_ptr, const int32_t* __restrict__ q_terms, const float* __restrict__ q_vals,
                     int k, int cap, int64_t id_offset, double* __restrict__ part_scores, int64_t* __restrict__ part_ids) {
     extern __shared__ __align__(16) char smem[];
     const int tid = threadIdx.x;
-    const int blk = blockIdx.x;
-    const int q = blockIdx.y;
-    const int64_t doc0 = (int64_t)blk * block_docs;
-    const int docs_here = (int)min((int64_t)block_docs, n_docs - doc0);
-
-    float* acc = reinterpret_cast<float*>(smem);                                   // [block_docs]
-    uint32_t* touched = reinterpret_cast<uint32_t*>(smem + (size_t)block_docs * 4);  // [block_docs/32]
-    const int n_words = (block_docs + 31) / 32;
+    const int q = blockIdx.x;
+    const int slice = blockIdx.y;
+    const int n_words = block_docs / 32;                                            // <= 2048
+    float* acc = reinterpret_cast<float*>(smem);                                    // [block_docs]
+    uint32_t* touched = reinterpret_cast<uint32_t*>(smem + (size_t)block_docs * 4);  // [n_words]
     char* p = smem + (size_t)block_docs * 4 + (size_t)n_words * 4;
     p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
+    __shared__ long long s_beg[SP_TG], s_end[SP_TG];
+    __shared__ float s_qv[SP_TG];
     BlockTopK<SP_THREADS, uint32_t> tk;
-    tk.attach(p, cap, k, SP_THREADS * SP_ITEMS, /*start_digit=*/BlockTopK<SP_THREADS, uint32_t>::NLO + 3);
+    tk.attach(p, cap, k, SP_THREADS, /*start_digit=*/BlockTopK<SP_THREADS, uint32_t>::NLO + 3);
     tk.init();
     for (int i = tid; i < block_docs; i += SP_THREADS) acc[i] = 0.0f;
     for (int i = tid; i < n_words; i += SP_THREADS) touched[i] = 0u;
     __syncthreads();
 
-    const int64_t* tp = blk_term_ptr + (size_t)blk * (n_terms + 1);
-    const int64_t qs = q_ptr[q], qe = q_ptr[q + 1];
-    for (int64_t j = qs; j < qe; ++j) {
-        const int t = q_terms[j];
-        if (t < 0 || t >= n_terms) continue;          // uniform across the block
-        const float qv = q_vals[j];
-        const int64_t s = tp[t], e = tp[t + 1];
-        for (int64_t i = s + tid; i < e; i += SP_THREADS) {
-            const int d = post_doc[i];
-            const float w = post_w[i];
-            acc[d] = fmaf(qv, w, acc[d]);
-            atomicOr(&touched[d >> 5], 1u << (d & 31));
-        }
-        __syncthreads();
-    }
-
-    // stream touched documents into the top-k
-    for (int base = 0; base < n_words * 32; base += SP_THREADS * SP_ITEMS) {
+    const int64_t qs = q_ptr[q];
+    const int nq = (int)(q_ptr[q + 1] - qs);
+    const int b0 = (int)((int64_t)slice * n_blocks / n_slices), b1 = (int)((int64_t)(slice + 1) * n_blocks / n_slices);
+    for (int blk = b0; blk < b1; ++blk) {
+        const int64_t doc0 = (int64_t)blk * block_docs;
+        const int64_t* tp = blk_term_ptr + (size_t)blk * (n_terms + 1);
+        // ---- accumulate, SP_TG terms at a time ---------------------------------------------------------------
+        for (int g0 = 0; g0 < nq; g0 += SP_TG) {
+            if (tid < SP_TG) {
+                long long s = 0, e = 0;
+                float qv = 0.f;
+                if (g0 + tid < nq) {
+                    const int t = q_terms[qs + g0 + tid];
+                    if (t >= 0 && t < n_terms) { s = tp[t]; e = tp[t + 1]; qv = q_vals[qs + g0 + tid]; }
+                }
+                s_beg[tid] = s; s_end[tid] = e; s_qv[tid] = qv;
+            }
+            __syncthreads();
+            int dreg[SP_TG];
+            float wreg[SP_TG];
 #pragma unroll
-        for (int it = 0; it < SP_ITEMS; ++it) {
-            const int d = base + it * SP_THREADS + tid;
-            bool valid = d < docs_here && ((touched[d >> 5] >> (d & 31)) & 1u);
-            tk.offer(valid, valid ? (uint64_t)mono32(acc[d]) : 0, ~(uint32_t)d);
+            for (int j = 0; j < SP_TG; ++j) {
+                const long long i = s_beg[j] + tid;
+                dreg[j] = -1;
+                wreg[j] = 0.f;
+                if (i < s_end[j]) { dreg[j] = post_doc[i]; wreg[j] = post_w[i]; }
+            }
+#pragma unroll
+            for (int j = 0; j < SP_TG; ++j) {
+                const float qv = s_qv[j];
+                if (dreg[j] >= 0) {
+                    const int d = dreg[j];
+                    acc[d] = fmaf(qv, wreg[j], acc[d]);
+                    atomicOr(&touched[d >> 5], 1u << (d & 31));
+                }
+                for (long long i = s_beg[j] + tid + SP_THREADS; i < s_end[j]; i += SP_THREADS) {     // long posting lists
+                    const int d = post_doc[i];
+                    acc[d] = fmaf(qv, post_w[i], acc[d]);
+                    atomicOr(&touched[d >> 5], 1u << (d & 31));
+                }
+                __syncthreads();
+            }
         }
-        tk.settle();
+        // ---- collect: a thread owns words tid and tid + 1024 of the bitmap ---------------------------------------
+        unsigned long long m = 0;
+        if (tid < n_words) { m = touched[tid]; touched[tid] = 0u; }
+        if (tid + SP_THREADS < n_words) { m |= (unsigned long long)touched[tid + SP_THREADS] << 32; touched[tid + SP_THREADS] = 0u; }
+        while (__syncthreads_or(m != 0ull)) {
+            bool have = false;
+            uint64_t h = 0;
+            uint32_t l = 0;
+            while (m) {
+                const int bpos = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const int d = bpos < 32 ? tid * 32 + bpos : (tid + SP_THREADS) * 32 + (bpos - 32);
+                const float sc = acc[d];
+                acc[d] = 0.0f;
+                h = (uint64_t)mono32(sc);
+                l = ~(uint32_t)(doc0 + d);
+                if (tk.passes(h, l)) { have = true; break; }
+            }
+            tk.offer(have, h, l);
+            tk.settle();
+        }
     }
     __syncthreads();
     tk.finalize();
     const int n = tk.count();
     const uint64_t* oh = tk.out_hi();
     const uint32_t* ol = tk.out_lo();
-    double* ps = part_scores + ((size_t)q * n_blocks + blk) * k;
-    int64_t* pi = part_ids + ((size_t)q * n_blocks + blk) * k;
+    double* ps = part_scores + ((size_t)q * n_slices + slice) * k;
+    int64_t* pi = part_ids + ((size_t)q * n_slices + slice) * k;
     for (int i = tid; i < k; i += SP_THREADS) {
         if (i < n) {
             ps[i] = (double)unmono32((uint32_t)oh[i]);
-            pi[i] = id_offset + doc0 + (int64_t)(~ol[i]);
+            pi[i] = id_offset + (int64_t)(~ol[i]);
         } else {
             ps[i] = -CUDART_INF;
             pi[i] = -1;
@@ -89,7 +133,7 @@ sparse_block_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
 }
 
 static size_t sparse_smem(int block_docs, int k, int* cap_out) {
-    int cap = BlockTopK<SP_THREADS, uint32_t>::capacity_for(k, SP_THREADS * SP_ITEMS);
+    int cap = BlockTopK<SP_THREADS, uint32_t>::capacity_for(k, SP_THREADS);
     if (cap_out) *cap_out = cap;
     return (size_t)block_docs * 4 + (size_t)((block_docs + 31) / 32) * 4 + 16 +
            BlockTopK<SP_THREADS, uint32_t>::smem_bytes(cap) + 64;
@@ -130,7 +174,7 @@ int b200rag_sparse_topk(const int64_t* blk_term_ptr, const uint16_t* post_doc, c
     }
     int64_t n_blocks = (n_docs + block_docs - 1) / block_docs;
     if (n_blocks < 1) n_blocks = 1;
-    B200_REQUIRE(n_blocks <= 65535 * 32, "sparse_topk: too many blocks");
+    B200_REQUIRE(n_queries <= 2147483647 && n_blocks <= 2147483647, "sparse_topk: too many blocks");
     Workspace ws(workspace, workspace_bytes);
     double* part_scores = ws.take<double>((size_t)n_queries * n_blocks * k);
     int64_t* part_ids = ws.take<int64_t>((size_t)n_queries * n_blocks * k);
@@ -138,13 +182,20 @@ int b200rag_sparse_topk(const int64_t* blk_term_ptr, const uint16_t* post_doc, c
         set_error("sparse_topk: workspace too small (%zu < %zu)", workspace_bytes, ws.off);
         return B200RAG_E_WORKSPACE;
     }
-    B200_CUDA_CHECK(cudaFuncSetAttribute(sparse_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)n_blocks, (unsigned)n_queries);
-    sparse_block_kernel<<<grid, SP_THREADS, smem, st>>>(blk_term_ptr, post_doc, post_w, n_docs, n_terms, block_docs,
-                                                       (int)n_blocks, q_ptr, q_terms, q_vals, k, cap, id_offset,
+    B200_CUDA_CHECK(cudaFuncSetAttribute(sparse_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // one CTA per query; with fewer queries than ~2 per SM the blocks are cut into slices to fill the machine
+    int sm_count = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    int64_t n_slices = (2 * (int64_t)sm_count) / n_queries;
+    if (n_slices < 1) n_slices = 1;
+    if (n_slices > n_blocks) n_slices = n_blocks;
+    B200_REQUIRE(n_slices <= 65535, "sparse_topk: too many slices");
+    dim3 grid((unsigned)n_queries, (unsigned)n_slices);
+    sparse_query_kernel<<<grid, SP_THREADS, smem, st>>>(blk_term_ptr, post_doc, post_w, n_docs, n_terms, block_docs,
+                                                       (int)n_blocks, (int)n_slices, q_ptr, q_terms, q_vals, k, cap, id_offset,
                                                        part_scores, part_ids); count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
-    return launch_merge(part_scores, part_ids, n_queries, nullptr, (int)(n_blocks * k), k, nullptr, out_scores, out_ids,
+    return launch_merge(part_scores, part_ids, n_queries, nullptr, (int)(n_slices * k), k, nullptr, out_scores, out_ids,
                         out_counts, st);
 }
 

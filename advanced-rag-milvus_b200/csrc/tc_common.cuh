@@ -20,6 +20,7 @@ constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_MAX_C = 1280;         // candidate-buffer capacity limit (compaction scratch in smem)
 constexpr int TC_FALLBACK_BATCH = 32;
+constexpr size_t TC_SMEM_LIMIT = 232448;  // 227 KB of dynamic shared memory per CTA on sm_100
 constexpr int TC_QG_SPAN_MAX = 16;     // v3 tile-major order: per-query epilogue state of up to 16 block pairs lives in shared memory
 
 __host__ __device__ inline int tc_kprime(int k) { int s = k / 4 > 28 ? k / 4 : 28; return (k + s + 31) / 32 * 32; }
