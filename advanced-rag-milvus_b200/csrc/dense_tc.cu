@@ -288,47 +288,78 @@ __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishPa
     const unsigned int gk = p.gthr[q];
     const float m = fmaxf((n >= p.kprime) ? unmono32((uint32_t)oh[n - 1]) : -CUDART_INF_F, gk ? unmono32(gk) : -CUDART_INF_F);
 
-    // 2. exact canonical re-score
-    for (int i = tid; i < n; i += FN_THREADS) {
-        const uint32_t row = ~ol[i];
-        rows[i] = row;
-        approx[i] = unmono32((uint32_t)oh[i]);
-        exact[i] = canonical_dot<DTYPE>(qd, reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim), p.dim);
+    // 2. exact canonical re-score.  Eight threads share a row, one per canonical lane (lane j sums d = j mod 8 in
+    //    increasing d, exactly as oracle/exact_scan.c does); the lanes are combined in the canonical tree with shuffles.
+    //    (One thread per row left every 16-byte load's DRAM latency exposed: 44 % of this kernel's samples at k' = 640.)
+    float my_err = 0.f;
+    {
+        const int l8 = tid & 7, grp = tid >> 3;
+        const double* qj = qd + l8;
+        for (int i0 = 0; i0 < n; i0 += FN_THREADS / 8) {
+            const int i = i0 + grp;
+            const bool valid = i < n;
+            const uint32_t row = valid ? ~ol[i] : 0u;
+            const uint16_t* x = p.corpus + (size_t)row * p.dim + l8;
+            double acc = 0.0;
+            if (valid) {
+#pragma unroll 8
+                for (int d = 0; d < p.dim; d += 8) acc = fma(qj[d], bits_to_double<DTYPE>(__ldg(x + d)), acc);
+            }
+            double t = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, 1));      // lanes 0,2,4,6: p0+p1, p2+p3, ...
+            t = __dadd_rn(t, __shfl_down_sync(0xffffffffu, t, 2));                 // lanes 0,4: (p0+p1)+(p2+p3), ...
+            t = __dadd_rn(t, __shfl_down_sync(0xffffffffu, t, 4));                 // lane 0: the canonical score
+            if (valid && l8 == 0) {
+                rows[i] = row;
+                exact[i] = t;
+                my_err = fmaxf(my_err, fabsf((float)((double)unmono32((uint32_t)oh[i]) - t)));
+            }
+        }
     }
     if (tid == 0) {
         double s = 0.0;
         for (int d = 0; d < p.dim; ++d) s += qd[d] * qd[d];
         s_q2 = s;
     }
-    __syncthreads();
-    // 3. rank by (exact desc, row asc)
-    float my_err = 0.f;
-    for (int i = tid; i < n; i += FN_THREADS) {
-        const double e = exact[i];
-        const uint32_t r = rows[i];
-        int rk = 0;
-        for (int j = 0; j < n; ++j) rk += (exact[j] > e) || (exact[j] == e && rows[j] < r);
-        rank_of[i] = rk;
-        my_err = fmaxf(my_err, fabsf((float)((double)approx[i] - e)));
-    }
     if (p.err_max) atomicMax(reinterpret_cast<int*>(&s_err), __float_as_int(my_err));   // non-negative floats order as ints
     __syncthreads();
-    // 4. emit + completeness proof
+    // 3. rank by (exact desc, row asc) and emit.  Small candidate sets: all-pairs rank count (n^2 / 256 compares per
+    //    thread, no barriers); large ones (k' > 256): the selection buffers double as a bitonic sorter.
     const int kk = min(p.k, n);
-    __shared__ double s_ek;
-    if (tid == 0) s_ek = -CUDART_INF;
-    __syncthreads();
-    for (int i = tid; i < n; i += FN_THREADS) {
-        const int rk = rank_of[i];
-        if (rk < p.k) {
-            p.out_scores[(size_t)q * p.k + rk] = exact[i];
-            p.out_ids[(size_t)q * p.k + rk] = p.id_offset + (int64_t)rows[i];
+    __shared__ double s_ek_sh;
+    double s_ek = -CUDART_INF;
+    if (n <= 256) {
+        if (tid == 0) s_ek_sh = -CUDART_INF;
+        __syncthreads();
+        for (int i = tid; i < n; i += FN_THREADS) {
+            const double e = exact[i];
+            const uint32_t r = rows[i];
+            int rk = 0;
+            for (int j = 0; j < n; ++j) rk += (exact[j] > e) || (exact[j] == e && rows[j] < r);
+            if (rk < p.k) {
+                p.out_scores[(size_t)q * p.k + rk] = e;
+                p.out_ids[(size_t)q * p.k + rk] = p.id_offset + (int64_t)r;
+            }
+            if (rk == kk - 1) s_ek_sh = e;
         }
-        if (rk == kk - 1) s_ek = exact[i];
-    }
-    for (int i = kk + tid; i < p.k; i += FN_THREADS) {
-        p.out_scores[(size_t)q * p.k + i] = -CUDART_INF;
-        p.out_ids[(size_t)q * p.k + i] = -1;
+        for (int i = kk + tid; i < p.k; i += FN_THREADS) {
+            p.out_scores[(size_t)q * p.k + i] = -CUDART_INF;
+            p.out_ids[(size_t)q * p.k + i] = -1;
+        }
+        __syncthreads();
+        s_ek = s_ek_sh;
+    } else {
+        tk.init();
+        __syncthreads();
+        for (int i = tid; i < n; i += FN_THREADS) tk.offer(true, mono64(exact[i]), ~rows[i]);
+        __syncthreads();
+        tk.finalize();
+        const uint64_t* sh = tk.out_hi();
+        const uint32_t* sl = tk.out_lo();
+        for (int i = tid; i < p.k; i += FN_THREADS) {
+            p.out_scores[(size_t)q * p.k + i] = i < kk ? unmono64(sh[i]) : -CUDART_INF;
+            p.out_ids[(size_t)q * p.k + i] = i < kk ? p.id_offset + (int64_t)(~sl[i]) : -1;
+        }
+        if (kk > 0) s_ek = unmono64(sh[kk - 1]);
     }
     __syncthreads();
     if (tid == 0) {

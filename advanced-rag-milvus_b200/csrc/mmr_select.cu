@@ -23,6 +23,8 @@ namespace b200rag {
 
 constexpr int MMR_MAX_THREADS = 1024;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int MMR_G = 4;      // candidates a warp keeps in flight
+constexpr int MMR_R = 4;      // 32-token rounds of a candidate held in registers (fast path: documents of <= 128 unique tokens)
 
 __device__ __forceinline__ bool mmr_better(double ob, int oi, double b, int bi) {
     return oi != 0x7fffffff && (bi == 0x7fffffff || ob > b || (ob == b && oi < bi));
@@ -32,7 +34,7 @@ __global__ void __launch_bounds__(MMR_MAX_THREADS)
 mmr_select_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict__ cand_rel, const int32_t* __restrict__ cand_n,
                   int n_max, const int64_t* __restrict__ doc_tok_ptr, const int32_t* __restrict__ doc_tok_ids, int vocab_words,
                   const double* __restrict__ lambda, const int32_t* __restrict__ k_sel, int k_max,
-                  int32_t* __restrict__ out_pick, int32_t* __restrict__ out_n) {
+                  int32_t* __restrict__ out_pick, int32_t* __restrict__ out_n, int cache_cap, int n_hi) {
     extern __shared__ __align__(16) char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
@@ -43,6 +45,13 @@ mmr_select_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict
     int* tok_len = reinterpret_cast<int*>(tok_begin + n_max);      // [n_max]
     int* alive = tok_len + n_max;                                  // [n_max]
     uint32_t* bits = reinterpret_cast<uint32_t*>(alive + n_max);   // [vocab_words]
+    // token cache: the low 16 bits of the candidates' token ids, list after list, for as many leading candidates as
+    // fit; hi_bnd[c][b] = number of tokens of candidate c whose id is < (b + 1) << 16 (lists are sorted), which gives
+    // the high bits back.  Reading the lists from L2 on every pick (100 picks x 360 KB per query) was the bound.
+    int* cache_off = reinterpret_cast<int*>(bits + vocab_words);                        // [n_max]
+    uint16_t* hi_bnd = reinterpret_cast<uint16_t*>(cache_off + n_max);                  // [n_max][n_hi]
+    uint16_t* cache = hi_bnd + (size_t)n_max * n_hi + ((n_max * n_hi) & 1);             // [cache_cap], 4-byte aligned
+    __shared__ int s_ncached;
     __shared__ double s_best[MMR_MAX_THREADS / 32];
     __shared__ int s_best_idx[MMR_MAX_THREADS / 32];
     __shared__ int s_pick;
@@ -63,6 +72,50 @@ mmr_select_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict
     }
     for (int i = tid; i < vocab_words; i += nthreads) bits[i] = 0u;
     if (tid == 0) s_done = 0;
+    __syncthreads();
+    // ---- token cache: offsets (warp 0: chunked scan), then one warp per candidate copies its list ---------------
+    if (warp == 0) {
+        const int per = (n + 31) / 32;
+        int sum = 0;
+        for (int c = lane * per; c < min(n, (lane + 1) * per); ++c) sum += tok_len[c];
+        int incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int v = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += v;
+        }
+        int run = incl - sum;
+        int first_miss = n;
+        for (int c = lane * per; c < min(n, (lane + 1) * per); ++c) {
+            const bool fits = cache_cap > 0 && run + tok_len[c] <= cache_cap && tok_len[c] < 65536;
+            cache_off[c] = fits ? run : -1;
+            if (!fits && first_miss == n) first_miss = c;
+            run += tok_len[c];
+        }
+        first_miss = __reduce_min_sync(FULL, first_miss);
+        if (lane == 0) s_ncached = first_miss;      // candidates [0, s_ncached) are cached
+    }
+    __syncthreads();
+    const int n_cached = s_ncached;
+    for (int c = warp; c < n_cached; c += nwarps) {
+        const int32_t* toks = doc_tok_ids + tok_begin[c];
+        const int len_c = tok_len[c];
+        uint16_t* dst = cache + cache_off[c];
+        int below[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = lane; i < len_c; i += 32) {
+            const int t = __ldg(toks + i);
+            dst[i] = (uint16_t)(t & 0xffff);
+#pragma unroll
+            for (int b = 0; b < 8; ++b) below[b] += (b < n_hi && (t >> 16) <= b) ? 1 : 0;
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (b < n_hi) {
+                const int cnt = __reduce_add_sync(FULL, below[b]);
+                if (lane == 0) hi_bnd[(size_t)c * n_hi + b] = (uint16_t)cnt;
+            }
+        }
+    }
     __syncthreads();
 
     for (int step = 0; step < k; ++step) {
@@ -112,21 +165,87 @@ mmr_select_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict
             atomicOr(&bits[t >> 5], 1u << (t & 31));
         }
         __syncthreads();
-        // ---- 3. warp per candidate: |tokens(c) & tokens(pick)| -------------------------------------
-        for (int c = warp; c < n; c += nwarps) {
-            if (!alive[c]) continue;              // warp-uniform
-            const int32_t* toks = doc_tok_ids + tok_begin[c];
-            const int len_c = tok_len[c];
-            int inter = 0;
-            for (int i = lane; i < len_c; i += 32) {
-                const int t = __ldg(toks + i);
-                inter += (bits[t >> 5] >> (t & 31)) & 1u;
+        // ---- 3. |tokens(c) & tokens(pick)| for every alive candidate --------------------------------------------
+        // A warp takes candidates in batches of 32 (c = cb + j * nwarps): for candidate j the 32 lanes probe 32 tokens at a
+        // time and the count is reduced across the warp; lane j keeps the result, and after the batch every lane does ONE
+        // fp64 division (the division is ~100 instructions: one per candidate on a single active lane dominated round 1).
+        for (int cb = warp; cb < n; cb += nwarps * 32) {
+            int my_inter = 0, my_len = -1;
+            if (cb < n_cached) {
+                // ---- 3a. cached candidates: tokens from shared memory
+                for (int j = 0; j < 32; ++j) {
+                    const int c = cb + j * nwarps;
+                    if (c >= n) break;                                    // warp-uniform
+                    if (c >= n_cached || !alive[c]) continue;             // (uncached tail of a mixed batch: 3b below)
+                    const uint16_t* src = cache + cache_off[c];
+                    const int len_c = tok_len[c];
+                    const uint16_t* bnd = hi_bnd + (size_t)c * n_hi;
+                    const int b0 = n_hi ? bnd[0] : 0x7fffffff;
+                    int inter = 0;
+#pragma unroll
+                    for (int r = 0; r < MMR_R; ++r) {
+                        const int i = lane + 32 * r;
+                        if (i < len_c) {
+                            int hi = i >= b0;
+                            for (int bb = 1; bb < n_hi; ++bb) hi += i >= bnd[bb];
+                            const int t = (hi << 16) | src[i];
+                            inter += (bits[t >> 5] >> (t & 31)) & 1u;
+                        }
+                    }
+                    for (int i = lane + 32 * MMR_R; i < len_c; i += 32) {
+                        int hi = i >= b0;
+                        for (int bb = 1; bb < n_hi; ++bb) hi += i >= bnd[bb];
+                        const int t = (hi << 16) | src[i];
+                        inter += (bits[t >> 5] >> (t & 31)) & 1u;
+                    }
+                    inter = __reduce_add_sync(FULL, inter);
+                    if (lane == j) { my_inter = inter; my_len = len_c; }
+                }
             }
-            inter = __reduce_add_sync(FULL, inter);
-            if (lane == 0) {
-                const int uni = len_c + len_p - inter;
-                const double j = __ddiv_rn((double)inter, (double)(uni ? uni : 1));
-                if (j > max_sim[c]) max_sim[c] = j;
+            if (cb + 31 * nwarps >= n_cached) {
+                // ---- 3b. candidates that did not fit in the cache: tokens from global memory, MMR_G lists in flight
+                for (int j0 = 0; j0 < 32; j0 += MMR_G) {
+                    if (cb + j0 * nwarps >= n) break;                     // warp-uniform
+                    int tt[MMR_G][MMR_R];
+                    int lens[MMR_G];
+#pragma unroll
+                    for (int g = 0; g < MMR_G; ++g) {
+                        const int c = cb + (j0 + g) * nwarps;
+                        const bool ok = c < n && c >= n_cached && alive[c];
+                        lens[g] = ok ? tok_len[c] : -1;
+                        const int32_t* toks = doc_tok_ids + (ok ? tok_begin[c] : 0);
+#pragma unroll
+                        for (int r = 0; r < MMR_R; ++r) {
+                            const int i = lane + 32 * r;
+                            tt[g][r] = i < lens[g] ? __ldg(toks + i) : -1;
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < MMR_G; ++g) {
+                        if (lens[g] < 0) continue;                        // warp-uniform
+                        int inter = 0;
+#pragma unroll
+                        for (int r = 0; r < MMR_R; ++r) {
+                            const int t = tt[g][r];
+                            if (t >= 0) inter += (bits[t >> 5] >> (t & 31)) & 1u;
+                        }
+                        if (lens[g] > 32 * MMR_R) {                       // long documents: the rest of the list
+                            const int32_t* toks = doc_tok_ids + tok_begin[cb + (j0 + g) * nwarps];
+                            for (int i = lane + 32 * MMR_R; i < lens[g]; i += 32) {
+                                const int t = __ldg(toks + i);
+                                inter += (bits[t >> 5] >> (t & 31)) & 1u;
+                            }
+                        }
+                        inter = __reduce_add_sync(FULL, inter);
+                        if (lane == j0 + g) { my_inter = inter; my_len = lens[g]; }
+                    }
+                }
+            }
+            if (my_len >= 0) {
+                const int c = cb + lane * nwarps;
+                const int uni = my_len + len_p - my_inter;
+                const double jac = __ddiv_rn((double)my_inter, (double)(uni ? uni : 1));
+                if (jac > max_sim[c]) max_sim[c] = jac;
             }
         }
         __syncthreads();
@@ -157,17 +276,30 @@ int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const in
     B200_REQUIRE(n_queries >= 0 && n_max >= 1 && vocab_size >= 1 && k_max >= 1, "mmr_select: bad sizes");
     if (n_queries == 0) return B200RAG_OK;
     int vocab_words = (vocab_size + 31) / 32;
-    size_t smem = (size_t)n_max * (8 + 8 + 8 + 4 + 4) + (size_t)vocab_words * 4 + 64;
+    // tokens >= (n_hi << 16) do not exist; n_hi thresholds per candidate give the high bits of cached tokens back
+    int n_hi = (vocab_size - 1) >> 16;
+    size_t fixed = (size_t)n_max * (8 + 8 + 8 + 4 + 4) + (size_t)vocab_words * 4 + 64;
+    size_t smem = fixed;
     if (smem > 225 * 1024) {
         set_error("mmr_select: n_max=%d vocab=%d needs %zu bytes of shared memory", n_max, vocab_size, smem);
         return B200RAG_E_UNSUPPORTED;
     }
+    int cache_cap = 0;
+    if (n_hi <= 8) {
+        const size_t meta = (size_t)n_max * 4 + (size_t)n_max * n_hi * 2 + 8;
+        const size_t limit = 227 * 1024 - 1024;      // static shared memory (reduction scratch) takes the rest
+        if (fixed + meta + 4096 <= limit) {
+            cache_cap = (int)((limit - fixed - meta) / 2);
+            smem = fixed + meta + (size_t)cache_cap * 2;
+        }
+    }
+    if (cache_cap == 0) n_hi = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     B200_CUDA_CHECK(cudaFuncSetAttribute(mmr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // one warp per candidate in the intersection phase: as many warps as there are candidates, up to 32
     const int threads = n_max >= 32 ? MMR_MAX_THREADS : (n_max >= 8 ? 256 : 128);
     mmr_select_kernel<<<n_queries, threads, smem, st>>>(cand_doc, cand_rel, cand_n, n_max, doc_tok_ptr, doc_tok_ids,
-                                                           vocab_words, lambda, k_sel, k_max, out_pick, out_n); count_launch();
+                                                           vocab_words, lambda, k_sel, k_max, out_pick, out_n, cache_cap, n_hi); count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;
 }

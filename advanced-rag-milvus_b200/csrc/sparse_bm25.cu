@@ -52,6 +52,18 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
     const int64_t qs = q_ptr[q];
     const int nq = (int)(q_ptr[q + 1] - qs);
     const int b0 = (int)((int64_t)slice * n_blocks / n_slices), b1 = (int)((int64_t)(slice + 1) * n_blocks / n_slices);
+    // ranges of the first term group of the NEXT block are fetched one block ahead (pointer -> postings is a dependent chain)
+    long long pre_s = 0, pre_e = 0;
+    float pre_qv = 0.f;
+    int my_t = -1;
+    if (tid < SP_TG && tid < nq) {
+        const int t = q_terms[qs + tid];
+        if (t >= 0 && t < n_terms) { my_t = t; pre_qv = q_vals[qs + tid]; }
+    }
+    if (my_t >= 0 && b0 < b1) {
+        const int64_t* tp0 = blk_term_ptr + (size_t)b0 * (n_terms + 1);
+        pre_s = tp0[my_t]; pre_e = tp0[my_t + 1];
+    }
     for (int blk = b0; blk < b1; ++blk) {
         const int64_t doc0 = (int64_t)blk * block_docs;
         const int64_t* tp = blk_term_ptr + (size_t)blk * (n_terms + 1);
@@ -60,7 +72,13 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
             if (tid < SP_TG) {
                 long long s = 0, e = 0;
                 float qv = 0.f;
-                if (g0 + tid < nq) {
+                if (g0 == 0) {
+                    s = pre_s; e = pre_e; qv = pre_qv;
+                    if (my_t >= 0 && blk + 1 < b1) {                  // issue the next block's pointer loads now
+                        const int64_t* tpn = tp + (n_terms + 1);
+                        pre_s = tpn[my_t]; pre_e = tpn[my_t + 1];
+                    }
+                } else if (g0 + tid < nq) {
                     const int t = q_terms[qs + g0 + tid];
                     if (t >= 0 && t < n_terms) { s = tp[t]; e = tp[t + 1]; qv = q_vals[qs + g0 + tid]; }
                 }

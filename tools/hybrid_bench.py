@@ -100,6 +100,12 @@ if "c4" not in args.skip:
         return sparse.search(qp, qt, qv, K2)
 
     t_dense, (ds, di, _) = timed(dense_fn, args.reps)
+    from b200rag import _lib
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); e1.record(); torch.cuda.synchronize()
+    _lib.load().b200rag_profile_next_scan(e0.cuda_event, e1.cuda_event)
+    dense_fn(); torch.cuda.synchronize()
+    t_dense_scan = e0.elapsed_time(e1)
     t_sparse, (ss, si, sc) = timed(sparse_fn, args.reps)
     sp_bytes = statistics.mean(sparse.query_bytes(q[0], q[1]) for q in qs)
     lists = torch.stack([di, si]).contiguous()
@@ -126,7 +132,7 @@ if "c4" not in args.skip:
     t_all, _ = timed(hybrid, max(3, args.reps // 4))
     flops = 2.0 * B * args.docs * args.dim
     dbytes = args.docs * args.dim * 2
-    out["c4"] = {"dense_ms": t_dense, "dense_tflops": flops / t_dense / 1e9, "dense_hbm_frac": dbytes / (t_dense * 1e-3) / HBM,
+    out["c4"] = {"dense_ms": t_dense, "dense_full_scan_kernel_ms": t_dense_scan, "dense_tflops": flops / t_dense / 1e9, "dense_hbm_frac": dbytes / (t_dense * 1e-3) / HBM,
                  "sparse_ms": t_sparse, "sparse_alg_bytes": sp_bytes, "sparse_gbs": sp_bytes / t_sparse / 1e6,
                  "sparse_hbm_frac": sp_bytes / (t_sparse * 1e-3) / HBM, "rrf_ms": t_rrf, "mmr_ms": t_mmr,
                  "fused_candidates_mean": float(fused.n.float().mean()), "hybrid_ms": t_all, "hybrid_qps": B / t_all * 1e3}
