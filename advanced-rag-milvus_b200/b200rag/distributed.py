@@ -38,8 +38,13 @@ def unpack_gathered(gathered: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch
 
 def gather_and_merge(scores: torch.Tensor, ids: torch.Tensor, k: int,
                      merge_fn: Callable[[torch.Tensor, torch.Tensor, int], Tuple[torch.Tensor, torch.Tensor]],
-                     group: Optional[dist.ProcessGroup] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """All-gather every rank's local top-k and merge.  Identity when not running distributed."""
+                     group: Optional[dist.ProcessGroup] = None,
+                     merge_gathered_fn: Optional[Callable[[torch.Tensor, int], Tuple[torch.Tensor, torch.Tensor]]] = None
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather every rank's local top-k and merge.  Identity when not running distributed.
+
+    merge_gathered_fn (engine.merge_gathered on the GPU) reduces the gathered [G, B, 2k] buffer in place; without it the
+    buffer is unpacked into [B, G*k] candidate lists for merge_fn (the CPU tests stand the oracle in there)."""
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     if world == 1:
         return scores, ids
@@ -47,7 +52,10 @@ def gather_and_merge(scores: torch.Tensor, ids: torch.Tensor, k: int,
     # concatenated (not stacked) output layout: the one form both NCCL and gloo accept
     out = torch.empty((world * msg.shape[0], msg.shape[1]), dtype=msg.dtype, device=msg.device)
     dist.all_gather_into_tensor(out, msg, group=group)
-    cs, ci = unpack_gathered(out.view(world, msg.shape[0], msg.shape[1]), k)
+    gathered = out.view(world, msg.shape[0], msg.shape[1])
+    if merge_gathered_fn is not None:
+        return merge_gathered_fn(gathered, k)
+    cs, ci = unpack_gathered(gathered, k)
     return merge_fn(cs, ci, k)
 
 
@@ -69,4 +77,4 @@ class ShardedDenseIndex:
         """Replicated queries -> global exact top-k on every rank: (scores f64 [B,k], ids i64 [B,k])."""
         eng = self._engine
         s, i, _ = self.local.search(queries_f32, k, eng.DENSE_AUTO if mode is None else mode)
-        return gather_and_merge(s, i, k, eng.merge_topk, self.group)
+        return gather_and_merge(s, i, k, eng.merge_topk, self.group, eng.merge_gathered)

@@ -103,9 +103,9 @@ def dense_topk(corpus16: torch.Tensor, queries16: torch.Tensor, k: int, id_offse
     dev = corpus16.device
     scores = torch.empty((b, k), dtype=torch.float64, device=dev)
     ids = torch.empty((b, k), dtype=torch.int64, device=dev)
-    flags = torch.zeros((b,), dtype=torch.int32, device=dev)
     if b == 0:
-        return scores, ids, flags
+        return scores, ids, torch.zeros((0,), dtype=torch.int32, device=dev)
+    flags = torch.empty((b,), dtype=torch.int32, device=dev)      # every mode writes all b entries
     if out_err is not None and (out_err.dtype != torch.float32 or out_err.numel() < b or not out_err.is_cuda):
         raise ValueError("out_err must be a CUDA float32 tensor with one entry per query")
     L = _lib.load()
@@ -133,6 +133,20 @@ def merge_topk(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tup
     with torch.cuda.device(dev):
         check(_lib.load().b200rag_merge_topk(cand_scores.data_ptr(), cand_ids.data_ptr(), b, m, k, scores.data_ptr(),
                                              ids.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)))
+    return scores, ids
+
+
+def merge_gathered(gathered: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather buffer i64 [G, B, 2k] (k fp64 score bit patterns, then k ids, per rank and query) -> global top-k."""
+    _require_cuda(gathered, "gathered")
+    if gathered.dtype != torch.int64 or gathered.dim() != 3 or gathered.shape[2] != 2 * k:
+        raise ValueError("merge_gathered expects an int64 [G, B, 2k] tensor")
+    g, b, _ = gathered.shape
+    dev = gathered.device
+    scores = torch.empty((b, k), dtype=torch.float64, device=dev)
+    ids = torch.empty((b, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().b200rag_merge_gathered(gathered.data_ptr(), g, b, k, scores.data_ptr(), ids.data_ptr(), _stream_ptr(dev)))
     return scores, ids
 
 

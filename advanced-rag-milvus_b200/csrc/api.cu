@@ -38,7 +38,8 @@ __device__ __forceinline__ uint16_t double_to_bits(double v) {
     return __bfloat16_as_ushort(__double2bfloat16(v));
 }
 
-constexpr int PREP_ROWS = 32;   // rows per block (one thread each for the reduction)
+constexpr int PREP_ROWS = 8;    // rows per block (one thread each for the sequential fp64 norm; few rows per block so that a
+                                // 1024-query batch spreads over 128 SMs instead of 32)
 constexpr int PREP_THREADS = 256;
 
 template <int DTYPE>

@@ -6,7 +6,7 @@ namespace b200rag {
 size_t exact_workspace_bytes(int64_t n_rows, int dim, int n_q, int k);
 int run_exact(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_launch,
               const int32_t* q_list, int k, int64_t id_offset, double* out_scores, int64_t* out_ids,
-              void* workspace, size_t workspace_bytes, cudaStream_t st);
+              void* workspace, size_t workspace_bytes, cudaStream_t st, const int32_t* n_active, int slot_base);
 size_t tensor_workspace_bytes(int64_t n_rows, int dim, int n_q, int k);
 int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_q, int k,
                int64_t id_offset, double* out_scores, int64_t* out_ids, int32_t* out_flags, double row_norm_bound,
@@ -55,7 +55,7 @@ int b200rag_dense_topk(const void* corpus16, int64_t n_rows, int32_t dim, int32_
         if (out_flags) B200_CUDA_CHECK(cudaMemsetAsync(out_flags, 0, (size_t)n_queries * sizeof(int32_t), st));
         if (out_err) B200_CUDA_CHECK(cudaMemsetAsync(out_err, 0, (size_t)n_queries * sizeof(float), st));
         return run_exact(corpus16, n_rows, dim, dtype, queries16, n_queries, nullptr, k, id_offset, out_scores, out_ids,
-                         workspace, workspace_bytes, st);
+                         workspace, workspace_bytes, st, nullptr, 0);
     }
     if (mode == B200RAG_DENSE_AUTO || mode == B200RAG_DENSE_TENSOR) {
         B200_REQUIRE(row_norm_bound > 0.0 && row_norm_bound < 1e30, "dense_topk: row_norm_bound must be positive (got %g)",

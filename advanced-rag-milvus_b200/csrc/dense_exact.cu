@@ -22,11 +22,19 @@ __global__ void __launch_bounds__(EX_THREADS)
 dense_exact_kernel(const uint16_t* __restrict__ corpus, int64_t n_rows, int dim,
                    const uint16_t* __restrict__ queries, int n_q, const int32_t* __restrict__ q_list, int k, int cap,
                    int64_t rows_per_chunk, int n_chunks, int64_t id_offset,
-                   double* __restrict__ part_scores, int64_t* __restrict__ part_ids) {
+                   double* __restrict__ part_scores, int64_t* __restrict__ part_ids,
+                   const int32_t* __restrict__ n_active, int slot_base) {
     extern __shared__ __align__(16) char smem[];
     const int tid = threadIdx.x;
     const int chunk = blockIdx.x;
     const int q0 = blockIdx.y * EX_QT;
+    // device-side gate: only launch slots slot_base + s < *n_active carry a query (lets the tensor path's fallback be
+    // launched unconditionally, without a host round trip; an idle CTA leaves at once)
+    if (n_active) {
+        const int na = *n_active - slot_base;
+        if (na < n_q) n_q = na;
+    }
+    if (q0 >= n_q) return;
     const int64_t r_begin = (int64_t)chunk * rows_per_chunk;
     const int64_t r_end = min(n_rows, r_begin + rows_per_chunk);
 
@@ -123,10 +131,11 @@ template <typename OutT>
 __global__ void __launch_bounds__(MG_THREADS)
 merge_topk_kernel(const double* __restrict__ cand_scores, const int64_t* __restrict__ cand_ids, int n_cand, int k, int cap,
                   const int32_t* __restrict__ q_list, OutT* __restrict__ out_scores, int64_t* __restrict__ out_ids,
-                  int32_t* __restrict__ out_counts) {
+                  int32_t* __restrict__ out_counts, const int32_t* __restrict__ n_active, int slot_base) {
     extern __shared__ __align__(16) char smem[];
     const int tid = threadIdx.x;
     const int slot = blockIdx.x;                       // candidate lists are indexed by launch slot
+    if (n_active && slot_base + slot >= *n_active) return;
     const int q = q_list ? q_list[slot] : slot;         // results go to the original query row
     BlockTopK<MG_THREADS, uint64_t> tk;
     tk.attach(smem, cap, k, MG_THREADS);
@@ -157,6 +166,45 @@ merge_topk_kernel(const double* __restrict__ cand_scores, const int64_t* __restr
         }
     }
     if (out_counts && tid == 0) out_counts[q] = n;
+}
+
+// Merge straight out of the all-gather buffer: gathered i64 [n_ranks][n_queries][2k] holds, per rank and query, k fp64
+// score bit patterns followed by k ids (b200rag/distributed.py packs it that way).  Same ranking rule as above.
+__global__ void __launch_bounds__(MG_THREADS)
+merge_gathered_kernel(const int64_t* __restrict__ gathered, int n_ranks, int n_queries, int k, int cap,
+                      double* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+    extern __shared__ __align__(16) char smem[];
+    const int tid = threadIdx.x;
+    const int q = blockIdx.x;
+    BlockTopK<MG_THREADS, uint64_t> tk;
+    tk.attach(smem, cap, k, MG_THREADS);
+    tk.init();
+    __syncthreads();
+    const int n_cand = n_ranks * k;
+    for (int base = 0; base < n_cand; base += MG_THREADS) {
+        const int i = base + tid;
+        bool valid = i < n_cand;
+        int64_t id = -1;
+        double sc = 0.0;
+        if (valid) {
+            const int g = i / k, j = i - g * k;
+            const int64_t* rec = gathered + ((size_t)g * n_queries + q) * (2 * (size_t)k);
+            id = rec[k + j];
+            sc = __longlong_as_double(rec[j]);
+        }
+        valid = valid && id >= 0;
+        tk.offer(valid, valid ? mono64(sc) : 0, ~(uint64_t)id);
+        tk.settle();
+    }
+    __syncthreads();
+    tk.finalize();
+    const int n = tk.count();
+    const uint64_t* oh = tk.out_hi();
+    const uint64_t* ol = tk.out_lo();
+    for (int i = tid; i < k; i += MG_THREADS) {
+        out_scores[(size_t)q * k + i] = i < n ? unmono64(oh[i]) : -CUDART_INF;
+        out_ids[(size_t)q * k + i] = i < n ? (int64_t)(~ol[i]) : -1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -191,8 +239,19 @@ size_t exact_workspace_bytes(int64_t n_rows, int dim, int n_q, int k) {
            align_up((size_t)n_q * pl.n_chunks * k * sizeof(int64_t), 256) + 512;
 }
 
+int launch_merge_gated(const double* cand_scores, const int64_t* cand_ids, int n_launch, const int32_t* q_list, int n_cand, int k,
+                       double* out_scores_f64, float* out_scores_f32, int64_t* out_ids, int32_t* out_counts, cudaStream_t st,
+                       const int32_t* n_active, int slot_base);
+
 int launch_merge(const double* cand_scores, const int64_t* cand_ids, int n_launch, const int32_t* q_list, int n_cand, int k,
                  double* out_scores_f64, float* out_scores_f32, int64_t* out_ids, int32_t* out_counts, cudaStream_t st) {
+    return launch_merge_gated(cand_scores, cand_ids, n_launch, q_list, n_cand, k, out_scores_f64, out_scores_f32, out_ids,
+                              out_counts, st, nullptr, 0);
+}
+
+int launch_merge_gated(const double* cand_scores, const int64_t* cand_ids, int n_launch, const int32_t* q_list, int n_cand, int k,
+                       double* out_scores_f64, float* out_scores_f32, int64_t* out_ids, int32_t* out_counts, cudaStream_t st,
+                       const int32_t* n_active, int slot_base) {
     int cap = BlockTopK<MG_THREADS, uint64_t>::capacity_for(k, MG_THREADS);
     size_t smem = BlockTopK<MG_THREADS, uint64_t>::smem_bytes(cap) + 64;
     if (smem > 220 * 1024) {
@@ -203,11 +262,11 @@ int launch_merge(const double* cand_scores, const int64_t* cand_ids, int n_launc
     if (out_scores_f64) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(merge_topk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         merge_topk_kernel<double><<<n_launch, MG_THREADS, smem, st>>>(cand_scores, cand_ids, n_cand, k, cap, q_list,
-                                                                     out_scores_f64, out_ids, out_counts); count_launch();
+                                                                     out_scores_f64, out_ids, out_counts, n_active, slot_base); count_launch();
     } else {
         B200_CUDA_CHECK(cudaFuncSetAttribute(merge_topk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         merge_topk_kernel<float><<<n_launch, MG_THREADS, smem, st>>>(cand_scores, cand_ids, n_cand, k, cap, q_list,
-                                                                    out_scores_f32, out_ids, out_counts); count_launch();
+                                                                    out_scores_f32, out_ids, out_counts, n_active, slot_base); count_launch();
     }
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;
@@ -217,7 +276,7 @@ int launch_merge(const double* cand_scores, const int64_t* cand_ids, int n_launc
 // number; query vectors are read from, and results written to, the ORIGINAL query rows.
 int run_exact(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_launch,
               const int32_t* q_list, int k, int64_t id_offset, double* out_scores, int64_t* out_ids,
-              void* workspace, size_t workspace_bytes, cudaStream_t st) {
+              void* workspace, size_t workspace_bytes, cudaStream_t st, const int32_t* n_active, int slot_base) {
     if (n_launch <= 0) return B200RAG_OK;
     ExactPlan pl = plan_exact(n_rows, dim, n_launch, k);
     if (pl.smem > 220 * 1024) {
@@ -237,14 +296,15 @@ int run_exact(const void* corpus16, int64_t n_rows, int dim, int dtype, const vo
     if (dtype == B200RAG_F16) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(dense_exact_kernel<B200RAG_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         dense_exact_kernel<B200RAG_F16><<<grid, EX_THREADS, pl.smem, st>>>(c, n_rows, dim, q, n_launch, q_list, k, pl.cap,
-                                                                         pl.rows_per_chunk, pl.n_chunks, id_offset, part_scores, part_ids); count_launch();
+                                                                         pl.rows_per_chunk, pl.n_chunks, id_offset, part_scores, part_ids, n_active, slot_base); count_launch();
     } else {
         B200_CUDA_CHECK(cudaFuncSetAttribute(dense_exact_kernel<B200RAG_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         dense_exact_kernel<B200RAG_BF16><<<grid, EX_THREADS, pl.smem, st>>>(c, n_rows, dim, q, n_launch, q_list, k, pl.cap,
-                                                                          pl.rows_per_chunk, pl.n_chunks, id_offset, part_scores, part_ids); count_launch();
+                                                                          pl.rows_per_chunk, pl.n_chunks, id_offset, part_scores, part_ids, n_active, slot_base); count_launch();
     }
     B200_CUDA_CHECK(cudaGetLastError());
-    return launch_merge(part_scores, part_ids, n_launch, q_list, pl.n_chunks * k, k, out_scores, nullptr, out_ids, nullptr, st);
+    return launch_merge_gated(part_scores, part_ids, n_launch, q_list, pl.n_chunks * k, k, out_scores, nullptr, out_ids, nullptr, st,
+                              n_active, slot_base);
 }
 
 }  // namespace b200rag
@@ -263,6 +323,24 @@ int b200rag_merge_topk(const double* cand_scores, const int64_t* cand_ids, int32
     B200_REQUIRE(n_queries >= 0 && n_cand >= 0 && k > 0, "merge_topk: bad sizes");
     return launch_merge(cand_scores, cand_ids, n_queries, nullptr, n_cand, k, out_scores, nullptr, out_ids, nullptr,
                         static_cast<cudaStream_t>(stream));
+}
+
+int b200rag_merge_gathered(const int64_t* gathered, int32_t n_ranks, int32_t n_queries, int32_t k,
+                           double* out_scores, int64_t* out_ids, void* stream) {
+    B200_REQUIRE(gathered && out_scores && out_ids, "merge_gathered: null pointer");
+    B200_REQUIRE(n_ranks >= 1 && n_queries >= 0 && k > 0, "merge_gathered: bad sizes");
+    if (n_queries == 0) return B200RAG_OK;
+    int cap = BlockTopK<MG_THREADS, uint64_t>::capacity_for(k, MG_THREADS);
+    size_t smem = BlockTopK<MG_THREADS, uint64_t>::smem_bytes(cap) + 64;
+    if (smem > 220 * 1024) {
+        set_error("merge_gathered: k=%d needs %zu bytes of shared memory", k, smem);
+        return B200RAG_E_UNSUPPORTED;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    B200_CUDA_CHECK(cudaFuncSetAttribute(merge_gathered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_gathered_kernel<<<n_queries, MG_THREADS, smem, st>>>(gathered, n_ranks, n_queries, k, cap, out_scores, out_ids); count_launch();
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200RAG_OK;
 }
 
 }  // extern "C"

@@ -29,7 +29,7 @@ namespace b200rag {
 size_t exact_workspace_bytes(int64_t n_rows, int dim, int n_q, int k);
 int run_exact(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_launch,
               const int32_t* q_list, int k, int64_t id_offset, double* out_scores, int64_t* out_ids,
-              void* workspace, size_t workspace_bytes, cudaStream_t st);
+              void* workspace, size_t workspace_bytes, cudaStream_t st, const int32_t* n_active, int slot_base);
 
 // ----------------------------------------------------------------------------------------------- scan kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishPa
     __shared__ float s_err;
 
     BlockTopK<FN_THREADS, uint32_t> tk;
-    tk.attach(tkmem, p.topk_cap, p.kprime, FN_THREADS, /*start_digit=*/BlockTopK<FN_THREADS, uint32_t>::NLO + 3);
+    char* stage = tk.attach(tkmem, p.topk_cap, p.kprime, FN_THREADS, /*start_digit=*/BlockTopK<FN_THREADS, uint32_t>::NLO + 3);
     tk.init();
     for (int d = tid; d < p.dim; d += FN_THREADS) qd[d] = bits_to_double<DTYPE>(p.queries[(size_t)q * p.dim + d]);
     if (tid == 0) s_err = 0.f;
@@ -288,31 +288,43 @@ __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishPa
     const unsigned int gk = p.gthr[q];
     const float m = fmaxf((n >= p.kprime) ? unmono32((uint32_t)oh[n - 1]) : -CUDART_INF_F, gk ? unmono32(gk) : -CUDART_INF_F);
 
-    // 2. exact canonical re-score.  Eight threads share a row, one per canonical lane (lane j sums d = j mod 8 in
-    //    increasing d, exactly as oracle/exact_scan.c does); the lanes are combined in the canonical tree with shuffles.
-    //    (One thread per row left every 16-byte load's DRAM latency exposed: 44 % of this kernel's samples at k' = 640.)
+    // 2. exact canonical re-score.  Rows are staged through shared memory 32 at a time with 16-byte loads (every thread
+    //    has dim/64 independent loads in flight: one exposed DRAM latency per batch instead of one per element), then
+    //    eight threads share a row, one per canonical lane (lane j sums d = j mod 8 in increasing d, exactly as
+    //    oracle/exact_scan.c does), and the lanes are combined in the canonical tree with shuffles.
     float my_err = 0.f;
     {
+        constexpr int RB = FN_THREADS / 8;                       // rows per batch
         const int l8 = tid & 7, grp = tid >> 3;
+        const int vec_per_row = p.dim / 8;                        // 16-byte vectors per row
+        const int stride = p.dim * 2 + 16;                        // staged row pitch: +16 bytes keeps the 4 rows of a warp on different banks
         const double* qj = qd + l8;
-        for (int i0 = 0; i0 < n; i0 += FN_THREADS / 8) {
+        for (int i0 = 0; i0 < n; i0 += RB) {
+            const int rows_here = min(RB, n - i0);
+            for (int v = tid; v < rows_here * vec_per_row; v += FN_THREADS) {
+                const int r = v / vec_per_row, c = v - r * vec_per_row;
+                const uint32_t row = ~ol[i0 + r];
+                *reinterpret_cast<uint4*>(stage + (size_t)r * stride + c * 16) =
+                    __ldg(reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim) + c);
+            }
+            __syncthreads();
             const int i = i0 + grp;
             const bool valid = i < n;
-            const uint32_t row = valid ? ~ol[i] : 0u;
-            const uint16_t* x = p.corpus + (size_t)row * p.dim + l8;
+            const uint16_t* x = reinterpret_cast<const uint16_t*>(stage + (size_t)grp * stride) + l8;
             double acc = 0.0;
             if (valid) {
-#pragma unroll 8
-                for (int d = 0; d < p.dim; d += 8) acc = fma(qj[d], bits_to_double<DTYPE>(__ldg(x + d)), acc);
+#pragma unroll 4
+                for (int d = 0; d < p.dim; d += 8) acc = fma(qj[d], bits_to_double<DTYPE>(x[d]), acc);
             }
             double t = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, 1));      // lanes 0,2,4,6: p0+p1, p2+p3, ...
             t = __dadd_rn(t, __shfl_down_sync(0xffffffffu, t, 2));                 // lanes 0,4: (p0+p1)+(p2+p3), ...
             t = __dadd_rn(t, __shfl_down_sync(0xffffffffu, t, 4));                 // lane 0: the canonical score
             if (valid && l8 == 0) {
-                rows[i] = row;
+                rows[i] = ~ol[i];
                 exact[i] = t;
                 my_err = fmaxf(my_err, fabsf((float)((double)unmono32((uint32_t)oh[i]) - t)));
             }
+            __syncthreads();
         }
     }
     if (tid == 0) {
@@ -550,7 +562,8 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     pl.s_topk_cap = BlockTopK<FN_THREADS, uint32_t>::capacity_for(pl.s_rank, FN_THREADS);
     pl.topk_cap = BlockTopK<FN_THREADS, uint32_t>::capacity_for(pl.kprime, FN_THREADS);
     pl.finish_smem = (size_t)dim * 8 + (size_t)pl.kprime * (8 + 4 + 4 + 4) + 32 +
-                     BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.topk_cap) + 64;
+                     BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.topk_cap) + 64 +
+                     (size_t)(FN_THREADS / 8) * ((size_t)dim * 2 + 16);          // staged candidate rows of one re-score batch
     size_t off = 0;
     auto take = [&](size_t bytes) { off = align_up(off, 256); size_t o = off; off += bytes; return o; };
     const int max_chunks = pl.n_chunks > pl.s_chunks ? pl.n_chunks : pl.s_chunks;
@@ -561,7 +574,12 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     pl.off_qpad = take((size_t)pl.nqb * TC_BM * dim * 2);      // query block padded with zero rows (no TMA out-of-bounds rows)
     pl.off_nflag = take(256);
     pl.off_stats = take((size_t)256 * ST_N * 8);
-    pl.off_exact = take(exact_workspace_bytes(n_rows, dim, TC_FALLBACK_BATCH, k));
+    {   // exact fallback, tier A (<= TC_FALLBACK_BATCH queries) and tier B (the rest): they run one after the other in the same region
+        const int na = n_q < TC_FALLBACK_BATCH ? n_q : TC_FALLBACK_BATCH;
+        size_t ea = exact_workspace_bytes(n_rows, dim, na, k);
+        size_t eb = n_q > na ? exact_workspace_bytes(n_rows, dim, n_q - na, k) : 0;
+        pl.off_exact = take(ea > eb ? ea : eb);
+    }
     pl.total = align_up(off, 256);
     return pl;
 }
@@ -719,14 +737,18 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
     B200_CUDA_CHECK(cudaGetLastError());
 
     if (with_fallback) {
-        // AUTO: results must be exact for every query, so learn how many queries could not be proven (4-byte read-back)
-        int32_t h_n = 0;
-        B200_CUDA_CHECK(cudaMemcpyAsync(&h_n, n_flagged, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        B200_CUDA_CHECK(cudaStreamSynchronize(st));
-        for (int done = 0; done < h_n; done += TC_FALLBACK_BATCH) {
-            int nb = h_n - done < TC_FALLBACK_BATCH ? h_n - done : TC_FALLBACK_BATCH;
-            int rc = run_exact(corpus16, n_rows, dim, dtype, queries16, nb, flag_list + done, k, id_offset, out_scores, out_ids,
-                               ws + pl.off_exact, pl.total - pl.off_exact, st);
+        // AUTO: results must be exact for every query, so the flagged ones are re-run on the exact path -- without a host
+        // round trip: the exact scan is launched unconditionally over the flag list and gated ON THE DEVICE by the
+        // flagged-query counter (CTAs of unused slots leave at once).  Tier A covers the first TC_FALLBACK_BATCH flagged
+        // queries with a many-chunk plan (the usual case: zero, one or a few of them); tier B covers every further slot
+        // with the few-chunk plan of a large batch and only does work on pathological inputs (massive ties).
+        const int na = n_q < TC_FALLBACK_BATCH ? n_q : TC_FALLBACK_BATCH;
+        int rc = run_exact(corpus16, n_rows, dim, dtype, queries16, na, flag_list, k, id_offset, out_scores, out_ids,
+                           ws + pl.off_exact, pl.total - pl.off_exact, st, n_flagged, 0);
+        if (rc) return rc;
+        if (n_q > na) {
+            rc = run_exact(corpus16, n_rows, dim, dtype, queries16, n_q - na, flag_list + na, k, id_offset, out_scores, out_ids,
+                           ws + pl.off_exact, pl.total - pl.off_exact, st, n_flagged, na);
             if (rc) return rc;
         }
     }

@@ -221,7 +221,7 @@ def main():
     def search(q):
         s, i, f = idx.search(q, K, engine.DENSE_AUTO)
         if world > 1:
-            s, i = bdist.gather_and_merge(s, i, K, engine.merge_topk)
+            s, i = bdist.gather_and_merge(s, i, K, engine.merge_topk, None, engine.merge_gathered)
         return s, i, f
 
     def barrier():

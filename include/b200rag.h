@@ -135,6 +135,12 @@ int b200rag_merge_topk(const double* cand_scores, const int64_t* cand_ids, int32
                        int32_t k, double* out_scores, int64_t* out_ids,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same reduce, reading the NCCL all-gather buffer in place: gathered i64 [n_ranks, n_queries, 2k] = per rank and query
+ * k fp64 score bit patterns followed by k ids (id < 0 = empty slot).  Saves the unpack / transpose passes between the
+ * collective and the merge (they cost more than the merge itself at 8 GPUs). */
+int b200rag_merge_gathered(const int64_t* gathered, int32_t n_ranks, int32_t n_queries, int32_t k,
+                           double* out_scores, int64_t* out_ids, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Weighted Reciprocal Rank Fusion (K5).  Replaces HybridRetriever._fuse_results (reference
  * retrieval.py:421-491) for a batch.
