@@ -241,8 +241,8 @@ __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishPa
     double* exact = qd + p.dim;                                     // [kprime]
     uint32_t* rows = reinterpret_cast<uint32_t*>(exact + p.kprime);  // [kprime]
     float* approx = reinterpret_cast<float*>(rows + p.kprime);      // [kprime]
-    int* rank_of = reinterpret_cast<int*>(approx + p.kprime);       // [kprime]
-    char* tkmem = reinterpret_cast<char*>(rank_of + p.kprime);
+    int* s_cnt = reinterpret_cast<int*>(approx + p.kprime);         // [n_chunks] fill of this query's buffer in every chunk
+    char* tkmem = reinterpret_cast<char*>(s_cnt + p.n_chunks);
     tkmem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tkmem) + 15) & ~uintptr_t(15));
     __shared__ double s_q2;
     __shared__ float s_err;
@@ -254,27 +254,30 @@ __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishPa
     if (tid == 0) s_err = 0.f;
     __syncthreads();
 
-    // 1. k' best by tensor-core score over all chunks of this query: warp w takes chunks w, w+8, ...; one settle per
-    //    round of 8 chunks x 32 entries (a chunk rarely holds more than a handful of survivors)
+    // 1. k' best by tensor-core score over all chunks of this query.  Chunk fill counts go to shared memory first; then
+    //    warp w takes chunks w, w+8, ... with the NEXT round's entries already in flight while this round's are offered
+    //    (one settle per round of 8 chunks x 32 entries; a chunk rarely holds more than a handful of survivors).
     {
         const int warp = tid >> 5, lane = tid & 31;
         constexpr int NW = FN_THREADS / 32;
+        for (int c = tid; c < p.n_chunks; c += FN_THREADS) s_cnt[c] = p.cand_cnt[((size_t)(c * p.nqb + qb)) * TC_BM + ql];
+        __syncthreads();
+        auto entry = [&](int chunk, int i) -> unsigned long long {
+            return (chunk < p.n_chunks && i < s_cnt[chunk]) ? __ldg(p.cand + (((size_t)(chunk * p.nqb + qb)) * TC_BM + ql) * p.cap + i) : 0ull;
+        };
+        unsigned long long e_cur = entry(warp, lane);
         for (int c0 = 0; c0 < p.n_chunks; c0 += NW) {
             const int chunk = c0 + warp;
-            size_t slot = 0;
-            int n = 0;
-            if (chunk < p.n_chunks) {
-                slot = ((size_t)(chunk * p.nqb + qb)) * TC_BM + ql;
-                n = p.cand_cnt[slot];
-            }
-            const unsigned long long* b = p.cand + slot * p.cap;
-            for (int base = 0; __syncthreads_or(base < n); base += 32) {
-                const int i = base + lane;
-                const bool valid = i < n;
-                unsigned long long e = valid ? b[i] : 0ull;
-                tk.offer(valid, (uint64_t)mono32(__uint_as_float((uint32_t)(e >> 32))), ~(uint32_t)e);
+            const unsigned long long e_next = entry(chunk + NW, lane);
+            const int n = chunk < p.n_chunks ? s_cnt[chunk] : 0;
+            tk.offer(lane < n, (uint64_t)mono32(__uint_as_float((uint32_t)(e_cur >> 32))), ~(uint32_t)e_cur);
+            tk.settle();
+            for (int base = 32; __syncthreads_or(base < n); base += 32) {          // chunks with more than 32 survivors
+                const unsigned long long e = entry(chunk, base + lane);
+                tk.offer(base + lane < n, (uint64_t)mono32(__uint_as_float((uint32_t)(e >> 32))), ~(uint32_t)e);
                 tk.settle();
             }
+            e_cur = e_next;
         }
     }
     __syncthreads();
@@ -301,12 +304,15 @@ __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishPa
         const double* qj = qd + l8;
         for (int i0 = 0; i0 < n; i0 += RB) {
             const int rows_here = min(RB, n - i0);
+            // cp.async: the copies do not pass through registers, so all dim/64 of a thread's 16-byte loads are in flight
             for (int v = tid; v < rows_here * vec_per_row; v += FN_THREADS) {
                 const int r = v / vec_per_row, c = v - r * vec_per_row;
                 const uint32_t row = ~ol[i0 + r];
-                *reinterpret_cast<uint4*>(stage + (size_t)r * stride + c * 16) =
-                    __ldg(reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim) + c);
+                const void* src = reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim) + c;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stage + (size_t)r * stride + c * 16)), "l"(src) : "memory");
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
             const int i = i0 + grp;
             const bool valid = i < n;
@@ -561,7 +567,7 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     pl.s_cap = TC_SAMPLE_R;
     pl.s_topk_cap = BlockTopK<FN_THREADS, uint32_t>::capacity_for(pl.s_rank, FN_THREADS);
     pl.topk_cap = BlockTopK<FN_THREADS, uint32_t>::capacity_for(pl.kprime, FN_THREADS);
-    pl.finish_smem = (size_t)dim * 8 + (size_t)pl.kprime * (8 + 4 + 4 + 4) + 32 +
+    pl.finish_smem = (size_t)dim * 8 + (size_t)pl.kprime * (8 + 4 + 4) + (size_t)pl.n_chunks * 4 + 32 +
                      BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.topk_cap) + 64 +
                      (size_t)(FN_THREADS / 8) * ((size_t)dim * 2 + 16);          // staged candidate rows of one re-score batch
     size_t off = 0;
