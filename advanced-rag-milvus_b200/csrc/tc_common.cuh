@@ -177,8 +177,12 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+// Arrive on a barrier that may live in the peer CTA.  Default semantics (release at CTA scope): what travels through this
+// barrier is "the TMEM accumulator is drained", which tcgen05.fence::before_thread_sync orders.  A cluster-scope release here
+// made every hand-back wait until the thread's candidate stores to global memory were visible cluster-wide (17 % of the
+// scan kernel's stall samples in capture r1g).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
