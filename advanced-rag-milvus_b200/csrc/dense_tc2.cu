@@ -230,7 +230,7 @@ dense_scan2_kernel(const __grid_constant__ CUtensorMap map_x, const ScanParams p
                 const int64_t row0 = (int64_t)tile * p.tile_stride * N_ACC;
                 const uint32_t taddr = lane_taddr + (uint32_t)(Cfg::ACC_COL0 + astage * N_ACC);
                 if (p.sample) epi_sample_tile(taddr, N_ACC / 32, row0, p.n_rows, top);
-                else epi_filter_tile(taddr, N_ACC / 32, row0, p.n_rows, thr, cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane, ec);
+                else epi_filter_tile<N_ACC / 32>(taddr, row0, p.n_rows, thr, cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane, ec);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[astage]);

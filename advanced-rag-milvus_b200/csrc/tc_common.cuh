@@ -88,6 +88,28 @@ __device__ __forceinline__ bool elect_one() {
         "}" : "=r"(pred));
     return pred != 0;
 }
+// Issue a 32-column load without waiting; pair with tmem_ld32_wait(r) before the first use of r.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+// Wait for every tcgen05.ld issued so far.  The registers are in/out operands so that the compiler cannot move a use
+// of them above the wait.
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+          "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+          "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -344,53 +366,72 @@ enum { ST_MMA_TOTAL = 0, ST_MMA_WAIT_FULL, ST_MMA_WAIT_TEMPTY, ST_MMA_WAIT_Q, ST
 // nearly full the warp compacts it to kp entries and raises the threshold.
 struct EpiCounters { long long compact = 0, ncompact = 0, nslow = 0; };
 
-__device__ __forceinline__ void epi_filter_tile(uint32_t taddr, int n_groups, int64_t row0, int64_t n_rows, float& thr, int& cnt,
+__device__ __forceinline__ void epi_filter_group(uint32_t (&r)[32], int c, bool partial, int64_t row0, int64_t n_rows, float& thr,
+                                                 int& cnt, unsigned long long* buf, EpiCounters& ec) {
+    if (partial) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (row0 + c * 32 + i >= n_rows) r[i] = 0xff800000u;      // -inf: never passes
+    }
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) any |= __uint_as_float(r[i]) > thr;
+    if (any) {
+        ++ec.nslow;
+        const uint32_t rbase = (uint32_t)(row0 + c * 32);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (__uint_as_float(r[i]) > thr) {
+                buf[cnt] = ((unsigned long long)r[i] << 32) | (unsigned long long)(rbase + i);
+                ++cnt;
+            }
+        }
+    }
+}
+
+// make room: a lane appends at most 32 entries per column group
+__device__ __forceinline__ void epi_make_room(float& thr, int& cnt, unsigned long long* buf, unsigned int* my_gthr, int kp, int cap,
+                                              uint32_t scratch, int lane, EpiCounters& ec) {
+    unsigned need = __ballot_sync(0xffffffffu, cnt > cap - 32);
+    if (need) {
+        ST_T0(tc0);
+        ec.ncompact += __popc(need);
+        while (need) {
+            const int L = __ffs(need) - 1;
+            need &= need - 1;
+            unsigned long long* b = reinterpret_cast<unsigned long long*>(
+                __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), L));
+            const int n = __shfl_sync(0xffffffffu, cnt, L);
+            const float t = warp_compact(b, n, kp, cap, scratch, lane);
+            if (lane == L) {
+                cnt = kp;
+                thr = fmaxf(thr, t);
+                atomicMax(my_gthr, mono32(t));
+            }
+        }
+        ST_ADD(ec.compact, tc0);
+    }
+}
+
+// The 32-column TMEM loads are software pipelined: while one group of 32 scores is compared, the next is in flight.
+template <int NG>
+__device__ __forceinline__ void epi_filter_tile(uint32_t taddr, int64_t row0, int64_t n_rows, float& thr, int& cnt,
                                                 unsigned long long* buf, unsigned int* my_gthr, int kp, int cap,
                                                 uint32_t scratch, int lane, EpiCounters& ec) {
-    const bool partial = row0 + n_groups * 32 > n_rows;
+    static_assert(NG % 2 == 0, "column groups are processed in pairs");
+    const bool partial = row0 + NG * 32 > n_rows;
+    uint32_t ra[32], rb[32];
+    tmem_ld32_issue(taddr, ra);
 #pragma unroll 1
-    for (int c = 0; c < n_groups; ++c) {
-        // make room: a lane appends at most 32 entries per column group
-        unsigned need = __ballot_sync(0xffffffffu, cnt > cap - 32);
-        if (need) {
-            ST_T0(tc0);
-            ec.ncompact += __popc(need);
-            while (need) {
-                const int L = __ffs(need) - 1;
-                need &= need - 1;
-                unsigned long long* b = reinterpret_cast<unsigned long long*>(
-                    __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), L));
-                const int n = __shfl_sync(0xffffffffu, cnt, L);
-                const float t = warp_compact(b, n, kp, cap, scratch, lane);
-                if (lane == L) {
-                    cnt = kp;
-                    thr = fmaxf(thr, t);
-                    atomicMax(my_gthr, mono32(t));
-                }
-            }
-            ST_ADD(ec.compact, tc0);
-        }
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        if (partial) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (row0 + c * 32 + i >= n_rows) r[i] = 0xff800000u;      // -inf: never passes
-        }
-        bool any = false;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) any |= __uint_as_float(r[i]) > thr;
-        if (any) {
-            ++ec.nslow;
-            const uint32_t rbase = (uint32_t)(row0 + c * 32);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (__uint_as_float(r[i]) > thr) {
-                    buf[cnt] = ((unsigned long long)r[i] << 32) | (unsigned long long)(rbase + i);
-                    ++cnt;
-                }
-            }
-        }
+    for (int c = 0; c < NG; c += 2) {
+        epi_make_room(thr, cnt, buf, my_gthr, kp, cap, scratch, lane, ec);
+        tmem_ld32_wait(ra);
+        tmem_ld32_issue(taddr + (c + 1) * 32, rb);
+        epi_filter_group(ra, c, partial, row0, n_rows, thr, cnt, buf, ec);
+        epi_make_room(thr, cnt, buf, my_gthr, kp, cap, scratch, lane, ec);
+        tmem_ld32_wait(rb);
+        if (c + 2 < NG) tmem_ld32_issue(taddr + (c + 2) * 32, ra);
+        epi_filter_group(rb, c + 1, partial, row0, n_rows, thr, cnt, buf, ec);
     }
 }
 
