@@ -428,8 +428,91 @@ class B200IndexManager:
         c = self.collections[collection_name]
         return {"name": collection_name, "num_entities": c.num_entities, "schema": c.schema, "indexes": list(c.indexes)}
 
+    def _keep_rows(self, keep: np.ndarray) -> None:
+        """Compact every index and the payload to the rows `keep` (ascending row numbers) marks."""
+        rows = np.flatnonzero(keep)
+        dev_rows = torch.as_tensor(rows).to(self.device)
+        for name in ("_sem", "_dom"):
+            old = getattr(self, name)
+            if old.n == 0:
+                continue
+            if old.n != keep.size:
+                raise ValueError("domain index does not cover every row; cannot delete consistently")
+            new = engine.DenseIndex(old.dim, self.dtype, "COSINE", self.device, capacity=rows.size)
+            if rows.size:
+                new.add_prepared(old.rows[dev_rows])
+            setattr(self, name, new)
+        self._dom_rows = self._dom.n
+        self._sp_idx = [self._sp_idx[r] for r in rows]
+        self._sp_val = [self._sp_val[r] for r in rows]
+        self._sp_ptr = [0]
+        for a in self._sp_idx:
+            self._sp_ptr.append(self._sp_ptr[-1] + a.size)
+        self._tok_ids = [self._tok_ids[r] for r in rows]
+        self._tok_ptr = [0]
+        for a in self._tok_ids:
+            self._tok_ptr.append(self._tok_ptr[-1] + a.size)
+        old_p = self.payload
+        self.payload = PayloadStore()
+        for r in rows:
+            self.payload.append(old_p.ids[r], old_p.content[r], {f: old_p.cols[f][r] for f in old_p.cols})
+        self._sparse, self._sparse_dirty, self._tok_dev = None, True, None
+
     async def delete_by_filter(self, collection_name: str, expr: str):
-        raise NotImplementedError("row deletion is not implemented yet (DESIGN.md, 'next' rows)")
+        """Reference MilvusIndexManager.delete_by_filter (indexing.py:692-695: `collection.delete(expr)`).  The three
+        collections hold the same rows here, so the matching rows leave ALL of them (the reference deletes per collection;
+        a chunk missing from one index but not the others is not a state this engine represents).  Returns the count."""
+        if collection_name not in self.collections:
+            raise ValueError(f"Collection {collection_name} not found")
+        mask = _eval_filter(self.payload, expr)
+        n_del = int(mask.sum())
+        if n_del:
+            self._keep_rows(~mask)
+        return n_del
+
+    # ------------------------------------------------------------------------------------------- checkpoint / resume
+    def save(self, path: str) -> None:
+        """Write the whole index (stored 16-bit rows, sparse CSR, token sets, payload) to one torch file.  The reference
+        leaves durability to the Milvus server (collection.flush, indexing.py:430-431)."""
+        state = {
+            "version": 1, "dtype": self.dtype,
+            "dims": (self.semantic_dim, self.sparse_dim, self.domain_dim),
+            "sem": self._sem.rows.cpu(), "dom": self._dom.rows.cpu(),
+            "sp_ptr": np.asarray(self._sp_ptr, dtype=np.int64),
+            "sp_idx": np.concatenate(self._sp_idx) if self._sp_idx else np.zeros(0, np.int64),
+            "sp_val": np.concatenate(self._sp_val) if self._sp_val else np.zeros(0, np.float32),
+            "tok_vocab": self._tok_vocab, "tok_ptr": np.asarray(self._tok_ptr, dtype=np.int64),
+            "tok_ids": np.concatenate(self._tok_ids) if self._tok_ids else np.zeros(0, np.int32),
+            "ids": self.payload.ids, "content": self.payload.content, "cols": self.payload.cols,
+            "sparse_enabled": "sparse_index" in self.collections,
+        }
+        torch.save(state, path)
+
+    @classmethod
+    def load(cls, path: str, device: str = "cuda", **kwargs) -> "B200IndexManager":
+        st = torch.load(path, map_location="cpu", weights_only=False)
+        if st.get("version") != 1:
+            raise ValueError("unknown index file version")
+        sd, pd, dd = st["dims"]
+        m = cls(semantic_dim=sd, sparse_dim=pd, domain_dim=dd, device=device, dtype=st["dtype"],
+                enable_sparse=st["sparse_enabled"], **kwargs)
+        if st["sem"].shape[0]:
+            m._sem.add_prepared(st["sem"])
+        if st["dom"].shape[0]:
+            m._dom.add_prepared(st["dom"])
+        m._dom_rows = m._dom.n
+        sp_ptr, tok_ptr = st["sp_ptr"], st["tok_ptr"]
+        n = len(st["ids"])
+        m._sp_ptr = [int(v) for v in sp_ptr]
+        m._sp_idx = [st["sp_idx"][sp_ptr[r]: sp_ptr[r + 1]] for r in range(n)]
+        m._sp_val = [st["sp_val"][sp_ptr[r]: sp_ptr[r + 1]] for r in range(n)]
+        m._tok_vocab = dict(st["tok_vocab"])
+        m._tok_ptr = [int(v) for v in tok_ptr]
+        m._tok_ids = [st["tok_ids"][tok_ptr[r]: tok_ptr[r + 1]] for r in range(n)]
+        for r in range(n):
+            m.payload.append(st["ids"][r], st["content"][r], {f: st["cols"][f][r] for f in st["cols"]})
+        m._sparse_dirty = True
+        return m
 
     async def close(self):
         self._sparse = None

@@ -94,3 +94,59 @@ def test_auto_equals_exact_mode_at_one_million_rows(eng):
     assert int(f1.sum()) == 0
     assert bool((s1[:, 1:] <= s1[:, :-1]).all())
     assert bool(((s1[:, 1:] < s1[:, :-1]) | (i1[:, 1:] > i1[:, :-1])).all())
+
+
+@pytest.mark.parametrize("b", [129, 257, 520])
+def test_ragged_batches_through_the_pair_kernel(eng, oracle_lib, b):
+    """Batches that do not fill whole 128-query blocks / block pairs (zero-padded query blocks, padded pair)."""
+    s, i, f, err, ref_s, ref_i, qf, rnb = _case(eng, oracle_lib, 70000, 256, b, 20, "f16", seed=b, mode=eng.DENSE_AUTO)
+    assert np.array_equal(i, ref_i) and np.array_equal(s, ref_s)
+    assert f.sum() == 0
+
+
+def test_more_flagged_queries_than_the_first_fallback_tier(eng, oracle_lib):
+    """48 queries that all hit 300-way ties: the device-gated exact fallback must cover tier A (32 slots) and tier B."""
+    o = oracle_lib
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((60, 64)).astype(np.float32)
+    x = np.concatenate([base] * 300)
+    q = base[:48]
+    xb, qb = o.normalize_rows(x, o.F16), o.normalize_rows(q, o.F16)
+    ref_s, ref_i = o.dense_topk(xb, qb, 100, o.F16)
+    idx = eng.DenseIndex(64, "f16", "COSINE", DEV)
+    idx.add(torch.from_numpy(x))
+    s, i, f = idx.search(torch.from_numpy(q), 100, mode=eng.DENSE_AUTO)
+    assert int(f.sum()) == 48
+    assert np.array_equal(i.cpu().numpy(), ref_i) and np.array_equal(s.cpu().numpy(), ref_s)
+
+
+def test_full_size_properties_10m_rows(eng):
+    """BASELINE config 3 at full size (10M x 768 fp16 cosine, top-100, batch 1024) through size-independent properties:
+    the tensor path equals the CUDA-core exact path on a query subset, every list is strictly ordered by (score desc,
+    id asc), no query is flagged, and searching two half shards + the merge kernel reproduces the whole-index result."""
+    n, d, b, k = 10_000_000, 768, 1024, 100
+    g = torch.Generator(device=DEV).manual_seed(7)
+    idx = eng.DenseIndex(d, "f16", "COSINE", DEV, capacity=n)
+    for _ in range(n // 250_000):
+        idx.add(torch.randn(250_000, d, generator=g, device=DEV))
+    q = torch.randn(b, d, generator=g, device=DEV)
+    s, i, f = idx.search(q, k, mode=eng.DENSE_AUTO)
+    assert int(f.sum()) == 0
+    assert bool(((s[:, 1:] < s[:, :-1]) | ((s[:, 1:] == s[:, :-1]) & (i[:, 1:] > i[:, :-1]))).all())
+    assert int(i.min()) >= 0 and int(i.max()) < n
+    sub = torch.tensor([0, 1, 127, 128, 511, 640, 1000, 1023], device=DEV)
+    s2, i2, _ = idx.search(q[sub], k, mode=eng.DENSE_EXACT)
+    assert torch.equal(i[sub], i2) and torch.equal(s[sub], s2)
+    # two half shards (views of the same rows) + merge == whole
+    halves = []
+    q16 = idx.prepare_queries(q)
+    for lo, hi in ((0, n // 2), (n // 2, n)):
+        hs, hi_ids, _ = eng.dense_topk(idx.rows[lo:hi], q16, k, id_offset=lo)
+        halves.append((hs, hi_ids))
+    ms, mi = eng.merge_topk(torch.cat([h[0] for h in halves], 1).contiguous(), torch.cat([h[1] for h in halves], 1).contiguous(), k)
+    assert torch.equal(mi, i) and torch.equal(ms, s)
+    # the same through the all-gather layout the multi-GPU path uses
+    from b200rag import distributed as bdist
+    gathered = torch.stack([bdist.pack_candidates(h[0], h[1]) for h in halves]).contiguous()
+    gs, gi = eng.merge_gathered(gathered, k)
+    assert torch.equal(gi, i) and torch.equal(gs, s)
