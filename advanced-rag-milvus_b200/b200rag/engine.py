@@ -285,13 +285,13 @@ class SparseIndex:
     sort/scan ops (ingest side, not the hot path).
     """
 
-    def __init__(self, doc_ptr, term_ids, weights, n_terms: int, device="cuda", block_docs: int = 32768,
+    def __init__(self, doc_ptr, term_ids, weights, n_terms: int, device="cuda", block_docs: int = 16384,
                  id_offset: int = 0):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("SparseIndex lives on a CUDA device (b200rag has no CPU path)")
-        if block_docs % 32 or not 0 < block_docs <= 65536:
-            raise ValueError("block_docs must be a multiple of 32 in (0, 65536]")
+        if block_docs % 32 or not 0 < block_docs <= 32768:
+            raise ValueError("block_docs must be a multiple of 32 in (0, 32768]")
         def _t(a, np_dtype, t_dtype):           # numpy / list / torch (any device) -> torch tensor of the wanted dtype
             return a.to(t_dtype) if torch.is_tensor(a) else torch.as_tensor(np.asarray(a, dtype=np_dtype))
 

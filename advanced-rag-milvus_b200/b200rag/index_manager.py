@@ -147,7 +147,7 @@ class B200IndexManager:
 
     def __init__(self, semantic_dim: int = 1536, sparse_dim: int = 10000, domain_dim: int = 768,
                  device: str = "cuda", dtype: str = "f16", enable_sparse: Optional[bool] = None,
-                 sparse_block_docs: int = 32768, host: str = "", port: int = 0, connect: bool = True, **_ignored):
+                 sparse_block_docs: int = 16384, host: str = "", port: int = 0, connect: bool = True, **_ignored):
         # host / port / connect / enable_sharding / num_shards are accepted for signature compatibility with
         # MilvusIndexManager(...) (indexing.py:86-96); there is no server to connect to.
         self.semantic_dim, self.sparse_dim, self.domain_dim = int(semantic_dim), int(sparse_dim), int(domain_dim)

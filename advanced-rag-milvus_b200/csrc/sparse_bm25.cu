@@ -1,6 +1,6 @@
 // sparse_bm25.cu -- sparse inner-product (BM25-weighted) top-k over doc-range-blocked postings  (K3).
 //
-// One CTA (1024 threads) owns one QUERY and walks the document blocks of its slice one after the other:
+// One CTA (512 threads) owns one QUERY and walks the document blocks of its slice one after the other:
 //   * the block's per-document accumulators live in shared memory (fp32, block_docs <= 32768 -> 128 KB) and are zeroed
 //     once per CTA; collecting a block's candidates puts them back to zero;
 //   * the postings of up to 8 query terms inside the block are fetched TOGETHER (one coalesced u16 doc + f32 weight per
@@ -23,10 +23,10 @@ namespace b200rag {
 int launch_merge(const double* cand_scores, const int64_t* cand_ids, int n_launch, const int32_t* q_list, int n_cand, int k,
                  double* out_scores_f64, float* out_scores_f32, int64_t* out_ids, int32_t* out_counts, cudaStream_t st);
 
-constexpr int SP_THREADS = 1024;
+constexpr int SP_THREADS = 512;     // with 16384-document blocks two CTAs fit per SM and overlap each other's latencies
 constexpr int SP_TG = 8;       // query terms fetched together (one register pair per term and thread)
 
-__global__ void __launch_bounds__(SP_THREADS, 1)
+__global__ void __launch_bounds__(SP_THREADS, 2)
 sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __restrict__ post_doc,
                     const float* __restrict__ post_w, int64_t n_docs, int n_terms, int block_docs, int n_blocks, int n_slices,
                     const int64_t* __restrict__ q_ptr, const int32_t* __restrict__ q_terms, const float* __restrict__ q_vals,
@@ -110,7 +110,7 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
                 __syncthreads();
             }
         }
-        // ---- collect: a thread owns words tid and tid + 1024 of the bitmap ---------------------------------------
+        // ---- collect: a thread owns words tid and tid + SP_THREADS of the bitmap ---------------------------------------
         unsigned long long m = 0;
         if (tid < n_words) { m = touched[tid]; touched[tid] = 0u; }
         if (tid + SP_THREADS < n_words) { m |= (unsigned long long)touched[tid + SP_THREADS] << 32; touched[tid + SP_THREADS] = 0u; }
@@ -179,8 +179,8 @@ int b200rag_sparse_topk(const int64_t* blk_term_ptr, const uint16_t* post_doc, c
                         void* workspace, size_t workspace_bytes, void* stream) {
     B200_REQUIRE(blk_term_ptr && q_ptr && out_scores && out_ids && out_counts && workspace, "sparse_topk: null pointer");
     B200_REQUIRE(n_docs >= 0 && n_terms > 0 && n_queries >= 0 && k > 0, "sparse_topk: bad sizes");
-    B200_REQUIRE(block_docs > 0 && block_docs <= 65536 && block_docs % 32 == 0,
-                 "sparse_topk: block_docs must be a multiple of 32 in (0, 65536], got %d", block_docs);
+    B200_REQUIRE(block_docs > 0 && block_docs <= 64 * SP_THREADS && block_docs % 32 == 0,
+                 "sparse_topk: block_docs must be a multiple of 32 in (0, %d], got %d", 64 * SP_THREADS, block_docs);
     if (n_queries == 0) return B200RAG_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int cap = 0;

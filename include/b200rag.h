@@ -111,7 +111,7 @@ int b200rag_debug_scan_stats(int32_t enable, uint64_t* out_host, int32_t max_cta
  * Sparse inner-product top-k over doc-range-blocked postings (K3).  Replaces Collection.search on
  * "sparse_index" (reference indexing.py:472,487-498,505-523, reached from retrieval.py:367-395).
  * Postings layout ("blocked CSR"): documents are cut into blocks of `block_docs` consecutive rows
- * (block_docs <= 65536); inside block b the postings of term t occupy
+ * (block_docs <= 32768; 16384 lets two CTAs share an SM); inside block b the postings of term t occupy
  *   [blk_term_ptr[b*(n_terms+1)+t], blk_term_ptr[b*(n_terms+1)+t+1])  of post_doc / post_w,
  * post_doc holding the row index RELATIVE to the block start (u16), ascending.
  * Queries are a CSR over terms: q_ptr i64 [n_queries+1], q_terms i32 ascending per query, q_vals f32.

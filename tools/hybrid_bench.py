@@ -28,7 +28,7 @@ ap.add_argument("--depth", type=int, default=500)
 ap.add_argument("--k", type=int, default=100)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--skip", default="")
-ap.add_argument("--block-docs", type=int, default=32768)
+ap.add_argument("--block-docs", type=int, default=16384)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 HBM = 6545e9
