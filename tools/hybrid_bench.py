@@ -140,6 +140,45 @@ if "c4" not in args.skip:
     del dense, sparse, doc_ptr, term_ids, tok_ptr, tok_ids
     torch.cuda.empty_cache()
 
+if "c1" not in args.skip:
+    # BASELINE config 1: 100K chunks, 384-d, BM25 over a 30K-term vocabulary, alpha 0.7, top_k 20 (dense top-40 + sparse top-40
+    # -> RRF -> top 20), on the GPU in batches of 256 and on the host cores through the oracle's restatement of the chain.
+    from oracle import pipeline as opipe
+    n1, d1, v1, b1, tk = 100_000, 384, 30_000, 256, 20
+    x = synth.dense_rows(n1, d1, 0)
+    dp, ti, tf = synth.zipf_corpus(n1, v1, 0)
+    w = bm25.bm25_weights(dp, ti, tf, v1)
+    dense = engine.DenseIndex(d1, "f16", "COSINE", dev)
+    dense.add(torch.from_numpy(x))
+    sparse = engine.SparseIndex(dp, ti, w, v1, dev, block_docs=args.block_docs)
+    q = synth.dense_rows(b1, d1, 1000)
+    qp, qt, qv = synth.zipf_queries(b1, v1, 1, n_terms=8, skip_top=100)
+    qd = torch.from_numpy(q).to(dev)
+    wts = torch.tensor([[0.7, 0.3]] * b1, dtype=torch.float64, device=dev)
+
+    def c1_step():
+        ds, di, _ = dense.search(qd, 2 * tk)
+        ss, si, sc = sparse.search(qp, qt, qv, 2 * tk)
+        li = torch.stack([di, si]).contiguous()
+        ln = torch.stack([torch.full((b1,), 2 * tk, dtype=torch.int32, device=dev), sc]).contiguous()
+        return engine.rrf_fuse(li, ln, wts)
+
+    t_c1, fused = timed(c1_step, args.reps)
+    corpus = opipe.ArrayCorpus(x, None, dp, ti, w, v1, None)
+    n_cpu = 40
+    t0 = time.time()
+    same = True
+    for r in range(n_cpu):
+        sq = {"indices": qt[qp[r]:qp[r + 1]].tolist(), "values": qv[qp[r]:qp[r + 1]].tolist()}
+        ids, scs, _ = opipe.retrieve(corpus, q[r], sq, None, tk)
+        same &= fused.ids[r, :tk].cpu().tolist() == ids and fused.scores[r, :tk].cpu().tolist() == scs
+    t_cpu = (time.time() - t0) / n_cpu
+    out["c1"] = {"gpu_ms_per_batch": t_c1, "gpu_qps": b1 / t_c1 * 1e3, "cpu_port_ms_per_query": t_cpu * 1e3, "cpu_port_qps": 1.0 / t_cpu,
+                 "cpu_cores": os.cpu_count(), "bit_exact_vs_oracle_pipeline": bool(same), "checked_queries": n_cpu}
+    print("c1", json.dumps(out["c1"]), flush=True)
+    del dense, sparse
+    torch.cuda.empty_cache()
+
 for name, (n, d, b, k, metric) in (("c2", (1_000_000, 768, 1024, 100, "IP")), ("c5_shard", (12_500_000, 384, 4096, 10, "COSINE"))):
     if name in args.skip:
         continue
