@@ -240,8 +240,7 @@ __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishPa
     double* qd = reinterpret_cast<double*>(smem);                   // [dim]
     double* exact = qd + p.dim;                                     // [kprime]
     uint32_t* rows = reinterpret_cast<uint32_t*>(exact + p.kprime);  // [kprime]
-    float* approx = reinterpret_cast<float*>(rows + p.kprime);      // [kprime]
-    int* s_cnt = reinterpret_cast<int*>(approx + p.kprime);         // [n_chunks] fill of this query's buffer in every chunk
+    int* s_cnt = reinterpret_cast<int*>(rows + p.kprime);           // [n_chunks] fill of this query's buffer in every chunk
     char* tkmem = reinterpret_cast<char*>(s_cnt + p.n_chunks);
     tkmem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tkmem) + 15) & ~uintptr_t(15));
     __shared__ double s_q2;
@@ -567,7 +566,7 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     pl.s_cap = TC_SAMPLE_R;
     pl.s_topk_cap = BlockTopK<FN_THREADS, uint32_t>::capacity_for(pl.s_rank, FN_THREADS);
     pl.topk_cap = BlockTopK<FN_THREADS, uint32_t>::capacity_for(pl.kprime, FN_THREADS);
-    pl.finish_smem = (size_t)dim * 8 + (size_t)pl.kprime * (8 + 4 + 4) + (size_t)pl.n_chunks * 4 + 32 +
+    pl.finish_smem = (size_t)dim * 8 + (size_t)pl.kprime * (8 + 4) + (size_t)pl.n_chunks * 4 + 32 +
                      BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.topk_cap) + 64 +
                      (size_t)(FN_THREADS / 8) * ((size_t)dim * 2 + 16);          // staged candidate rows of one re-score batch
     size_t off = 0;
