@@ -17,6 +17,8 @@
 //   4. the bitset is cleared again (only the picked document's words).
 // Work = picks x candidates x tokens per candidate bitset probes; the shared-memory bank conflicts of the random probes
 // (~3.5 wavefronts per 32 probes) are the bound.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200rag {
@@ -258,6 +260,211 @@ mmr_select_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict
     for (int i = done + tid; i < k_max; i += nthreads) out_pick[(size_t)q * k_max + i] = -1;
 }
 
+// ----------------------------------------------------------------------------------------------- fast path (n <= 1024)
+// One THREAD per candidate, the thread <-> candidate assignment fixed for the whole query, all per-candidate state
+// (relevance, running max similarity, list length, high-bit boundaries) in registers.  Candidates are counting-sorted by
+// token-list length so that the 32 candidates of a warp have (nearly) equal lengths; their lists are cached TRANSPOSED in
+// shared memory -- token p of the warp's 32 candidates is contiguous -- so the per-step token load is one conflict-free
+// 64-byte access and every lane does useful work: ~10 warp instructions per 32 probes, no cross-lane reduction, and the
+// fp64 division runs on all lanes at once.  (The warp-per-candidate kernel above spends ~1.5 warp instructions per probe.)
+constexpr int MMT_THREADS = 1024;
+constexpr int MMT_LEN_BINS = 1024;
+
+__global__ void __launch_bounds__(MMT_THREADS, 1)
+mmr_select_sorted_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict__ cand_rel, const int32_t* __restrict__ cand_n,
+                         int n_max, const int64_t* __restrict__ doc_tok_ptr, const int32_t* __restrict__ doc_tok_ids, int vocab_words,
+                         const double* __restrict__ lambda, const int32_t* __restrict__ k_sel, int k_max,
+                         int32_t* __restrict__ out_pick, int32_t* __restrict__ out_n, int cache_cap, int n_hi) {
+    extern __shared__ __align__(16) char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = blockIdx.x;
+    uint32_t* bits = reinterpret_cast<uint32_t*>(smem);                              // [vocab_words]
+    uint16_t* cache = reinterpret_cast<uint16_t*>(bits + vocab_words);               // [cache_cap]
+    __shared__ int s_hist[MMT_LEN_BINS];
+    __shared__ uint16_t s_owner[MMT_THREADS];
+    __shared__ int s_wsum[32], s_glen[32], s_goff[33];
+    __shared__ double s_best[32];
+    __shared__ int s_best_idx[32];
+    __shared__ int s_pick, s_done, s_pick_len;
+    __shared__ long long s_pick_begin;
+
+    const int n = min(min(cand_n[q], n_max), MMT_THREADS);
+    const int k = min(min(k_sel[q], k_max), n);
+    const double lam = lambda[q];
+    const double one_minus = __dsub_rn(1.0, lam);
+    const int32_t* docs = cand_doc + (size_t)q * n_max;
+
+    // ---- counting sort of the candidates by list length -------------------------------------------------------
+    s_hist[tid] = 0;
+    s_owner[tid] = 0xffff;
+    for (int i = tid; i < vocab_words; i += MMT_THREADS) bits[i] = 0u;
+    if (tid == 0) s_done = 0;
+    __syncthreads();
+    int key = 0;
+    if (tid < n) {
+        const int64_t b0 = doc_tok_ptr[docs[tid]];
+        const int len = (int)(doc_tok_ptr[docs[tid] + 1] - b0);
+        key = len < MMT_LEN_BINS - 1 ? len : MMT_LEN_BINS - 1;
+        atomicAdd(&s_hist[key], 1);
+    }
+    __syncthreads();
+    {
+        const int v = s_hist[tid];
+        int incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int u = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += u;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = s_wsum[lane];
+            int wi = w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int u = __shfl_up_sync(FULL, wi, off);
+                if (lane >= off) wi += u;
+            }
+            s_wsum[lane] = wi - w;                       // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        s_hist[tid] = incl - v + s_wsum[warp];           // first position of this length
+    }
+    __syncthreads();
+    if (tid < n) s_owner[atomicAdd(&s_hist[key], 1)] = (uint16_t)tid;
+    __syncthreads();
+
+    // ---- this thread's candidate, for the rest of the kernel ----------------------------------------------------
+    const int c = tid < n ? (int)s_owner[tid] : -1;      // original candidate index (fused order), -1: idle thread
+    double rel = 0.0, max_sim = 0.0;
+    long long tbeg = 0;
+    int len = 0;
+    bool alive = c >= 0;
+    if (alive) {
+        rel = cand_rel[(size_t)q * n_max + c];
+        tbeg = doc_tok_ptr[docs[c]];
+        len = (int)(doc_tok_ptr[docs[c] + 1] - tbeg);
+    }
+    // group (= warp) geometry: every list of the group is padded to the longest one
+    int glen = len;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) glen = max(glen, __shfl_xor_sync(FULL, glen, off));
+    if (lane == 0) s_glen[warp] = glen;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = s_glen[lane] * 32;
+        int wi = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int u = __shfl_up_sync(FULL, wi, off);
+            if (lane >= off) wi += u;
+        }
+        s_goff[lane] = wi - w;
+        if (lane == 31) s_goff[32] = wi;
+    }
+    __syncthreads();
+    const int goff = s_goff[warp];
+    const bool cached = glen > 0 && goff + glen * 32 <= cache_cap && glen < 65536;
+    // fill (warp-cooperative, coalesced reads): candidate j of the group -> column j of the transposed block
+    int bnd0 = 0x7fffffff, bnd1 = 0x7fffffff;            // token p has high bits  (p >= bnd0) + (p >= bnd1)
+    if (cached) {
+        for (int j = 0; j < 32; ++j) {
+            const long long tb = __shfl_sync(FULL, tbeg, j);
+            const int lj = __shfl_sync(FULL, len, j);
+            int below0 = 0, below1 = 0;
+            for (int i = lane; i < lj; i += 32) {
+                const int t = __ldg(doc_tok_ids + tb + i);
+                cache[goff + i * 32 + j] = (uint16_t)(t & 0xffff);
+                below0 += (t >> 16) <= 0;
+                below1 += (t >> 16) <= 1;
+            }
+            below0 = __reduce_add_sync(FULL, below0);
+            below1 = __reduce_add_sync(FULL, below1);
+            if (lane == j) { if (n_hi >= 1) bnd0 = below0; if (n_hi >= 2) bnd1 = below1; }
+        }
+    }
+    __syncthreads();
+
+    for (int step = 0; step < k; ++step) {
+        // ---- 1. argmax with "earliest wins" ---------------------------------------------------------------------
+        double best = -1e9;
+        int best_i = 0x7fffffff;
+        if (alive) {
+            const double sc = step == 0 ? rel : __dsub_rn(__dmul_rn(lam, rel), __dmul_rn(one_minus, max_sim));
+            if (sc > best) { best = sc; best_i = c; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ob = __shfl_xor_sync(FULL, best, off);
+            const int oi = __shfl_xor_sync(FULL, best_i, off);
+            if (mmr_better(ob, oi, best, best_i)) { best = ob; best_i = oi; }
+        }
+        if (lane == 0) { s_best[warp] = best; s_best_idx[warp] = best_i; }
+        __syncthreads();
+        if (warp == 0) {
+            double b = s_best[lane];
+            int bi = s_best_idx[lane];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ob = __shfl_xor_sync(FULL, b, off);
+                const int oi = __shfl_xor_sync(FULL, bi, off);
+                if (mmr_better(ob, oi, b, bi)) { b = ob; bi = oi; }
+            }
+            if (lane == 0) {
+                s_pick = bi;
+                if (bi != 0x7fffffff) {
+                    out_pick[(size_t)q * k_max + step] = bi;
+                    s_done = step + 1;
+                }
+            }
+        }
+        __syncthreads();
+        const int pick = s_pick;
+        if (pick == 0x7fffffff) break;                    // nothing beat -1e9 (the reference would fail here too)
+        if (step + 1 == k) break;
+        if (c == pick) { alive = false; s_pick_len = len; s_pick_begin = tbeg; }
+        __syncthreads();
+        // ---- 2. raise the picked document's tokens --------------------------------------------------------------
+        const long long ps = s_pick_begin;
+        const int len_p = s_pick_len;
+        for (int i = tid; i < len_p; i += MMT_THREADS) {
+            const int t = doc_tok_ids[ps + i];
+            atomicOr(&bits[t >> 5], 1u << (t & 31));
+        }
+        __syncthreads();
+        // ---- 3. every thread intersects its own candidate -------------------------------------------------------
+        if (alive) {
+            int inter = 0;
+            if (cached) {
+                const uint16_t* col = cache + goff + lane;
+#pragma unroll 4
+                for (int p = 0; p < len; ++p) {
+                    const int t = (((p >= bnd0) + (p >= bnd1)) << 16) | col[p * 32];
+                    inter += (bits[t >> 5] >> (t & 31)) & 1u;
+                }
+            } else {
+                const int32_t* toks = doc_tok_ids + tbeg;
+#pragma unroll 4
+                for (int p = 0; p < len; ++p) {
+                    const int t = __ldg(toks + p);
+                    inter += (bits[t >> 5] >> (t & 31)) & 1u;
+                }
+            }
+            const int uni = len + len_p - inter;
+            const double jac = __ddiv_rn((double)inter, (double)(uni ? uni : 1));
+            if (jac > max_sim) max_sim = jac;
+        }
+        __syncthreads();
+        // ---- 4. clear (the next raise happens two barriers later) -------------------------------------------------
+        for (int i = tid; i < len_p; i += MMT_THREADS) bits[doc_tok_ids[ps + i] >> 5] = 0u;
+    }
+    __syncthreads();
+    const int done = s_done;
+    if (tid == 0) out_n[q] = done;
+    for (int i = done + tid; i < k_max; i += MMT_THREADS) out_pick[(size_t)q * k_max + i] = -1;
+}
+
 }  // namespace b200rag
 
 using namespace b200rag;
@@ -278,6 +485,22 @@ int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const in
     int vocab_words = (vocab_size + 31) / 32;
     // tokens >= (n_hi << 16) do not exist; n_hi thresholds per candidate give the high bits of cached tokens back
     int n_hi = (vocab_size - 1) >> 16;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_max >= 32 && n_max <= MMT_THREADS && n_hi <= 2 && getenv("B200RAG_MMR_WARP") == nullptr) {
+        // fast path: one thread per candidate, transposed token cache (static shared memory of the kernel: ~7 KB)
+        const size_t limit = 227 * 1024 - 8192;
+        const size_t bits_bytes = (size_t)vocab_words * 4;
+        if (bits_bytes + 65536 <= limit) {
+            const int cap = (int)((limit - bits_bytes) / 2);
+            const size_t smem_t = bits_bytes + (size_t)cap * 2;
+            B200_CUDA_CHECK(cudaFuncSetAttribute(mmr_select_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+            mmr_select_sorted_kernel<<<n_queries, MMT_THREADS, smem_t, st>>>(cand_doc, cand_rel, cand_n, n_max, doc_tok_ptr, doc_tok_ids,
+                                                                              vocab_words, lambda, k_sel, k_max, out_pick, out_n, cap, n_hi);
+            count_launch();
+            B200_CUDA_CHECK(cudaGetLastError());
+            return B200RAG_OK;
+        }
+    }
     size_t fixed = (size_t)n_max * (8 + 8 + 8 + 4 + 4) + (size_t)vocab_words * 4 + 64;
     size_t smem = fixed;
     if (smem > 225 * 1024) {
@@ -294,7 +517,6 @@ int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const in
         }
     }
     if (cache_cap == 0) n_hi = 0;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     B200_CUDA_CHECK(cudaFuncSetAttribute(mmr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // one warp per candidate in the intersection phase: as many warps as there are candidates, up to 32
     const int threads = n_max >= 32 ? MMR_MAX_THREADS : (n_max >= 8 ? 256 : 128);

@@ -245,3 +245,29 @@ def test_mmr_batch_matches_oracle_random(eng):
     for q in range(b):
         ref = fusion.mmr_select(list(rel_pq[q]), [fusion.tokens(t) for t in contents_pq[q]], k[q], lam[q])
         assert picks[q, : int(n[q])].cpu().tolist() == ref, q
+
+
+@pytest.mark.parametrize("force_warp_kernel", [False, True])
+def test_mmr_config4_scale_matches_oracle(eng, monkeypatch, force_warp_kernel):
+    """BASELINE config-4 shape for the diversification: ~1000 candidates with ~90 unique tokens each out of a 100K-term
+    Zipf vocabulary (token ids beyond 65535 exercise the 16-bit token cache), lambda 0.7, k = 100.  Both MMR kernels
+    (thread-per-candidate fast path, warp-per-candidate general path) against the oracle restatement of the reference."""
+    from b200rag import synth
+    from oracle import fusion
+    if force_warp_kernel:
+        monkeypatch.setenv("B200RAG_MMR_WARP", "1")
+    vocab, n_docs, b, n_max, k = 100_000, 4000, 3, 1000, 100
+    dp, ti, _ = synth.zipf_corpus(n_docs, vocab, 3)
+    rng = np.random.default_rng(17)
+    cand = np.stack([rng.choice(n_docs, size=n_max, replace=False) for _ in range(b)]).astype(np.int32)
+    n = np.asarray([n_max, 997, 640], np.int32)
+    rel = np.sort(rng.random((b, n_max)) * 0.016, axis=1)[:, ::-1].copy()
+    rel[1, 5] = rel[1, 4]                                   # an exact relevance tie: the earlier candidate must win
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    picks, pn = eng.mmr_select(t(cand), t(rel), t(n), t(dp), t(ti.astype(np.int32)), vocab,
+                               t(np.asarray([0.7, 0.5, 0.8])), t(np.asarray([k, k, 37], np.int32)), k)
+    assert int(ti.max()) > 65535
+    for q in range(b):
+        sets = [frozenset(ti[dp[d]: dp[d + 1]].tolist()) for d in cand[q, : n[q]]]
+        ref = fusion.mmr_select(list(rel[q, : n[q]]), sets, [k, k, 37][q], [0.7, 0.5, 0.8][q])
+        assert picks[q, : int(pn[q])].cpu().tolist() == ref, q
