@@ -552,14 +552,23 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     // TC_SAMPLE_R best 32-row group maxima per (chunk, query) in registers, and the s_rank-th best over all chunks becomes
     // the query's starting threshold.  About s_rank * s_stride rows of the whole corpus beat it; that product is held
     // near 6 k' (enough to contain the top-k' with overwhelming probability, few enough that appends and compactions in
-    // the full scan are rare).
-    pl.s_rank = (6 * pl.kprime + 63) / 64;
-    if (pl.s_rank < 8) pl.s_rank = 8;
-    if (pl.s_rank > TC_SAMPLE_R) pl.s_rank = TC_SAMPLE_R;
-    pl.s_stride = (6 * pl.kprime + pl.s_rank - 1) / pl.s_rank;
-    if (pl.s_stride < 64) pl.s_stride = 64;
+    // the full scan are rare); the stride adapts to the corpus (1/128 of the tiles for large ones, >= 8 sampled tiles).
+    {
+        const int target = 6 * pl.kprime;                       // survivors per query the threshold should leave
+        int stride = pl.n_tiles / 8;
+        if (stride > 128) stride = 128;
+        if (stride < 16) stride = 16;
+        int rank = (target + stride - 1) / stride;
+        if (rank > TC_SAMPLE_R) { rank = TC_SAMPLE_R; stride = (target + rank - 1) / rank; }
+        if (rank < 8) {                                         // below 8 the order statistic is too noisy (needless fallbacks):
+            rank = 8;                                           // sample more densely instead
+            stride = target / 8 > 16 ? target / 8 : 16;
+        }
+        pl.s_rank = rank;
+        pl.s_stride = stride;
+    }
     pl.s_tiles = pl.n_tiles / pl.s_stride;
-    pl.sample = pl.s_tiles >= 8 && env_int("B200RAG_NO_SAMPLE", 0) == 0;
+    pl.sample = pl.s_tiles >= 4 && env_int("B200RAG_NO_SAMPLE", 0) == 0;
     pl.s_chunks = want < pl.s_tiles ? want : (pl.s_tiles > 0 ? pl.s_tiles : 1);
     pl.s_items = qgroups * pl.s_chunks;
     pl.s_kprime = TC_SAMPLE_R;
