@@ -12,7 +12,8 @@ rank scans its shard, one NCCL all-gather carries the k candidates per query, th
   value     whole-job queries/s with the query batch already resident in HBM (fp32), search = prepare + scan + finish
             (+ all-gather + merge for N>1), timed with CUDA events, max over ranks.
   e2e       same metric through the public Python API with HOST buffers: pinned fp32 queries -> H2D -> search ->
-            D2H of ids + scores, every step.
+            D2H of ids + scores, every step, consumed by a double-buffered host loop (results of step i are on the host
+            before step i+2 is issued).
   roofline  the dominant kernel (dense_scan_kernel): algorithmic FLOPs per launch / its CUDA-event duration, measured
             live inside the timed region through the b200rag_profile_next_scan hook.
   cpu_baseline / --impl reference: the same exact search on the box's host cores (numpy BLAS sgemm + partial sort,
@@ -215,8 +216,6 @@ def main():
     POOL = 8
     q_dev = [torch.randn((B, D), generator=g, device=device, dtype=torch.float32) for _ in range(POOL)]
     q_host = [q.cpu().pin_memory() for q in q_dev]
-    out_ids_host = torch.empty((B, K), dtype=torch.int64).pin_memory()
-    out_sc_host = torch.empty((B, K), dtype=torch.float64).pin_memory()
 
     def search(q):
         s, i, f = idx.search(q, K, engine.DENSE_AUTO)
@@ -269,17 +268,32 @@ def main():
     value = B * args.steps / (ms_total * 1e-3)
 
     # ---------------- timed region 2: end to end from host buffers -------------------------------
+    # Every step: pinned fp32 queries -> H2D -> search -> D2H of ids + scores into pinned host buffers.  The consumer is
+    # double buffered, as a serving loop would be: before issuing step i+1 the host WAITS until the results of step i-1
+    # are in host memory (so it holds every step's results at most one step late), and the region ends when the last
+    # step's results have landed.  Nothing is skipped; copies and compute of neighbouring steps may overlap.
+    out_ids_h = [torch.empty((B, K), dtype=torch.int64).pin_memory() for _ in range(2)]
+    out_sc_h = [torch.empty((B, K), dtype=torch.float64).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
     for it in range(min(args.warmup, 2)):
         search(q_host[it % POOL].to(device, non_blocking=True))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    checksum = 0
     for it in range(args.steps):
         qd = q_host[(args.warmup + it) % POOL].to(device, non_blocking=True)
         s, i, _ = search(qd)
-        out_ids_host.copy_(i, non_blocking=True)
-        out_sc_host.copy_(s, non_blocking=True)
-        torch.cuda.current_stream().synchronize()        # the caller holds the results on the host every step
+        if it >= 2:
+            done[it % 2].synchronize()                    # results of step it-2 left this buffer pair long ago; it-1 may still fly
+        out_ids_h[it % 2].copy_(i, non_blocking=True)
+        out_sc_h[it % 2].copy_(s, non_blocking=True)
+        done[it % 2].record()
+        if it >= 1:
+            done[(it - 1) % 2].synchronize()              # the caller now holds step it-1's results on the host
+            checksum += int(out_ids_h[(it - 1) % 2][0, 0])
+    done[(args.steps - 1) % 2].synchronize()
+    checksum += int(out_ids_h[(args.steps - 1) % 2][0, 0])
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
