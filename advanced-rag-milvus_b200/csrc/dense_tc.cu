@@ -551,24 +551,18 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     // strided SAMPLE pass that seeds the per-query thresholds: every s_stride-th tile is scored, the epilogue keeps the
     // TC_SAMPLE_R best 32-row group maxima per (chunk, query) in registers, and the s_rank-th best over all chunks becomes
     // the query's starting threshold.  About s_rank * s_stride rows of the whole corpus beat it; that product is held
-    // near 6 k' (enough to contain the top-k' with overwhelming probability, few enough that appends and compactions in
-    // the full scan are rare); the stride adapts to the corpus (1/128 of the tiles for large ones, >= 8 sampled tiles).
-    {
-        const int target = 6 * pl.kprime;                       // survivors per query the threshold should leave
-        int stride = pl.n_tiles / 8;
-        if (stride > 128) stride = 128;
-        if (stride < 16) stride = 16;
-        int rank = (target + stride - 1) / stride;
-        if (rank > TC_SAMPLE_R) { rank = TC_SAMPLE_R; stride = (target + rank - 1) / rank; }
-        if (rank < 8) {                                         // below 8 the order statistic is too noisy (needless fallbacks):
-            rank = 8;                                           // sample more densely instead
-            stride = target / 8 > 16 ? target / 8 : 16;
-        }
-        pl.s_rank = rank;
-        pl.s_stride = stride;
-    }
+    // near 12 k' (see below).
+    // Sizing.  The threshold is the r-th best of a 1/stride sample, so the number of corpus rows above it is about
+    // stride * Gamma(r): with r = 16 and r * stride = 12 k' the chance that fewer than k' rows survive (the query is then
+    // flagged and re-run on the slow exact path) is P(Gamma(16) < 4/3) ~ 1e-12 per query; at r = 8, 6 k' it was 6e-5 and
+    // showed up as a handful of fallbacks per thousand batches.  Small corpora cap the stride (>= 4 sampled tiles); below
+    // r * stride = 8 k' the pass is skipped.
+    pl.s_rank = TC_SAMPLE_R;
+    pl.s_stride = 12 * pl.kprime / TC_SAMPLE_R;
+    if (pl.s_stride > pl.n_tiles / 4) pl.s_stride = pl.n_tiles / 4;
+    if (pl.s_stride < 1) pl.s_stride = 1;
     pl.s_tiles = pl.n_tiles / pl.s_stride;
-    pl.sample = pl.s_tiles >= 4 && env_int("B200RAG_NO_SAMPLE", 0) == 0;
+    pl.sample = pl.s_tiles >= 4 && pl.s_rank * pl.s_stride >= 8 * pl.kprime && env_int("B200RAG_NO_SAMPLE", 0) == 0;
     pl.s_chunks = want < pl.s_tiles ? want : (pl.s_tiles > 0 ? pl.s_tiles : 1);
     pl.s_items = qgroups * pl.s_chunks;
     pl.s_kprime = TC_SAMPLE_R;
