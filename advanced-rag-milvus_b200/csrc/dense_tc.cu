@@ -218,6 +218,7 @@ struct FinishParams {
     int nqb;
     int n_chunks;
     int topk_cap;        // BlockTopK capacity
+    int stage_rows;      // candidate rows staged per re-score batch (<= FN_THREADS / 8; fewer for very wide vectors)
     int64_t id_offset;
     double row_norm_bound;
     const unsigned long long* cand;
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishPa
     //    oracle/exact_scan.c does), and the lanes are combined in the canonical tree with shuffles.
     float my_err = 0.f;
     {
-        constexpr int RB = FN_THREADS / 8;                       // rows per batch
+        const int RB = p.stage_rows;                             // rows per batch (<= FN_THREADS / 8)
         const int l8 = tid & 7, grp = tid >> 3;
         const int vec_per_row = p.dim / 8;                        // 16-byte vectors per row
         const int stride = p.dim * 2 + 16;                        // staged row pitch: +16 bytes keeps the 4 rows of a warp on different banks
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishPa
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
             const int i = i0 + grp;
-            const bool valid = i < n;
+            const bool valid = i < n && grp < RB;
             const uint16_t* x = reinterpret_cast<const uint16_t*>(stage + (size_t)grp * stride) + l8;
             double acc = 0.0;
             if (valid) {
@@ -475,6 +476,7 @@ int launch_scan3(const void* corpus16, int dtype, const ScanParams& sp, int max_
 struct TensorPlan {
     int sm_count, version, cs, tile_rows, nqb, n_tiles, n_chunks, n_items, kprime, cap, topk_cap, max_ctas, qg_span;
     int sample, s_stride, s_tiles, s_chunks, s_items, s_kprime, s_cap, s_rank, s_topk_cap;   // strided sample pass
+    int stage_rows;
     size_t scan_smem, finish_smem;
     size_t off_cand, off_cnt, off_gthr, off_flaglist, off_nflag, off_stats, off_qpad, off_exact, total;
 };
@@ -570,8 +572,10 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     pl.s_topk_cap = BlockTopK<FN_THREADS, uint32_t>::capacity_for(pl.s_rank, FN_THREADS);
     pl.topk_cap = BlockTopK<FN_THREADS, uint32_t>::capacity_for(pl.kprime, FN_THREADS);
     pl.finish_smem = (size_t)dim * 8 + (size_t)pl.kprime * (8 + 4) + (size_t)pl.n_chunks * 4 + 32 +
-                     BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.topk_cap) + 64 +
-                     (size_t)(FN_THREADS / 8) * ((size_t)dim * 2 + 16);          // staged candidate rows of one re-score batch
+                     BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.topk_cap) + 64;
+    pl.stage_rows = FN_THREADS / 8;                             // staged candidate rows of one re-score batch
+    while (pl.stage_rows > 1 && pl.finish_smem + (size_t)pl.stage_rows * ((size_t)dim * 2 + 16) > 160 * 1024) pl.stage_rows /= 2;
+    pl.finish_smem += (size_t)pl.stage_rows * ((size_t)dim * 2 + 16);
     size_t off = 0;
     auto take = [&](size_t bytes) { off = align_up(off, 256); size_t o = off; off += bytes; return o; };
     const int max_chunks = pl.n_chunks > pl.s_chunks ? pl.n_chunks : pl.s_chunks;
@@ -724,6 +728,7 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
     fp.nqb = pl.nqb;
     fp.n_chunks = n_rows > 0 ? pl.n_chunks : 0;
     fp.topk_cap = pl.topk_cap;
+    fp.stage_rows = pl.stage_rows;
     fp.id_offset = id_offset;
     fp.row_norm_bound = row_norm_bound;
     fp.cand = reinterpret_cast<const unsigned long long*>(ws + pl.off_cand);

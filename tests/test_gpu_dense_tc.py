@@ -45,6 +45,9 @@ def _case(eng, o, n, d, b, k, dt, seed, metric="COSINE", mode=None):
     (100000, 768, 256, 100, "f16"),
     (60000, 384, 1024, 10, "f16"),    # 8 query blocks, config-5-like k
     (30000, 128, 16, 500, "f16"),     # deep candidate list (config-4-like K)
+    (6000, 1536, 70, 20, "f16"),      # the reference's default semantic_dim (indexing.py:61-77)
+    (3000, 4096, 130, 10, "bf16"),    # very wide vectors: 64 k-blocks, fewer staged rows in the re-score
+    (2000, 8, 9, 5, "f16"),           # narrowest vectors the ABI accepts
 ])
 def test_tensor_path_matches_oracle(eng, oracle_lib, n, d, b, k, dt):
     s, i, f, err, ref_s, ref_i, qf, rnb = _case(eng, oracle_lib, n, d, b, k, dt, seed=n + d + b)
@@ -150,3 +153,19 @@ def test_full_size_properties_10m_rows(eng):
     gathered = torch.stack([bdist.pack_candidates(h[0], h[1]) for h in halves]).contiguous()
     gs, gi = eng.merge_gathered(gathered, k)
     assert torch.equal(gi, i) and torch.equal(gs, s)
+
+
+def test_random_shapes_against_oracle(eng, oracle_lib):
+    """Seeded fuzz over shapes, dtypes, metrics and modes (AUTO path): ids and fp64 scores bit-exact every time."""
+    rng = np.random.default_rng(2024)
+    for case in range(14):
+        d = int(rng.integers(1, 66)) * 8
+        n = int(rng.choice([1, 7, 255, 256, 257, int(rng.integers(300, 30000))]))
+        b = int(rng.choice([1, 2, 127, 128, 129, int(rng.integers(1, 400))]))
+        k = int(rng.integers(1, 150))
+        dt = str(rng.choice(["f16", "bf16"]))
+        metric = str(rng.choice(["COSINE", "IP"]))
+        s, i, f, err, ref_s, ref_i, qf, rnb = _case(eng, oracle_lib, n, d, b, k, dt, seed=1000 + case, metric=metric,
+                                                    mode=eng.DENSE_AUTO)
+        assert np.array_equal(i, ref_i), (case, n, d, b, k, dt, metric)
+        assert np.array_equal(s, ref_s), (case, n, d, b, k, dt, metric)
