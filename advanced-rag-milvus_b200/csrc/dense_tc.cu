@@ -304,12 +304,14 @@ __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishPa
         const double* qj = qd + l8;
         for (int i0 = 0; i0 < n; i0 += RB) {
             const int rows_here = min(RB, n - i0);
-            // cp.async: the copies do not pass through registers, so all dim/64 of a thread's 16-byte loads are in flight
-            for (int v = tid; v < rows_here * vec_per_row; v += FN_THREADS) {
-                const int r = v / vec_per_row, c = v - r * vec_per_row;
+            // cp.async: the copies do not pass through registers, so all of a thread's 16-byte loads are in flight.
+            // Warp w copies rows w, w + 8, ...; its lanes stride over the row's 16-byte vectors.
+            for (int r = tid >> 5; r < rows_here; r += FN_THREADS / 32) {
                 const uint32_t row = ~ol[i0 + r];
-                const void* src = reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim) + c;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stage + (size_t)r * stride + c * 16)), "l"(src) : "memory");
+                const uint4* src = reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim);
+                const uint32_t dst = smem_u32(stage + (size_t)r * stride);
+                for (int c = tid & 31; c < vec_per_row; c += 32)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * 16), "l"(src + c) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -574,6 +576,7 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     pl.finish_smem = (size_t)dim * 8 + (size_t)pl.kprime * (8 + 4) + (size_t)pl.n_chunks * 4 + 32 +
                      BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.topk_cap) + 64;
     pl.stage_rows = FN_THREADS / 8;                             // staged candidate rows of one re-score batch
+    { int sr = env_int("B200RAG_STAGE_ROWS", 0); if (sr == 8 || sr == 16 || sr == 32) pl.stage_rows = sr; }
     while (pl.stage_rows > 1 && pl.finish_smem + (size_t)pl.stage_rows * ((size_t)dim * 2 + 16) > 160 * 1024) pl.stage_rows /= 2;
     pl.finish_smem += (size_t)pl.stage_rows * ((size_t)dim * 2 + 16);
     size_t off = 0;
