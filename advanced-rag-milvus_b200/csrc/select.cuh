@@ -99,6 +99,11 @@ struct BlockTopK {
     __device__ __forceinline__ bool passes(uint64_t h, LoT l) const {
         return !st->has_thr || key_gt<LoT>(h, l, st->thr_hi, (LoT)st->thr_lo);
     }
+    // For keys whose hi word is mono32(score): the score of the current k-th best, or -inf while fewer than k were seen.
+    // Anything strictly below it can be dropped without building a key.
+    __device__ __forceinline__ float threshold_hi32_as_float() const {
+        return st->has_thr ? unmono32((uint32_t)st->thr_hi) : -CUDART_INF_F;
+    }
     // Barrier + (when the next round could overflow) compaction.  All threads must call.  Ends synchronised.
     __device__ __forceinline__ void settle() {
         __syncthreads();

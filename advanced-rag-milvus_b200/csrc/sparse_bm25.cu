@@ -110,26 +110,32 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
                 __syncthreads();
             }
         }
-        // ---- collect: a thread owns words tid and tid + SP_THREADS of the bitmap ---------------------------------------
+        // ---- collect: a thread owns words tid and tid + SP_THREADS of the bitmap -----------------------------------
+        // Losers are dropped with ONE float compare against the running k-th best score (read once per block; the exact
+        // (score, id) comparison happens only for the few candidates at or above it).
         unsigned long long m = 0;
         if (tid < n_words) { m = touched[tid]; touched[tid] = 0u; }
         if (tid + SP_THREADS < n_words) { m |= (unsigned long long)touched[tid + SP_THREADS] << 32; touched[tid + SP_THREADS] = 0u; }
+        float thr_f = tk.threshold_hi32_as_float();
         while (__syncthreads_or(m != 0ull)) {
             bool have = false;
             uint64_t h = 0;
             uint32_t l = 0;
             while (m) {
-                const int bpos = __ffsll((long long)m) - 1;
+                const uint32_t lo32 = (uint32_t)m;
+                const int bpos = lo32 ? __ffs((int)lo32) - 1 : 32 + __ffs((int)(uint32_t)(m >> 32)) - 1;
                 m &= m - 1;
                 const int d = bpos < 32 ? tid * 32 + bpos : (tid + SP_THREADS) * 32 + (bpos - 32);
                 const float sc = acc[d];
                 acc[d] = 0.0f;
+                if (sc < thr_f) continue;
                 h = (uint64_t)mono32(sc);
                 l = ~(uint32_t)(doc0 + d);
                 if (tk.passes(h, l)) { have = true; break; }
             }
             tk.offer(have, h, l);
             tk.settle();
+            thr_f = tk.threshold_hi32_as_float();
         }
     }
     __syncthreads();
