@@ -8,6 +8,7 @@ int run_exact(const void* corpus16, int64_t n_rows, int dim, int dtype, const vo
               const int32_t* q_list, int k, int64_t id_offset, double* out_scores, int64_t* out_ids,
               void* workspace, size_t workspace_bytes, cudaStream_t st, const int32_t* n_active, int slot_base);
 size_t tensor_workspace_bytes(int64_t n_rows, int dim, int n_q, int k);
+bool tensor_supported(int64_t n_rows, int dim, int n_q, int k);
 int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_q, int k,
                int64_t id_offset, double* out_scores, int64_t* out_ids, int32_t* out_flags, double row_norm_bound,
                float* out_err, int with_fallback, void* workspace, size_t workspace_bytes, cudaStream_t st);
@@ -31,6 +32,7 @@ int b200rag_debug_scan_stats(int32_t enable, uint64_t* out_host, int32_t max_cta
 size_t b200rag_dense_topk_workspace_bytes(int64_t n_rows, int32_t dim, int32_t n_queries, int32_t k, int32_t mode) {
     if (n_rows < 0 || dim <= 0 || n_queries < 0 || k <= 0) return 0;
     if (mode == B200RAG_DENSE_EXACT) return exact_workspace_bytes(n_rows, dim, n_queries, k);
+    if (mode == B200RAG_DENSE_AUTO && !tensor_supported(n_rows, dim, n_queries, k)) return exact_workspace_bytes(n_rows, dim, n_queries, k);
     return tensor_workspace_bytes(n_rows, dim, n_queries, k);
 }
 
@@ -51,6 +53,7 @@ int b200rag_dense_topk(const void* corpus16, int64_t n_rows, int32_t dim, int32_
                  "dense_topk: corpus/queries must be 16-byte aligned and the workspace 256-byte aligned");
     if (n_queries == 0) return B200RAG_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mode == B200RAG_DENSE_AUTO && !tensor_supported(n_rows, dim, n_queries, k)) mode = B200RAG_DENSE_EXACT;   // e.g. k > 1000
     if (mode == B200RAG_DENSE_EXACT) {
         if (out_flags) B200_CUDA_CHECK(cudaMemsetAsync(out_flags, 0, (size_t)n_queries * sizeof(int32_t), st));
         if (out_err) B200_CUDA_CHECK(cudaMemsetAsync(out_err, 0, (size_t)n_queries * sizeof(float), st));

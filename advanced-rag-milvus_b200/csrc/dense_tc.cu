@@ -601,6 +601,13 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
 
 size_t tensor_workspace_bytes(int64_t n_rows, int dim, int n_q, int k) { return plan_tensor(n_rows, dim, n_q, k).total; }
 
+// Can the tensor-core path serve this shape?  (k beyond the candidate-buffer limit, or more rows than 32-bit local row
+// numbers address, go to the exact CUDA-core scan; AUTO mode does that on its own.)
+bool tensor_supported(int64_t n_rows, int dim, int n_q, int k) {
+    const TensorPlan pl = plan_tensor(n_rows, dim, n_q, k);
+    return !(pl.cap > TC_MAX_C || pl.scan_smem > TC_SMEM_LIMIT || n_rows >= ((int64_t)1 << 32) - TC_BN);
+}
+
 static bool g_stats_enabled = false;
 static unsigned long long* g_stats_last = nullptr;
 int scan_stats(int enable, unsigned long long* out_host, int max_ctas) {

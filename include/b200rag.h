@@ -83,7 +83,9 @@ int b200rag_prepare_rows(const float* in_f32, void* out16, int64_t n_rows, int32
  *   out_scores f64 [n_queries, k]  canonical scores;  out_ids i64 [n_queries, k] = local row + id_offset
  *   out_flags  i32 [n_queries] or NULL: bit0 = the tensor-core candidate set could not be PROVEN complete for
  *              this query (near-ties beyond the slack); in AUTO mode such queries were re-run on the exact path,
- *              so results are always exact and the flag is informational.
+ *              so results are always exact and the flag is informational.  AUTO never synchronises with the host: the
+ *              fallback is launched unconditionally and gated on the device by the number of flagged queries.  Shapes
+ *              the tensor-core path cannot serve (k > ~1000) are routed to the exact scan by AUTO on its own.
  *   row_norm_bound  upper bound on the L2 norm of any stored row (1.001 for rows prepared with normalize=1); it
  *              sizes the error margin of the completeness proof of the tensor-core path.  Ignored in EXACT mode.
  *   out_err    f32 [n_queries] or NULL: max |tensor-core score - canonical score| over the re-scored candidates

@@ -169,3 +169,9 @@ def test_random_shapes_against_oracle(eng, oracle_lib):
                                                     mode=eng.DENSE_AUTO)
         assert np.array_equal(i, ref_i), (case, n, d, b, k, dt, metric)
         assert np.array_equal(s, ref_s), (case, n, d, b, k, dt, metric)
+
+
+def test_auto_mode_serves_k_beyond_the_tensor_path_limit(eng, oracle_lib):
+    """k = 1500 exceeds the candidate-buffer limit of the tensor-core scan; AUTO must route to the exact scan by itself."""
+    s, i, f, err, ref_s, ref_i, qf, rnb = _case(eng, oracle_lib, 9000, 64, 5, 1500, "f16", seed=77, mode=eng.DENSE_AUTO)
+    assert np.array_equal(i, ref_i) and np.array_equal(s, ref_s) and f.sum() == 0
