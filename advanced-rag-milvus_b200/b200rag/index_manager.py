@@ -142,12 +142,72 @@ def _eval_filter(store: PayloadStore, expr: str) -> np.ndarray:
     return mask
 
 
+class _MicroBatcher:
+    """Turns concurrent one-query `search` awaits into GPU-sized batches.
+
+    The reference serves one query per call with up to 64 requests in flight (service.py:149) and hops to a thread for
+    every Milvus call (indexing.py:505).  Here the awaits that arrive within `max_wait_s` of each other (or until `max_batch`
+    of them are queued) for the same (collection, top_k, filter) are answered by ONE `search_batch` call, which runs on a
+    single worker thread so that the event loop stays responsive and GPU calls never overlap."""
+
+    def __init__(self, manager: "B200IndexManager", max_batch: int, max_wait_s: float):
+        import concurrent.futures as cf
+        self.m, self.max_batch, self.max_wait_s = manager, int(max_batch), float(max_wait_s)
+        self.pending: Dict[Tuple, List[Tuple[Any, "asyncio.Future"]]] = {}
+        self.timers: Dict[Tuple, Any] = {}
+        self.pool = cf.ThreadPoolExecutor(max_workers=1, thread_name_prefix="b200rag-batch")
+        self.batches = 0                                   # number of search_batch calls issued (observability / tests)
+
+    async def submit(self, query: Any, collection: str, top_k: int, filters: Optional[str]) -> List[Dict[str, Any]]:
+        loop = asyncio.get_running_loop()
+        key = (collection, int(top_k), filters)
+        fut = loop.create_future()
+        self.pending.setdefault(key, []).append((query, fut))
+        if len(self.pending[key]) >= self.max_batch:
+            self._flush(key)
+        elif key not in self.timers:
+            self.timers[key] = loop.call_later(self.max_wait_s, self._flush, key)
+        return await fut
+
+    def _flush(self, key: Tuple) -> None:
+        timer = self.timers.pop(key, None)
+        if timer is not None:
+            timer.cancel()
+        items = self.pending.pop(key, [])
+        if not items:
+            return
+        collection, top_k, filters = key
+        queries = [q for q, _ in items]
+        batch: Any = queries if collection == "sparse_index" else np.stack([np.asarray(q, dtype=np.float32).reshape(-1) for q in queries])
+        loop = asyncio.get_running_loop()
+        self.batches += 1
+        task = loop.run_in_executor(self.pool, self.m.search_batch, batch, collection, top_k, filters)
+
+        def deliver(done):
+            try:
+                results = done.result()
+            except Exception as e:  # noqa: BLE001 - every waiter of the batch sees the failure
+                for _, f in items:
+                    if not f.done():
+                        f.set_exception(e)
+                return
+            for (_, f), hits in zip(items, results):
+                if not f.done():
+                    f.set_result(hits)
+
+        task.add_done_callback(deliver)
+
+    def close(self) -> None:
+        self.pool.shutdown(wait=False)
+
+
 class B200IndexManager:
     """Device-resident semantic / sparse / domain indexes behind the reference's index-manager duck type."""
 
     def __init__(self, semantic_dim: int = 1536, sparse_dim: int = 10000, domain_dim: int = 768,
                  device: str = "cuda", dtype: str = "f16", enable_sparse: Optional[bool] = None,
-                 sparse_block_docs: int = 16384, host: str = "", port: int = 0, connect: bool = True, **_ignored):
+                 sparse_block_docs: int = 16384, host: str = "", port: int = 0, connect: bool = True,
+                 micro_batch: bool = False, max_batch: int = 256, max_wait_ms: float = 0.5, **_ignored):
         # host / port / connect / enable_sharding / num_shards are accepted for signature compatibility with
         # MilvusIndexManager(...) (indexing.py:86-96); there is no server to connect to.
         self.semantic_dim, self.sparse_dim, self.domain_dim = int(semantic_dim), int(sparse_dim), int(domain_dim)
@@ -157,6 +217,7 @@ class B200IndexManager:
         engine._lib.load()                                   # fail loudly when the CUDA library is missing
         self.dtype = dtype
         self.embedding_generator = None                      # set externally, as in the reference (indexing.py:119)
+        self._batcher = _MicroBatcher(self, max_batch, max_wait_ms * 1e-3) if micro_batch else None
         self.payload = PayloadStore()
         self._sem = engine.DenseIndex(self.semantic_dim, dtype, "COSINE", self.device)
         self._dom = engine.DenseIndex(self.domain_dim, dtype, "COSINE", self.device)
@@ -389,8 +450,12 @@ class B200IndexManager:
         if collection_name == "sparse_index":
             if not (isinstance(query_embedding, dict) or hasattr(query_embedding, "tocsr")):
                 raise ValueError("Sparse query embedding must be dict with indices/values or a scipy.sparse matrix")
+            if self._batcher is not None:
+                return await self._batcher.submit(query_embedding, collection_name, top_k, filters)
             batch: Any = [query_embedding]
         else:
+            if self._batcher is not None:
+                return await self._batcher.submit(query_embedding, collection_name, top_k, filters)
             batch = np.asarray(query_embedding, dtype=np.float32).reshape(1, -1)
         return self.search_batch(batch, collection_name, top_k, filters, search_params)[0]
 
@@ -515,5 +580,7 @@ class B200IndexManager:
         return m
 
     async def close(self):
+        if self._batcher is not None:
+            self._batcher.close()
         self._sparse = None
         self._tok_dev = None

@@ -108,24 +108,28 @@ class B200HybridRetriever:
     async def _retrieve_inner(self, query: str, filters: Optional[Dict[str, Any]] = None, use_domain_index: bool = False,
                               domain: Optional[str] = None, profile_hint: Optional[str] = None) -> List[Dict[str, Any]]:
         profile_name = self._pick_profile(query, profile_hint)
-        self.config = self.profiles.get(profile_name, self.config)      # per-request config, as in the reference (:281-284)
+        # per-request config.  The reference assigns it to self.config (:281-284) and reads it back after every await, which
+        # races when requests overlap on one retriever; here the request keeps its own reference and
+        # self.config is only updated for callers that inspect it afterwards.
+        cfg = self.profiles.get(profile_name, self.config)
+        self.config = cfg
         semantic_emb = await self._get_semantic_embedding(query)
         sparse_emb = await self._get_sparse_embedding(query)
         filter_expr = self._build_filter_expression(filters) if filters else None
-        tasks = [self._search_semantic(semantic_emb, filter_expr), self._search_sparse(sparse_emb, filter_expr)]
+        tasks = [self._search_semantic(semantic_emb, filter_expr, cfg), self._search_sparse(sparse_emb, filter_expr, cfg)]
         if use_domain_index and domain:
-            tasks.append(self._search_domain(await self._get_domain_embedding(query, domain), filter_expr))
+            tasks.append(self._search_domain(await self._get_domain_embedding(query, domain), filter_expr, cfg))
         lists = await asyncio.gather(*tasks)
-        self._adapt_weights(query, self.config)
+        self._adapt_weights(query, cfg)
         fused = self._fuse_results(semantic_results=lists[0], sparse_results=lists[1],
-                                   domain_results=lists[2] if len(lists) > 2 else [])
+                                   domain_results=lists[2] if len(lists) > 2 else [], cfg=cfg)
         for r in fused:
             meta = r.get("metadata")
             if isinstance(meta, dict):
                 meta.setdefault("retrieval_profile", profile_name)
             else:
                 r["retrieval_profile"] = profile_name
-        return fused[: self.config.top_k]
+        return fused[: cfg.top_k]
 
     async def _tagged_search(self, embedding, collection: str, top_k: int, filters, params, method: str):
         try:
@@ -138,27 +142,28 @@ class B200HybridRetriever:
             h["original_score"] = h["score"]
         return hits
 
-    async def _search_semantic(self, embedding, filters: Optional[str]) -> List[Dict[str, Any]]:
-        return await self._tagged_search(embedding, "semantic_index", self.config.top_k * 2, filters,
-                                         self.config.semantic_search_params, "semantic")
+    async def _search_semantic(self, embedding, filters: Optional[str], cfg: Optional[RetrievalConfig] = None) -> List[Dict[str, Any]]:
+        cfg = cfg or self.config
+        return await self._tagged_search(embedding, "semantic_index", cfg.top_k * 2, filters, cfg.semantic_search_params, "semantic")
 
-    async def _search_sparse(self, embedding, filters: Optional[str]) -> List[Dict[str, Any]]:
+    async def _search_sparse(self, embedding, filters: Optional[str], cfg: Optional[RetrievalConfig] = None) -> List[Dict[str, Any]]:
+        cfg = cfg or self.config
         collections = getattr(self.index_manager, "collections", None)
         if collections is not None and "sparse_index" not in collections:
             return []
-        return await self._tagged_search(embedding, "sparse_index", self.config.top_k * 2, filters,
-                                         self.config.sparse_search_params, "sparse")
+        return await self._tagged_search(embedding, "sparse_index", cfg.top_k * 2, filters, cfg.sparse_search_params, "sparse")
 
-    async def _search_domain(self, embedding, filters: Optional[str]) -> List[Dict[str, Any]]:
-        return await self._tagged_search(embedding, "domain_index", self.config.top_k, filters,
-                                         self.config.semantic_search_params, "domain")
+    async def _search_domain(self, embedding, filters: Optional[str], cfg: Optional[RetrievalConfig] = None) -> List[Dict[str, Any]]:
+        cfg = cfg or self.config
+        return await self._tagged_search(embedding, "domain_index", cfg.top_k, filters, cfg.semantic_search_params, "domain")
 
     # ------------------------------------------------------------------------------------------- fusion (GPU)
     def _fuse_results(self, semantic_results: List[Dict], sparse_results: List[Dict],
-                      domain_results: Optional[List[Dict]] = None) -> List[Dict[str, Any]]:
+                      domain_results: Optional[List[Dict]] = None, cfg: Optional[RetrievalConfig] = None) -> List[Dict[str, Any]]:
         """Weighted RRF of up to three ranked hit lists on the GPU; result dicts as the reference builds them."""
+        cfg = cfg or self.config
         lists = [semantic_results or [], sparse_results or []] + ([domain_results] if domain_results else [])
-        weights = [self.config.dense_weight, self.config.sparse_weight, DOMAIN_WEIGHT][: len(lists)]
+        weights = [cfg.dense_weight, cfg.sparse_weight, DOMAIN_WEIGHT][: len(lists)]
         code: Dict[Any, int] = {}
         for lst in lists:
             for h in lst:
@@ -199,8 +204,8 @@ class B200HybridRetriever:
                 except Exception:  # noqa: BLE001 - unparsable timestamps are skipped (:481-483)
                     pass
             out.append(r)
-        if self.config.enable_mmr and out:
-            return self._mmr_diversify(out, self.config.top_k, self.config.mmr_lambda)
+        if cfg.enable_mmr and out:
+            return self._mmr_diversify(out, cfg.top_k, cfg.mmr_lambda)
         return out
 
     def _mmr_diversify(self, ranked: List[Dict[str, Any]], k: int, mmr_lambda: float) -> List[Dict[str, Any]]:
