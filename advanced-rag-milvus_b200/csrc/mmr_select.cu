@@ -437,11 +437,25 @@ mmr_select_sorted_kernel(const int32_t* __restrict__ cand_doc, const double* __r
         if (alive) {
             int inter = 0;
             if (cached) {
+                // the list is sorted, so its tokens with high bits 0 / 1 / 2 are three consecutive runs: one loop per run,
+                // each probing the 2048-word slice of the bitset that belongs to its high bits (no per-token select)
                 const uint16_t* col = cache + goff + lane;
+                const int e0 = min(bnd0, len), e1 = min(bnd1, len);
+                int p = 0;
 #pragma unroll 4
-                for (int p = 0; p < len; ++p) {
-                    const int t = (((p >= bnd0) + (p >= bnd1)) << 16) | col[p * 32];
+                for (; p < e0; ++p) {
+                    const uint32_t t = col[p * 32];
                     inter += (bits[t >> 5] >> (t & 31)) & 1u;
+                }
+                const uint32_t* bits1 = bits + 2048;
+                for (; p < e1; ++p) {
+                    const uint32_t t = col[p * 32];
+                    inter += (bits1[t >> 5] >> (t & 31)) & 1u;
+                }
+                const uint32_t* bits2 = bits + 4096;
+                for (; p < len; ++p) {
+                    const uint32_t t = col[p * 32];
+                    inter += (bits2[t >> 5] >> (t & 31)) & 1u;
                 }
             } else {
                 const int32_t* toks = doc_tok_ids + tbeg;

@@ -18,6 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("report")
 ap.add_argument("func", help="substring of the mangled kernel name, e.g. dense_finish_kernelILi1")
 ap.add_argument("--top", type=int, default=25)
+ap.add_argument("--kernel", default=None, help="regex selecting one kernel of a multi-kernel report (ncu -k regex:...)")
 ap.add_argument("--lib", default=os.path.join(ROOT, "advanced-rag-milvus_b200", "b200rag", "libb200rag.so"))
 args = ap.parse_args()
 
@@ -43,7 +44,8 @@ for cubin in glob.glob(os.path.join(tmp, "*.cubin")):
 if lines is None:
     raise SystemExit(f"function matching {args.func!r} not found in {args.lib}")
 
-out = subprocess.run(["ncu", "-i", args.report, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+cmd = ["ncu", "-i", args.report, "--page", "source", "--csv"] + (["-k", "regex:" + args.kernel] if args.kernel else [])
+out = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
