@@ -466,11 +466,6 @@ int make_tensor_map(CUtensorMap* map, const void* base, int64_t rows, int dim, i
     return B200RAG_OK;
 }
 
-bool scan2_supported(int dim);
-int scan2_tile_rows(int dim);
-size_t scan2_smem_bytes(int cap);
-int scan2_max_clusters(int dim, int cap, int cs, int sm_count);
-int launch_scan2(const void* corpus16, int dtype, const ScanParams& sp, int cs, int max_ctas, cudaStream_t st, int* grid_out);
 size_t scan3_smem_bytes(int cap, int span);
 int scan3_max_clusters(int cap, int span, int sm_count);
 int launch_scan3(const void* corpus16, int dtype, const ScanParams& sp, int max_clusters, int span_cap, int span_max, cudaStream_t st);
@@ -506,11 +501,13 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     pl.nqb = (n_q + TC_BM - 1) / TC_BM;
     pl.kprime = tc_kprime(k);
     pl.cap = tc_bufcap(pl.kprime);
-    // kernel generation: 3 = CTA pairs (tcgen05 cta_group::2, dense_tc3.cu) is the product path; 1 (single CTA, this file)
-    // and 2 (query block in TMEM + multicast, dense_tc2.cu) are kept selectable for A/B measurements.
-    pl.version = pl.nqb >= 2 ? 3 : 1;     // a single query block cannot fill a pair's M = 256
+    // kernel generation: 3 = CTA pairs (tcgen05 cta_group::2, dense_tc3.cu) serves two or more query blocks; 1 (single CTA,
+    // this file) serves a single block (a pair's M = 256 cannot be filled) and stays selectable for A/B measurements.
+    // (A generation 2 -- query block resident in TMEM, TS-mode MMA with N = 64 accumulators, multicast corpus tiles -- was
+    // measured at 0.8 PFLOP/s, MMA-issue bound, and removed; it is in the history at commit 1cee701.)
+    pl.version = pl.nqb >= 2 ? 3 : 1;
     int forced = env_int("B200RAG_SCAN_VERSION", 0);
-    if (forced == 1 || forced == 3 || (forced == 2 && scan2_supported(dim))) pl.version = forced;
+    if (forced == 1 || forced == 3) pl.version = forced;
     int units;                                              // co-resident scheduling units (CTAs or clusters)
     int qgroups;
     if (pl.version == 3) {
@@ -526,15 +523,6 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
         units = scan3_max_clusters(pl.cap, pl.qg_span, pl.sm_count);
         pl.max_ctas = units * 2;
         pl.scan_smem = scan3_smem_bytes(pl.cap, pl.qg_span);
-    } else if (pl.version == 2) {
-        pl.tile_rows = scan2_tile_rows(dim);
-        pl.cs = pl.nqb % 4 == 0 ? 4 : (pl.nqb % 2 == 0 ? 2 : 1);
-        int fcs = env_int("B200RAG_CLUSTER", 0);
-        if ((fcs == 1 || fcs == 2 || fcs == 4 || fcs == 8) && pl.nqb % fcs == 0) pl.cs = fcs;
-        units = scan2_max_clusters(dim, pl.cap, pl.cs, pl.sm_count);
-        qgroups = pl.nqb / pl.cs;
-        pl.max_ctas = units * pl.cs;
-        pl.scan_smem = scan2_smem_bytes(pl.cap);
     } else {
         pl.tile_rows = TC_BN;
         pl.cs = 1;
@@ -680,7 +668,6 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
         }
         auto launch = [&](const ScanParams& spx) -> int {
             if (pl.version == 3) return launch_scan3(corpus16, dtype, spx, pl.max_ctas / 2, pl.cap, pl.qg_span, st);
-            if (pl.version == 2) return launch_scan2(corpus16, dtype, spx, pl.cs, pl.max_ctas, st, nullptr);
             int grid = spx.n_items < pl.sm_count ? spx.n_items : pl.sm_count;
             dense_scan_kernel<<<grid, TC_THREADS, pl.scan_smem, st>>>(map_q, map_x, spx); count_launch();
             B200_CUDA_CHECK(cudaGetLastError());

@@ -349,8 +349,7 @@ def main():
                     traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        scan_kernel = {"1": "dense_scan_kernel", "2": "dense_scan2_kernel"}.get(os.environ.get("B200RAG_SCAN_VERSION", ""),
-                                                                                  "dense_scan3_kernel")
+        scan_kernel = "dense_scan_kernel" if os.environ.get("B200RAG_SCAN_VERSION", "") == "1" else "dense_scan3_kernel"
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

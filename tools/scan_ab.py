@@ -24,7 +24,7 @@ ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--k", type=int, default=100)
 ap.add_argument("--dtype", default="f16")
 ap.add_argument("--reps", type=int, default=60)
-ap.add_argument("--configs", default="3:0:0,3:0:1,3:0:2,1:0:0,3:0:0")
+ap.add_argument("--configs", default="3:0:0,3:0:1,3:0:2,1:0:0,3:0:0", help="version:unused:span, comma separated")
 ap.add_argument("--mode", default="auto", choices=["auto", "tensor"])
 args = ap.parse_args()
 dev = "cuda:0"
