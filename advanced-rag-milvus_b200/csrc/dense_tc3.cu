@@ -1,6 +1,6 @@
 // dense_tc3.cu -- tensor-core scan, third generation: CTA PAIRS (tcgen05.mma.cta_group::2).
 //
-// Why (profiles/r1_scan_v1.md): the single-CTA kernel moves 48 KB from L2 into shared memory for every
+// Why (profiles/r1_scan3_ncu.md, history table): the single-CTA kernel moves 48 KB from L2 into shared memory for every
 // 128 x 256 x 64 block of multiply-adds (a 16 KB query tile + a 32 KB corpus tile) -- 12x the corpus size per scan at
 // batch 1024, ~11 TB/s of L2->SM traffic -- and the board sits on its power cap at ~0.95 GHz.  Two SMs of one TPC
 // can issue ONE MMA of M = 256 (two query blocks) x N = 256 (corpus rows) in which each CTA supplies its own 128
