@@ -1,7 +1,7 @@
 """Multi-GPU parity check (run under torchrun on a GPU box): the row-sharded search + NCCL all-gather + merge kernel must
 return exactly what the CPU oracle returns for the whole corpus, on every rank.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dist_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tests/scripts/dist_check.py
 """
 import os
 import sys
@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "advanced-rag-milvus_b200")]
 from b200rag import distributed as bdist  # noqa: E402
 from oracle import oracle  # noqa: E402

@@ -5,7 +5,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "advanced-rag-milvus_b200")]
 from b200rag import engine  # noqa: E402
 from oracle import oracle  # noqa: E402
