@@ -86,10 +86,22 @@ def prepare_rows(x_f32: torch.Tensor, dtype, normalize: bool, out: Optional[torc
     return out
 
 
+def pack_row_mask(allowed: torch.Tensor) -> torch.Tensor:
+    """bool [n] (device) -> the bit mask the *_masked entry points take: int32 [ceil(n / 32)], bit (row & 31) of word row >> 5."""
+    _require_cuda(allowed, "allowed")
+    n = allowed.numel()
+    pad = (-n) % 32
+    bits = torch.nn.functional.pad(allowed.to(torch.int64).view(-1), (0, pad)).view(-1, 32)
+    weights = torch.ones(32, dtype=torch.int64, device=allowed.device) << torch.arange(32, device=allowed.device)
+    words = (bits * weights).sum(dim=1)                              # 0 .. 2^32 - 1
+    return torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).contiguous()
+
+
 def dense_topk(corpus16: torch.Tensor, queries16: torch.Tensor, k: int, id_offset: int = 0, mode: int = DENSE_AUTO,
-               n_rows: Optional[int] = None, row_norm_bound: float = 1.001, out_err: Optional[torch.Tensor] = None
-               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Exact top-k of stored rows.  Returns (scores f64 [B,k], ids i64 [B,k], flags i32 [B])."""
+               n_rows: Optional[int] = None, row_norm_bound: float = 1.001, out_err: Optional[torch.Tensor] = None,
+               row_mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Exact top-k of stored rows (of the rows `row_mask` allows, see pack_row_mask).  Returns (scores f64 [B,k],
+    ids i64 [B,k], flags i32 [B])."""
     _require_cuda(corpus16, "corpus")
     _require_cuda(queries16, "queries")
     code = dtype_code(corpus16.dtype)
@@ -108,14 +120,19 @@ def dense_topk(corpus16: torch.Tensor, queries16: torch.Tensor, k: int, id_offse
     flags = torch.empty((b,), dtype=torch.int32, device=dev)      # every mode writes all b entries
     if out_err is not None and (out_err.dtype != torch.float32 or out_err.numel() < b or not out_err.is_cuda):
         raise ValueError("out_err must be a CUDA float32 tensor with one entry per query")
+    if row_mask is not None:
+        _require_cuda(row_mask, "row_mask")
+        if row_mask.dtype != torch.int32 or row_mask.numel() < (n + 31) // 32:
+            raise ValueError("row_mask must be an int32 tensor with one bit per row (engine.pack_row_mask)")
     L = _lib.load()
     with torch.cuda.device(dev):
         nbytes = L.b200rag_dense_topk_workspace_bytes(n, dim, b, k, mode)
         ws = _WS.get(dev, nbytes)
-        check(L.b200rag_dense_topk(corpus16.data_ptr(), n, dim, code, queries16.data_ptr(), b, k, id_offset,
-                                   scores.data_ptr(), ids.data_ptr(), flags.data_ptr(), float(row_norm_bound),
-                                   out_err.data_ptr() if out_err is not None else None,
-                                   ws.data_ptr(), ws.numel(), mode, _stream_ptr(dev)))
+        check(L.b200rag_dense_topk_masked(corpus16.data_ptr(), n, dim, code, queries16.data_ptr(), b, k, id_offset,
+                                          scores.data_ptr(), ids.data_ptr(), flags.data_ptr(), float(row_norm_bound),
+                                          out_err.data_ptr() if out_err is not None else None,
+                                          row_mask.data_ptr() if row_mask is not None else None,
+                                          ws.data_ptr(), ws.numel(), mode, _stream_ptr(dev)))
     return scores, ids, flags
 
 
@@ -267,14 +284,17 @@ class DenseIndex:
             q = q[None, :]
         return prepare_rows(q.contiguous(), self.code, self.metric == "COSINE")
 
-    def search(self, queries_f32: torch.Tensor, k: int, mode: int = DENSE_AUTO, out_err: Optional[torch.Tensor] = None):
-        """queries fp32 [B, dim] (host or device) -> (scores f64 [B,k], ids i64 [B,k], flags i32 [B]) on device."""
+    def search(self, queries_f32: torch.Tensor, k: int, mode: int = DENSE_AUTO, out_err: Optional[torch.Tensor] = None,
+               row_mask: Optional[torch.Tensor] = None):
+        """queries fp32 [B, dim] (host or device) -> (scores f64 [B,k], ids i64 [B,k], flags i32 [B]) on device.
+        row_mask (pack_row_mask) restricts the search to the allowed rows of this shard."""
         q16 = self.prepare_queries(queries_f32)
-        return self.search_prepared(q16, k, mode, out_err)
+        return self.search_prepared(q16, k, mode, out_err, row_mask)
 
-    def search_prepared(self, queries16: torch.Tensor, k: int, mode: int = DENSE_AUTO, out_err: Optional[torch.Tensor] = None):
+    def search_prepared(self, queries16: torch.Tensor, k: int, mode: int = DENSE_AUTO, out_err: Optional[torch.Tensor] = None,
+                        row_mask: Optional[torch.Tensor] = None):
         return dense_topk(self._rows, queries16, k, self.id_offset, mode, n_rows=self.n,
-                          row_norm_bound=max(self.row_norm_bound, 1e-30), out_err=out_err)
+                          row_norm_bound=max(self.row_norm_bound, 1e-30), out_err=out_err, row_mask=row_mask)
 
 
 class SparseIndex:
@@ -332,9 +352,9 @@ class SparseIndex:
         # term-major global view kept for statistics (df per term)
         self.df = torch.bincount(t, minlength=n_terms) if nnz else torch.zeros(n_terms, dtype=torch.int64, device=dev)
 
-    def search(self, q_ptr, q_terms, q_vals, k: int):
+    def search(self, q_ptr, q_terms, q_vals, k: int, doc_mask: Optional[torch.Tensor] = None):
         """CSR queries (q_ptr i64 [B+1], q_terms i32 ascending per query, q_vals f32) ->
-        (scores f32 [B,k], ids i64 [B,k], counts i32 [B]) on device."""
+        (scores f32 [B,k], ids i64 [B,k], counts i32 [B]) on device.  doc_mask (pack_row_mask) = metadata filter."""
         dev = self.device
         q_ptr = torch.as_tensor(q_ptr, dtype=torch.int64).to(dev).contiguous()
         q_terms = torch.as_tensor(q_terms, dtype=torch.int32).to(dev).contiguous()
@@ -347,10 +367,11 @@ class SparseIndex:
         with torch.cuda.device(dev):
             nbytes = L.b200rag_sparse_topk_workspace_bytes(self.n_docs, self.block_docs, b, k)
             ws = _WS.get(dev, nbytes)
-            check(L.b200rag_sparse_topk(self.blk_term_ptr.data_ptr(), self.post_doc.data_ptr(), self.post_w.data_ptr(),
-                                        self.n_docs, self.n_terms, self.block_docs, q_ptr.data_ptr(), q_terms.data_ptr(),
-                                        q_vals.data_ptr(), b, k, self.id_offset, scores.data_ptr(), ids.data_ptr(),
-                                        counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)))
+            check(L.b200rag_sparse_topk_masked(self.blk_term_ptr.data_ptr(), self.post_doc.data_ptr(), self.post_w.data_ptr(),
+                                               self.n_docs, self.n_terms, self.block_docs, q_ptr.data_ptr(), q_terms.data_ptr(),
+                                               q_vals.data_ptr(), b, k, self.id_offset, scores.data_ptr(), ids.data_ptr(),
+                                               counts.data_ptr(), doc_mask.data_ptr() if doc_mask is not None else None,
+                                               ws.data_ptr(), ws.numel(), _stream_ptr(dev)))
         return scores, ids, counts
 
     def query_bytes(self, q_ptr, q_terms) -> int:

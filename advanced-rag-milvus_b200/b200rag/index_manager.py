@@ -234,6 +234,7 @@ class B200IndexManager:
         self._tok_ptr: List[int] = [0]
         self._tok_ids: List[np.ndarray] = []
         self._tok_dev: Optional[Tuple[torch.Tensor, torch.Tensor, int]] = None
+        self._mask_cache: Dict[str, Tuple[int, int, Optional[torch.Tensor]]] = {}     # filter expression -> (rows, allowed, bit mask)
         self.collections: Dict[str, _Collection] = {"semantic_index": _Collection("semantic_index", "dense", self),
                                                     "domain_index": _Collection("domain_index", "dense", self)}
         if enable_sparse:
@@ -280,6 +281,7 @@ class B200IndexManager:
             self.payload.append(ids[r], contents[r], (metadata[r] if metadata is not None else {}) or {})
         self._sparse_dirty = True
         self._tok_dev = None
+        self._mask_cache = {}
 
     async def index_chunks(self, chunks: List[Any], domain: Optional[str] = None) -> Dict[str, Any]:
         """Reference MilvusIndexManager.index_chunks (indexing.py:264-437): embed every chunk through the generator
@@ -387,51 +389,29 @@ class B200IndexManager:
         return s.to(torch.float64), i, c
 
     def _search_filtered(self, queries, collection_name: str, k: int, expr: str):
-        """Exact filtered search: evaluate the predicate to a row mask on the host columns, then either search deeper
-        and drop masked rows (mild filters) or search a gathered sub-index of the surviving rows (selective filters)."""
-        mask = _eval_filter(self.payload, expr)
-        keep_rows = np.flatnonzero(mask)
-        m = keep_rows.size
-        n = self.num_rows
-        q = queries
-        b = (len(q) if collection_name == "sparse_index" else
-             (1 if np.ndim(q) == 1 else np.shape(q)[0]))
-        empty = (torch.full((b, k), float("-inf"), dtype=torch.float64, device=self.device),
-                 torch.full((b, k), -1, dtype=torch.int64, device=self.device),
-                 torch.zeros(b, dtype=torch.int32, device=self.device))
-        if m == 0:
-            return empty
-        mask_dev = torch.as_tensor(mask).to(self.device)
-        if collection_name in _DENSE and m * 4 < n:
-            # selective filter: scan only the surviving rows
-            src = self._dense_of(collection_name)
-            rows_dev = torch.as_tensor(keep_rows).to(self.device)
-            sub = engine.DenseIndex(src.dim, self.dtype, "COSINE", self.device)
-            sub.add_prepared(src.rows[rows_dev])
-            qq = torch.as_tensor(np.asarray(q, dtype=np.float32) if not torch.is_tensor(q) else q)
-            s, i, _ = sub.search(qq if qq.dim() == 2 else qq[None, :], k)
-            i = torch.where(i >= 0, rows_dev[i.clamp(min=0)], i)
+        """Exact filtered search: the predicate is evaluated to a row bit mask on the host columns (cached per expression
+        until the next insert / delete) and applied INSIDE the scan kernels -- sample pass, epilogue survivors and exact
+        fallback for the dense indexes, candidate collection for the sparse one (b200rag_*_topk_masked)."""
+        cached = self._mask_cache.get(expr)
+        if cached is None or cached[0] != self.num_rows:
+            allowed = _eval_filter(self.payload, expr)
+            words = engine.pack_row_mask(torch.as_tensor(allowed).to(self.device)) if allowed.size else None
+            cached = (self.num_rows, int(allowed.sum()), words)
+            self._mask_cache = {expr: cached}                 # one entry: serving loops repeat the same filter
+        _, m, words = cached
+        b = (len(queries) if collection_name == "sparse_index" else (1 if np.ndim(queries) == 1 else np.shape(queries)[0]))
+        if m == 0 or words is None:
+            return (torch.full((b, k), float("-inf"), dtype=torch.float64, device=self.device),
+                    torch.full((b, k), -1, dtype=torch.int64, device=self.device),
+                    torch.zeros(b, dtype=torch.int32, device=self.device))
+        if collection_name in _DENSE:
+            idx = self._dense_of(collection_name)
+            q = torch.as_tensor(np.asarray(queries, dtype=np.float32) if not torch.is_tensor(queries) else queries)
+            s, i, _ = idx.search(q if q.dim() == 2 else q[None, :], k, row_mask=words)
             return s, i, torch.full((b,), min(k, m), dtype=torch.int32, device=self.device)
-        depth = min(n, max(64, int(2 * k * n / m) + 16))
-        while True:
-            s, i, c = self.search_batch_ids(q, collection_name, min(depth, 2048), None)
-            ok = (i >= 0) & mask_dev[i.clamp(min=0)]
-            got = ok.sum(dim=1)
-            exhausted = (c.to(torch.int64) < min(depth, 2048)) | (min(depth, 2048) >= n)
-            if bool(((got >= k) | exhausted).all()) or depth >= 2048:
-                if not bool(((got >= k) | exhausted).all()):
-                    raise ValueError("filter too selective for the post-filter path (needs more than 2048 candidates)")
-                order = torch.argsort((~ok).to(torch.int8), dim=1, stable=True)[:, :k]      # kept hits first, order preserved
-                s2, i2, ok2 = s.gather(1, order), i.gather(1, order), ok.gather(1, order)
-                if s2.shape[1] < k:
-                    pad = k - s2.shape[1]
-                    s2 = torch.nn.functional.pad(s2, (0, pad), value=float("-inf"))
-                    i2 = torch.nn.functional.pad(i2, (0, pad), value=-1)
-                    ok2 = torch.nn.functional.pad(ok2, (0, pad), value=False)
-                s2 = torch.where(ok2, s2, torch.full_like(s2, float("-inf")))
-                i2 = torch.where(ok2, i2, torch.full_like(i2, -1))
-                return s2, i2, got.clamp(max=k).to(torch.int32)
-            depth *= 4
+        qp, qt, qv = self._sparse_queries(list(queries))
+        s, i, c = self._sparse_index().search(qp, qt, qv, k, doc_mask=words)
+        return s.to(torch.float64), i, c
 
     def search_batch(self, queries: Any, collection_name: str, top_k: int = 20, filters: Optional[str] = None,
                      search_params: Optional[Dict] = None) -> List[List[Dict[str, Any]]]:
@@ -522,6 +502,7 @@ class B200IndexManager:
         for r in rows:
             self.payload.append(old_p.ids[r], old_p.content[r], {f: old_p.cols[f][r] for f in old_p.cols})
         self._sparse, self._sparse_dirty, self._tok_dev = None, True, None
+        self._mask_cache = {}
 
     async def delete_by_filter(self, collection_name: str, expr: str):
         """Reference MilvusIndexManager.delete_by_filter (indexing.py:692-695: `collection.delete(expr)`).  The three

@@ -6,12 +6,14 @@ namespace b200rag {
 size_t exact_workspace_bytes(int64_t n_rows, int dim, int n_q, int k);
 int run_exact(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_launch,
               const int32_t* q_list, int k, int64_t id_offset, double* out_scores, int64_t* out_ids,
-              void* workspace, size_t workspace_bytes, cudaStream_t st, const int32_t* n_active, int slot_base);
+              void* workspace, size_t workspace_bytes, cudaStream_t st, const int32_t* n_active, int slot_base,
+              const uint32_t* row_mask);
 size_t tensor_workspace_bytes(int64_t n_rows, int dim, int n_q, int k);
 bool tensor_supported(int64_t n_rows, int dim, int n_q, int k);
 int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_q, int k,
                int64_t id_offset, double* out_scores, int64_t* out_ids, int32_t* out_flags, double row_norm_bound,
-               float* out_err, int with_fallback, void* workspace, size_t workspace_bytes, cudaStream_t st);
+               float* out_err, int with_fallback, void* workspace, size_t workspace_bytes, cudaStream_t st,
+               const uint32_t* row_mask);
 void profile_next_scan(void* a, void* b);
 int scan_stats(int enable, unsigned long long* out_host, int max_ctas);
 }  // namespace b200rag
@@ -41,6 +43,15 @@ int b200rag_dense_topk(const void* corpus16, int64_t n_rows, int32_t dim, int32_
                        double* out_scores, int64_t* out_ids, int32_t* out_flags,
                        double row_norm_bound, float* out_err,
                        void* workspace, size_t workspace_bytes, int32_t mode, void* stream) {
+    return b200rag_dense_topk_masked(corpus16, n_rows, dim, dtype, queries16, n_queries, k, id_offset, out_scores, out_ids,
+                                     out_flags, row_norm_bound, out_err, nullptr, workspace, workspace_bytes, mode, stream);
+}
+
+int b200rag_dense_topk_masked(const void* corpus16, int64_t n_rows, int32_t dim, int32_t dtype,
+                              const void* queries16, int32_t n_queries, int32_t k, int64_t id_offset,
+                              double* out_scores, int64_t* out_ids, int32_t* out_flags,
+                              double row_norm_bound, float* out_err, const uint32_t* row_mask,
+                              void* workspace, size_t workspace_bytes, int32_t mode, void* stream) {
     B200_REQUIRE(n_queries >= 0, "dense_topk: bad n_queries=%d", n_queries);
     if (n_queries == 0) return B200RAG_OK;
     B200_REQUIRE(queries16 && out_scores && out_ids && workspace, "dense_topk: null pointer");
@@ -58,13 +69,13 @@ int b200rag_dense_topk(const void* corpus16, int64_t n_rows, int32_t dim, int32_
         if (out_flags) B200_CUDA_CHECK(cudaMemsetAsync(out_flags, 0, (size_t)n_queries * sizeof(int32_t), st));
         if (out_err) B200_CUDA_CHECK(cudaMemsetAsync(out_err, 0, (size_t)n_queries * sizeof(float), st));
         return run_exact(corpus16, n_rows, dim, dtype, queries16, n_queries, nullptr, k, id_offset, out_scores, out_ids,
-                         workspace, workspace_bytes, st, nullptr, 0);
+                         workspace, workspace_bytes, st, nullptr, 0, row_mask);
     }
     if (mode == B200RAG_DENSE_AUTO || mode == B200RAG_DENSE_TENSOR) {
         B200_REQUIRE(row_norm_bound > 0.0 && row_norm_bound < 1e30, "dense_topk: row_norm_bound must be positive (got %g)",
                      row_norm_bound);
         return run_tensor(corpus16, n_rows, dim, dtype, queries16, n_queries, k, id_offset, out_scores, out_ids, out_flags,
-                          row_norm_bound, out_err, mode == B200RAG_DENSE_AUTO, workspace, workspace_bytes, st);
+                          row_norm_bound, out_err, mode == B200RAG_DENSE_AUTO, workspace, workspace_bytes, st, row_mask);
     }
     set_error("dense_topk: unknown mode %d", mode);
     return B200RAG_E_INVALID;

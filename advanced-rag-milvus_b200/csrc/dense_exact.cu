@@ -23,7 +23,7 @@ dense_exact_kernel(const uint16_t* __restrict__ corpus, int64_t n_rows, int dim,
                    const uint16_t* __restrict__ queries, int n_q, const int32_t* __restrict__ q_list, int k, int cap,
                    int64_t rows_per_chunk, int n_chunks, int64_t id_offset,
                    double* __restrict__ part_scores, int64_t* __restrict__ part_ids,
-                   const int32_t* __restrict__ n_active, int slot_base) {
+                   const int32_t* __restrict__ n_active, int slot_base, const uint32_t* __restrict__ row_mask) {
     extern __shared__ __align__(16) char smem[];
     const int tid = threadIdx.x;
     const int chunk = blockIdx.x;
@@ -62,7 +62,8 @@ dense_exact_kernel(const uint16_t* __restrict__ corpus, int64_t n_rows, int dim,
     const int64_t iters = (span + EX_THREADS - 1) / EX_THREADS;
     for (int64_t it = 0; it < iters; ++it) {
         const int64_t local = it * EX_THREADS + tid;
-        const bool valid = local < span;
+        bool valid = local < span;
+        if (valid && row_mask) valid = (__ldg(row_mask + ((r_begin + local) >> 5)) >> ((r_begin + local) & 31)) & 1u;    // metadata filter
         double s[EX_QT];
         if (valid) {
             const uint4* x = reinterpret_cast<const uint4*>(corpus + (r_begin + local) * dim);
@@ -276,7 +277,8 @@ int launch_merge_gated(const double* cand_scores, const int64_t* cand_ids, int n
 // number; query vectors are read from, and results written to, the ORIGINAL query rows.
 int run_exact(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_launch,
               const int32_t* q_list, int k, int64_t id_offset, double* out_scores, int64_t* out_ids,
-              void* workspace, size_t workspace_bytes, cudaStream_t st, const int32_t* n_active, int slot_base) {
+              void* workspace, size_t workspace_bytes, cudaStream_t st, const int32_t* n_active, int slot_base,
+              const uint32_t* row_mask) {
     if (n_launch <= 0) return B200RAG_OK;
     ExactPlan pl = plan_exact(n_rows, dim, n_launch, k);
     if (pl.smem > 220 * 1024) {
@@ -296,11 +298,11 @@ int run_exact(const void* corpus16, int64_t n_rows, int dim, int dtype, const vo
     if (dtype == B200RAG_F16) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(dense_exact_kernel<B200RAG_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         dense_exact_kernel<B200RAG_F16><<<grid, EX_THREADS, pl.smem, st>>>(c, n_rows, dim, q, n_launch, q_list, k, pl.cap,
-                                                                         pl.rows_per_chunk, pl.n_chunks, id_offset, part_scores, part_ids, n_active, slot_base); count_launch();
+                                                                         pl.rows_per_chunk, pl.n_chunks, id_offset, part_scores, part_ids, n_active, slot_base, row_mask); count_launch();
     } else {
         B200_CUDA_CHECK(cudaFuncSetAttribute(dense_exact_kernel<B200RAG_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         dense_exact_kernel<B200RAG_BF16><<<grid, EX_THREADS, pl.smem, st>>>(c, n_rows, dim, q, n_launch, q_list, k, pl.cap,
-                                                                          pl.rows_per_chunk, pl.n_chunks, id_offset, part_scores, part_ids, n_active, slot_base); count_launch();
+                                                                          pl.rows_per_chunk, pl.n_chunks, id_offset, part_scores, part_ids, n_active, slot_base, row_mask); count_launch();
     }
     B200_CUDA_CHECK(cudaGetLastError());
     return launch_merge_gated(part_scores, part_ids, n_launch, q_list, pl.n_chunks * k, k, out_scores, nullptr, out_ids, nullptr, st,

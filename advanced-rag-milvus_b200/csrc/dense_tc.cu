@@ -29,7 +29,8 @@ namespace b200rag {
 size_t exact_workspace_bytes(int64_t n_rows, int dim, int n_q, int k);
 int run_exact(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_launch,
               const int32_t* q_list, int k, int64_t id_offset, double* out_scores, int64_t* out_ids,
-              void* workspace, size_t workspace_bytes, cudaStream_t st, const int32_t* n_active, int slot_base);
+              void* workspace, size_t workspace_bytes, cudaStream_t st, const int32_t* n_active, int slot_base,
+              const uint32_t* row_mask);
 
 // ----------------------------------------------------------------------------------------------- scan kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -171,8 +172,8 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 tc_fence_after();
                 const int64_t row0 = (int64_t)tile * p.tile_stride * TC_BN;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)astage * TC_BN;
-                if (p.sample) epi_sample_tile(taddr, TC_BN / 32, row0, p.n_rows, top);
-                else epi_filter_tile<TC_BN / 32>(taddr, row0, p.n_rows, thr, cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane, ec);
+                if (p.sample) epi_sample_tile(taddr, TC_BN / 32, row0, p.n_rows, top, p.row_mask);
+                else epi_filter_tile<TC_BN / 32>(taddr, row0, p.n_rows, thr, cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane, ec, p.row_mask);
                 // accumulator drained: hand it back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
@@ -612,7 +613,8 @@ void profile_next_scan(void* a, void* b) { g_prof_start = static_cast<cudaEvent_
 
 int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const void* queries16, int n_q, int k,
                int64_t id_offset, double* out_scores, int64_t* out_ids, int32_t* out_flags, double row_norm_bound,
-               float* out_err, int with_fallback, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+               float* out_err, int with_fallback, void* workspace, size_t workspace_bytes, cudaStream_t st,
+               const uint32_t* row_mask) {
     TensorPlan pl = plan_tensor(n_rows, dim, n_q, k);
     if (pl.cap > TC_MAX_C || pl.scan_smem > TC_SMEM_LIMIT || n_rows >= ((int64_t)1 << 32) - TC_BN) {
         set_error("dense_topk(tensor): k=%d (k'=%d) or n_rows=%lld beyond the tensor-core path limits; use B200RAG_DENSE_EXACT",
@@ -653,6 +655,7 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
             n_q_scan = pl.nqb * TC_BM;
         }
         sp.queries = static_cast<const uint16_t*>(q_scan);
+        sp.row_mask = row_mask;
         sp.stats = g_stats_enabled ? reinterpret_cast<unsigned long long*>(ws + pl.off_stats) : nullptr;
         if (g_stats_enabled) {
             B200_CUDA_CHECK(cudaMemsetAsync(sp.stats, 0, (size_t)256 * ST_N * 8, st));
@@ -754,11 +757,11 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
         // with the few-chunk plan of a large batch and only does work on pathological inputs (massive ties).
         const int na = n_q < TC_FALLBACK_BATCH ? n_q : TC_FALLBACK_BATCH;
         int rc = run_exact(corpus16, n_rows, dim, dtype, queries16, na, flag_list, k, id_offset, out_scores, out_ids,
-                           ws + pl.off_exact, pl.total - pl.off_exact, st, n_flagged, 0);
+                           ws + pl.off_exact, pl.total - pl.off_exact, st, n_flagged, 0, row_mask);
         if (rc) return rc;
         if (n_q > na) {
             rc = run_exact(corpus16, n_rows, dim, dtype, queries16, n_q - na, flag_list + na, k, id_offset, out_scores, out_ids,
-                           ws + pl.off_exact, pl.total - pl.off_exact, st, n_flagged, na);
+                           ws + pl.off_exact, pl.total - pl.off_exact, st, n_flagged, na, row_mask);
             if (rc) return rc;
         }
     }

@@ -185,7 +185,7 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     ST_ADD(st_wtfull, tt);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)astage * T3_BN;
-                    epi_sample_tile(taddr, T3_BN / 32, (int64_t)tile * p.tile_stride * T3_BN, p.n_rows, top);
+                    epi_sample_tile(taddr, T3_BN / 32, (int64_t)tile * p.tile_stride * T3_BN, p.n_rows, top, p.row_mask);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(tempty_leader + astage * 8);
@@ -220,7 +220,7 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     ST_ADD(st_wtfull, tt);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)astage * T3_BN;
-                    epi_filter_tile<T3_BN / 32>(taddr, row0, p.n_rows, thr, cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane, ec);
+                    epi_filter_tile<T3_BN / 32>(taddr, row0, p.n_rows, thr, cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane, ec, p.row_mask);
                     // accumulator drained: hand it back to the leader's MMA warp
                     tc_fence_before();
                     __syncwarp();

@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(SP_THREADS, 2)
 sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __restrict__ post_doc,
                     const float* __restrict__ post_w, int64_t n_docs, int n_terms, int block_docs, int n_blocks, int n_slices,
                     const int64_t* __restrict__ q_ptr, const int32_t* __restrict__ q_terms, const float* __restrict__ q_vals,
-                    int k, int cap, int64_t id_offset, double* __restrict__ part_scores, int64_t* __restrict__ part_ids) {
+                    int k, int cap, int64_t id_offset, double* __restrict__ part_scores, int64_t* __restrict__ part_ids,
+                    const uint32_t* __restrict__ doc_mask) {
     extern __shared__ __align__(16) char smem[];
     const int tid = threadIdx.x;
     const int q = blockIdx.x;
@@ -116,6 +117,21 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
         unsigned long long m = 0;
         if (tid < n_words) { m = touched[tid]; touched[tid] = 0u; }
         if (tid + SP_THREADS < n_words) { m |= (unsigned long long)touched[tid + SP_THREADS] << 32; touched[tid + SP_THREADS] = 0u; }
+        if (doc_mask && m) {
+            // metadata filter: documents that are not allowed are dropped here (their accumulators still have to go back to
+            // zero).  block_docs is a multiple of 32, so a bitmap word of the block is a word of the mask.
+            unsigned long long allowed = 0;
+            const int64_t w0 = (doc0 >> 5) + tid, w1 = w0 + SP_THREADS, n_mask_words = (n_docs + 31) >> 5;
+            if (tid < n_words && w0 < n_mask_words) allowed = __ldg(doc_mask + w0);
+            if (tid + SP_THREADS < n_words && w1 < n_mask_words) allowed |= (unsigned long long)__ldg(doc_mask + w1) << 32;
+            unsigned long long drop = m & ~allowed;
+            while (drop) {
+                const int bpos = __ffsll((long long)drop) - 1;
+                drop &= drop - 1;
+                acc[bpos < 32 ? tid * 32 + bpos : (tid + SP_THREADS) * 32 + (bpos - 32)] = 0.0f;
+            }
+            m &= allowed;
+        }
         float thr_f = tk.threshold_hi32_as_float();
         while (__syncthreads_or(m != 0ull)) {
             bool have = false;
@@ -183,6 +199,17 @@ int b200rag_sparse_topk(const int64_t* blk_term_ptr, const uint16_t* post_doc, c
                         int32_t n_queries, int32_t k, int64_t id_offset,
                         float* out_scores, int64_t* out_ids, int32_t* out_counts,
                         void* workspace, size_t workspace_bytes, void* stream) {
+    return b200rag_sparse_topk_masked(blk_term_ptr, post_doc, post_w, n_docs, n_terms, block_docs, q_ptr, q_terms, q_vals,
+                                      n_queries, k, id_offset, out_scores, out_ids, out_counts, nullptr, workspace,
+                                      workspace_bytes, stream);
+}
+
+int b200rag_sparse_topk_masked(const int64_t* blk_term_ptr, const uint16_t* post_doc, const float* post_w,
+                               int64_t n_docs, int32_t n_terms, int32_t block_docs,
+                               const int64_t* q_ptr, const int32_t* q_terms, const float* q_vals,
+                               int32_t n_queries, int32_t k, int64_t id_offset,
+                               float* out_scores, int64_t* out_ids, int32_t* out_counts, const uint32_t* doc_mask,
+                               void* workspace, size_t workspace_bytes, void* stream) {
     B200_REQUIRE(blk_term_ptr && q_ptr && out_scores && out_ids && out_counts && workspace, "sparse_topk: null pointer");
     B200_REQUIRE(n_docs >= 0 && n_terms > 0 && n_queries >= 0 && k > 0, "sparse_topk: bad sizes");
     B200_REQUIRE(block_docs > 0 && block_docs <= 64 * SP_THREADS && block_docs % 32 == 0,
@@ -217,7 +244,7 @@ int b200rag_sparse_topk(const int64_t* blk_term_ptr, const uint16_t* post_doc, c
     dim3 grid((unsigned)n_queries, (unsigned)n_slices);
     sparse_query_kernel<<<grid, SP_THREADS, smem, st>>>(blk_term_ptr, post_doc, post_w, n_docs, n_terms, block_docs,
                                                        (int)n_blocks, (int)n_slices, q_ptr, q_terms, q_vals, k, cap, id_offset,
-                                                       part_scores, part_ids); count_launch();
+                                                       part_scores, part_ids, doc_mask); count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return launch_merge(part_scores, part_ids, n_queries, nullptr, (int)(n_slices * k), k, nullptr, out_scores, out_ids,
                         out_counts, st);

@@ -336,7 +336,7 @@ enum { ST_MMA_TOTAL = 0, ST_MMA_WAIT_FULL, ST_MMA_WAIT_TEMPTY, ST_MMA_WAIT_Q, ST
 struct EpiCounters { long long compact = 0, ncompact = 0, nslow = 0; };
 
 __device__ __forceinline__ void epi_filter_group(uint32_t (&r)[32], int c, bool partial, int64_t row0, int64_t n_rows, float& thr,
-                                                 int& cnt, unsigned long long* buf, EpiCounters& ec) {
+                                                 int& cnt, unsigned long long* buf, EpiCounters& ec, const uint32_t* row_mask) {
     if (partial) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -348,9 +348,12 @@ __device__ __forceinline__ void epi_filter_group(uint32_t (&r)[32], int c, bool 
     if (any) {
         ++ec.nslow;
         const uint32_t rbase = (uint32_t)(row0 + c * 32);
+        // metadata filter: consulted only here, for the rare rows that beat the threshold (the threshold itself is the
+        // k'-th best among ALLOWED rows, because only allowed rows are ever appended or sampled)
+        const uint32_t allowed = row_mask ? __ldg(row_mask + (rbase >> 5)) : 0xffffffffu;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            if (__uint_as_float(r[i]) > thr) {
+            if (__uint_as_float(r[i]) > thr && ((allowed >> i) & 1u)) {
                 buf[cnt] = ((unsigned long long)r[i] << 32) | (unsigned long long)(rbase + i);
                 ++cnt;
             }
@@ -386,7 +389,7 @@ __device__ __forceinline__ void epi_make_room(float& thr, int& cnt, unsigned lon
 template <int NG>
 __device__ __forceinline__ void epi_filter_tile(uint32_t taddr, int64_t row0, int64_t n_rows, float& thr, int& cnt,
                                                 unsigned long long* buf, unsigned int* my_gthr, int kp, int cap,
-                                                uint32_t scratch, int lane, EpiCounters& ec) {
+                                                uint32_t scratch, int lane, EpiCounters& ec, const uint32_t* row_mask) {
     static_assert(NG % 2 == 0, "column groups are processed in pairs");
     const bool partial = row0 + NG * 32 > n_rows;
     uint32_t ra[32], rb[32];
@@ -396,11 +399,11 @@ __device__ __forceinline__ void epi_filter_tile(uint32_t taddr, int64_t row0, in
         epi_make_room(thr, cnt, buf, my_gthr, kp, cap, scratch, lane, ec);
         tmem_ld32_wait(ra);
         tmem_ld32_issue(taddr + (c + 1) * 32, rb);
-        epi_filter_group(ra, c, partial, row0, n_rows, thr, cnt, buf, ec);
+        epi_filter_group(ra, c, partial, row0, n_rows, thr, cnt, buf, ec, row_mask);
         epi_make_room(thr, cnt, buf, my_gthr, kp, cap, scratch, lane, ec);
         tmem_ld32_wait(rb);
         if (c + 2 < NG) tmem_ld32_issue(taddr + (c + 2) * 32, ra);
-        epi_filter_group(rb, c + 1, partial, row0, n_rows, thr, cnt, buf, ec);
+        epi_filter_group(rb, c + 1, partial, row0, n_rows, thr, cnt, buf, ec, row_mask);
     }
 }
 
@@ -429,7 +432,7 @@ __device__ __forceinline__ void epi_filter_finish(int& cnt, unsigned long long* 
 constexpr int TC_SAMPLE_R = 16;
 
 __device__ __forceinline__ void epi_sample_tile(uint32_t taddr, int n_groups, int64_t row0, int64_t n_rows,
-                                                float (&top)[TC_SAMPLE_R]) {
+                                                float (&top)[TC_SAMPLE_R], const uint32_t* row_mask) {
     const bool partial = row0 + n_groups * 32 > n_rows;
 #pragma unroll 1
     for (int c = 0; c < n_groups; ++c) {
@@ -439,6 +442,12 @@ __device__ __forceinline__ void epi_sample_tile(uint32_t taddr, int n_groups, in
 #pragma unroll
             for (int i = 0; i < 32; ++i)
                 if (row0 + c * 32 + i >= n_rows) r[i] = 0xff800000u;
+        }
+        if (row_mask && row0 + c * 32 < n_rows) {               // filtered search: only allowed rows seed the threshold
+            const uint32_t allowed = __ldg(row_mask + ((row0 + c * 32) >> 5));
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (!((allowed >> i) & 1u)) r[i] = 0xff800000u;
         }
         float m = __uint_as_float(r[0]);
 #pragma unroll
@@ -477,7 +486,8 @@ struct ScanParams {
     unsigned long long* cand;   // [n_chunks][nqb][128][cap]  (score bits << 32 | local row)
     int* cand_cnt;              // [n_chunks][nqb][128]
     unsigned int* gthr;         // [nqb*128] shared per-query threshold keys (mono32), monotone via atomicMax
-    const uint16_t* queries;    // v2 loads Q rows itself
+    const uint16_t* queries;    // query block matrix (padded to whole blocks)
+    const uint32_t* row_mask;   // optional filter: bit (row & 31) of word (row >> 5) set = row allowed; NULL = no filter
     unsigned long long* stats;  // optional [gridDim.x][16] cycle counters (debug/profiling), may be NULL
 };
 

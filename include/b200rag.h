@@ -98,6 +98,17 @@ int b200rag_dense_topk(const void* corpus16, int64_t n_rows, int32_t dim, int32_
                        double row_norm_bound, float* out_err,
                        void* workspace, size_t workspace_bytes, int32_t mode, void* stream);
 
+/* The same search restricted to the rows a metadata filter allows (reference: the `expr=filters` argument of
+ * Collection.search, indexing.py:505-523, built by HybridRetriever._build_filter_expression, retrieval.py:565-632).
+ *   row_mask  u32 [ceil(n_rows / 32)]: bit (row & 31) of word (row >> 5) set = row allowed; NULL = no filter.
+ * The mask is applied inside the kernels (sample pass, survivors of the scan epilogue, exact scan); results are the exact
+ * top-k of the allowed rows, fewer than k hits are padded with id -1 / score -inf. */
+int b200rag_dense_topk_masked(const void* corpus16, int64_t n_rows, int32_t dim, int32_t dtype,
+                              const void* queries16, int32_t n_queries, int32_t k, int64_t id_offset,
+                              double* out_scores, int64_t* out_ids, int32_t* out_flags,
+                              double row_norm_bound, float* out_err, const uint32_t* row_mask,
+                              void* workspace, size_t workspace_bytes, int32_t mode, void* stream);
+
 /* Profiling hook (not part of the data path): when both handles are non-NULL cudaEvent_t values, the NEXT
  * tensor-core b200rag_dense_topk call on this thread records `start` immediately before and `stop` immediately
  * after its scan kernel on the call's stream, then clears the hook.  bench.py uses it to time the dominant kernel
@@ -126,6 +137,14 @@ int b200rag_sparse_topk(const int64_t* blk_term_ptr, const uint16_t* post_doc, c
                         int32_t n_queries, int32_t k, int64_t id_offset,
                         float* out_scores, int64_t* out_ids, int32_t* out_counts,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Filtered variant: doc_mask u32 [ceil(n_docs / 32)] as in b200rag_dense_topk_masked (NULL = no filter). */
+int b200rag_sparse_topk_masked(const int64_t* blk_term_ptr, const uint16_t* post_doc, const float* post_w,
+                               int64_t n_docs, int32_t n_terms, int32_t block_docs,
+                               const int64_t* q_ptr, const int32_t* q_terms, const float* q_vals,
+                               int32_t n_queries, int32_t k, int64_t id_offset,
+                               float* out_scores, int64_t* out_ids, int32_t* out_counts, const uint32_t* doc_mask,
+                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * k-way merge of gathered candidate lists (K4): the reduce after the NCCL all-gather of per-GPU top-k.  Stands

@@ -175,3 +175,29 @@ def test_auto_mode_serves_k_beyond_the_tensor_path_limit(eng, oracle_lib):
     """k = 1500 exceeds the candidate-buffer limit of the tensor-core scan; AUTO must route to the exact scan by itself."""
     s, i, f, err, ref_s, ref_i, qf, rnb = _case(eng, oracle_lib, 9000, 64, 5, 1500, "f16", seed=77, mode=eng.DENSE_AUTO)
     assert np.array_equal(i, ref_i) and np.array_equal(s, ref_s) and f.sum() == 0
+
+
+@pytest.mark.parametrize("keep_frac", [0.5, 0.05, 0.0004])
+def test_filtered_scan_equals_oracle_on_the_allowed_rows(eng, oracle_lib, keep_frac):
+    """Metadata filter applied inside the kernels (b200rag_dense_topk_masked): the result is the exact top-k of the allowed
+    rows, for mild, selective and nearly-empty masks (the last one leaves fewer allowed rows than k), in AUTO and EXACT mode."""
+    o = oracle_lib
+    n, d, b, k = 300_000, 128, 130, 50
+    rng = np.random.default_rng(31)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((b, d)).astype(np.float32)
+    allowed = rng.random(n) < keep_frac
+    rows = np.flatnonzero(allowed)
+    xb, qb = o.normalize_rows(x, o.F16), o.normalize_rows(q, o.F16)
+    kk = min(k, rows.size)
+    ref_s, ref_local = o.dense_topk(xb[rows], qb, kk, o.F16)
+    ref_i = rows[ref_local]
+    idx = eng.DenseIndex(d, "f16", "COSINE", DEV)
+    idx.add(torch.from_numpy(x))
+    mask = eng.pack_row_mask(torch.from_numpy(allowed).to(DEV))
+    for mode in (eng.DENSE_AUTO, eng.DENSE_EXACT):
+        s, i, f = idx.search(torch.from_numpy(q), k, mode=mode, row_mask=mask)
+        s, i = s.cpu().numpy(), i.cpu().numpy()
+        assert np.array_equal(i[:, :kk], ref_i), (keep_frac, mode)
+        assert np.array_equal(s[:, :kk], ref_s), (keep_frac, mode)
+        assert (i[:, kk:] == -1).all() and np.isneginf(s[:, kk:]).all()

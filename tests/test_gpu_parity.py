@@ -271,3 +271,26 @@ def test_mmr_config4_scale_matches_oracle(eng, monkeypatch, force_warp_kernel):
         sets = [frozenset(ti[dp[d]: dp[d + 1]].tolist()) for d in cand[q, : n[q]]]
         ref = fusion.mmr_select(list(rel[q, : n[q]]), sets, [k, k, 37][q], [0.7, 0.5, 0.8][q])
         assert picks[q, : int(pn[q])].cpu().tolist() == ref, q
+
+
+def test_sparse_filtered_matches_oracle(eng, oracle_lib):
+    """doc_mask applied in the candidate collection of the sparse scan: exact top-k of the allowed documents."""
+    from b200rag import synth
+    o = oracle_lib
+    n_docs, vocab, n_q, k = 60000, 3000, 24, 30
+    dp, ti, w, qp, qt, qv = _sparse_case(n_docs, vocab, n_q, seed=9)
+    rng = np.random.default_rng(4)
+    allowed = rng.random(n_docs) < 0.2
+    tp, pd, pw = synth.doc_major_to_term_major(dp, ti, w, vocab)
+    big = n_docs
+    rs, ri, rc = o.sparse_topk(tp, pd, pw, n_docs, qp, qt, qv, big)
+    sidx = eng.SparseIndex(dp, ti, w, vocab, DEV)
+    mask = eng.pack_row_mask(torch.from_numpy(allowed).to(DEV))
+    s, i, c = sidx.search(qp, qt, qv, k, doc_mask=mask)
+    s, i, c = s.cpu().numpy(), i.cpu().numpy(), c.cpu().numpy()
+    for q in range(n_q):
+        assert rc[q] <= big                                  # k = n_docs: the oracle list is complete
+        keep = [j for j in range(rc[q]) if allowed[ri[q, j]]][:k]
+        assert c[q] == len(keep)
+        assert list(i[q, : c[q]]) == [int(ri[q, j]) for j in keep]
+        assert list(s[q, : c[q]]) == [rs[q, j] for j in keep]
