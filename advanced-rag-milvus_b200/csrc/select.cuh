@@ -22,6 +22,7 @@ struct TopKShared {
     int has_thr;    // thr_* valid: entries <= thr were already discarded and may be refused
     int sel_digit;
     int sel_want;
+    int sel_exact;  // the selected bucket holds exactly sel_want entries: the remaining digits cannot matter
     int out_count;
     int eq_taken;
     int pad;
@@ -131,6 +132,11 @@ struct BlockTopK {
         uint64_t sel_hi = 0, mask_hi = 0;
         LoT sel_lo = 0, mask_lo = 0;
         int want = k;
+        if (start_digit < TOP_DIGIT) {   // bytes above start_digit are identical for all entries: part of the prefix from the start
+            mask_hi = ~uint64_t(0) << ((start_digit - NLO + 1) * 8);
+            sel_hi = bh[0] & mask_hi;
+        }
+        bool early = false;              // stopped before the last digit: every entry with the selected prefix is kept
         for (int d = start_digit; d >= 0; --d) {
             for (int i = tid; i < 256; i += THREADS) st->hist[i] = 0;
             __syncthreads();
@@ -162,6 +168,7 @@ struct BlockTopK {
                     }
                     st->sel_digit = tid * 8 + b;
                     st->sel_want = want - cum;
+                    st->sel_exact = c[b] == want - cum;
                 }
             }
             __syncthreads();
@@ -174,12 +181,13 @@ struct BlockTopK {
                 sel_lo |= (LoT)b << (d * 8);
                 mask_lo |= (LoT)255 << (d * 8);
             }
+            if (st->sel_exact && d > 0) {   // (no ties at the boundary is the common case: half of the passes or more are skipped)
+                early = true;
+                break;
+            }
         }
-        // (sel_hi, sel_lo) is the k-th greatest key; `want` of the entries equal to it are kept.
-        if (start_digit < TOP_DIGIT) {   // bytes above start_digit are identical for all entries: take them from any entry
-            uint64_t keep = ~uint64_t(0) << ((start_digit - NLO + 1) * 8);
-            sel_hi |= bh[0] & keep;
-        }
+        // complete walk: (sel_hi, sel_lo) is the k-th greatest key and `want` of the entries equal to it are kept.
+        // early stop:    entries whose masked key is >= the selected prefix are kept (exactly k of them).
         if (tid == 0) { st->out_count = 0; st->eq_taken = 0; }
         __syncthreads();
         uint64_t* oh = hi[a ^ 1];
@@ -187,13 +195,25 @@ struct BlockTopK {
         for (int i = tid; i < n; i += THREADS) {
             uint64_t h = bh[i];
             LoT l = bl[i];
-            bool keep = key_gt<LoT>(h, l, sel_hi, sel_lo);
-            if (!keep && h == sel_hi && l == sel_lo) keep = atomicAdd(&st->eq_taken, 1) < want;
+            bool keep;
+            if (early) {
+                const uint64_t mh = h & mask_hi;
+                const LoT ml = l & mask_lo;
+                keep = mh > sel_hi || (mh == sel_hi && ml >= sel_lo);
+            } else {
+                keep = key_gt<LoT>(h, l, sel_hi, sel_lo);
+                if (!keep && h == sel_hi && l == sel_lo) keep = atomicAdd(&st->eq_taken, 1) < want;
+            }
             if (keep) {
                 int j = atomicAdd(&st->out_count, 1);
                 oh[j] = h;
                 ol[j] = l;
             }
+        }
+        if (early) {
+            // threshold for later offers: the greatest key below every kept one = (prefix, low bits 0) - 1
+            if (sel_lo != 0) { sel_lo = (LoT)(sel_lo - 1); }
+            else { sel_hi -= 1; sel_lo = (LoT)~(LoT)0; }     // sel_hi > 0: a zero prefix would have kept all n > k entries
         }
         __syncthreads();
         if (tid == 0) {
