@@ -173,7 +173,7 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 const int64_t row0 = (int64_t)tile * p.tile_stride * TC_BN;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)astage * TC_BN;
                 if (p.sample) epi_sample_tile(taddr, TC_BN / 32, row0, p.n_rows, top, p.row_mask);
-                else epi_filter_tile<TC_BN / 32>(taddr, row0, p.n_rows, thr, cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane, ec, p.row_mask);
+                else epi_filter_tile<TC_BN / 32, 1>(taddr, row0, p.n_rows, thr, cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane, ec, p.row_mask);
                 // accumulator drained: hand it back to the MMA warp
                 tc_fence_before();
                 __syncwarp();

@@ -20,6 +20,8 @@
 //   warps 2..5  epilogue in BOTH CTAs (identical to the first generation): tcgen05.ld 32 columns at a time, a thread
 //               owns one query, threshold filter, append of the rare survivors, warp-cooperative compaction.  The
 //               accumulator is handed back by arriving on the LEADER's tmem-empty barrier (8 arrivals: 4 warps x 2 CTAs).
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace b200rag {
@@ -34,6 +36,7 @@ constexpr int T3_STAGE_BYTES = T3_Q_BYTES + T3_X_BYTES;  // 32 KB
 constexpr int T3_STAGES = 6;
 constexpr int T3_N_BARS = 2 * T3_STAGES + 4;
 
+template <int EPI_VAR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T3_THREADS, 1)
 dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const ScanParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -220,7 +223,7 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     ST_ADD(st_wtfull, tt);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)astage * T3_BN;
-                    epi_filter_tile<T3_BN / 32>(taddr, row0, p.n_rows, thr, cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane, ec, p.row_mask);
+                    epi_filter_tile<T3_BN / 32, EPI_VAR>(taddr, row0, p.n_rows, thr, cnt, buf, my_gthr, p.kprime, p.cap, scratch, lane, ec, p.row_mask);
                     // accumulator drained: hand it back to the leader's MMA warp
                     tc_fence_before();
                     __syncwarp();
@@ -275,7 +278,7 @@ int scan3_max_clusters(int cap, int span, int sm_count) {
 
 int scan3_max_clusters_query(int cap, int span, int sm_count) {
     const size_t smem = scan3_smem_bytes(cap, span);
-    if (cudaFuncSetAttribute(dense_scan3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(dense_scan3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return sm_count / 2;
     }
@@ -284,7 +287,7 @@ int scan3_max_clusters_query(int cap, int span, int sm_count) {
     cfg.gridDim = dim3(sm_count / 2 * 2);
     cfg.dynamicSmemBytes = smem;
     int max_active = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_active, dense_scan3_kernel, &cfg) != cudaSuccess || max_active <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&max_active, dense_scan3_kernel<1>, &cfg) != cudaSuccess || max_active <= 0) {
         cudaGetLastError();
         return sm_count / 2;
     }
@@ -300,10 +303,15 @@ int launch_scan3(const void* corpus16, int dtype, const ScanParams& sp, int max_
     rc = make_tensor_map(&map_x, corpus16, sp.n_rows, sp.dim, dtype, T3_HALF);
     if (rc) return rc;
     const size_t smem = scan3_smem_bytes(sp.cap > span_cap ? sp.cap : span_cap, span_max);
-    B200_CUDA_CHECK(cudaFuncSetAttribute(dense_scan3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const char* ev = getenv("B200RAG_EPI");                 // A/B switch of the epilogue variant (tc_common.cuh: epi_filter_group)
+    const bool var0 = ev && ev[0] == '0';
+    if (var0) B200_CUDA_CHECK(cudaFuncSetAttribute(dense_scan3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else B200_CUDA_CHECK(cudaFuncSetAttribute(dense_scan3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int n_clusters = sp.n_items < max_clusters ? sp.n_items : max_clusters;
     if (n_clusters < 1) n_clusters = 1;
-    dense_scan3_kernel<<<n_clusters * 2, T3_THREADS, smem, st>>>(map_q, map_x, sp); count_launch();
+    if (var0) dense_scan3_kernel<0><<<n_clusters * 2, T3_THREADS, smem, st>>>(map_q, map_x, sp);
+    else dense_scan3_kernel<1><<<n_clusters * 2, T3_THREADS, smem, st>>>(map_q, map_x, sp);
+    count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;
 }

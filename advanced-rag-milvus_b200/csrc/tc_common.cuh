@@ -335,6 +335,12 @@ enum { ST_MMA_TOTAL = 0, ST_MMA_WAIT_FULL, ST_MMA_WAIT_TEMPTY, ST_MMA_WAIT_Q, ST
 // nearly full the warp compacts it to kp entries and raises the threshold.
 struct EpiCounters { long long compact = 0, ncompact = 0, nslow = 0; };
 
+// One group of 32 scores against the query's threshold.
+//   VAR 0: a 32-long chain of compares decides "anything above?"; the survivor path then walks all 32 columns.
+//   VAR 1: maxima of the four 8-column sub-groups (a tree) decide, and the survivor path only walks the sub-groups whose
+//          maximum beats the threshold.  A warp takes the survivor path when ANY of its 32 queries has a survivor in the
+//          group, which is most groups on small shards (12 k' survivors spread over few tiles), so its cost matters.
+template <int VAR>
 __device__ __forceinline__ void epi_filter_group(uint32_t (&r)[32], int c, bool partial, int64_t row0, int64_t n_rows, float& thr,
                                                  int& cnt, unsigned long long* buf, EpiCounters& ec, const uint32_t* row_mask) {
     if (partial) {
@@ -342,20 +348,49 @@ __device__ __forceinline__ void epi_filter_group(uint32_t (&r)[32], int c, bool 
         for (int i = 0; i < 32; ++i)
             if (row0 + c * 32 + i >= n_rows) r[i] = 0xff800000u;      // -inf: never passes
     }
-    bool any = false;
+    if (VAR == 0) {
+        bool any = false;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) any |= __uint_as_float(r[i]) > thr;
-    if (any) {
-        ++ec.nslow;
-        const uint32_t rbase = (uint32_t)(row0 + c * 32);
-        // metadata filter: consulted only here, for the rare rows that beat the threshold (the threshold itself is the
-        // k'-th best among ALLOWED rows, because only allowed rows are ever appended or sampled)
-        const uint32_t allowed = row_mask ? __ldg(row_mask + (rbase >> 5)) : 0xffffffffu;
+        for (int i = 0; i < 32; ++i) any |= __uint_as_float(r[i]) > thr;
+        if (any) {
+            ++ec.nslow;
+            const uint32_t rbase = (uint32_t)(row0 + c * 32);
+            // metadata filter: consulted only here, for the rare rows that beat the threshold (the threshold itself is the
+            // k'-th best among ALLOWED rows, because only allowed rows are ever appended or sampled)
+            const uint32_t allowed = row_mask ? __ldg(row_mask + (rbase >> 5)) : 0xffffffffu;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if (__uint_as_float(r[i]) > thr && ((allowed >> i) & 1u)) {
-                buf[cnt] = ((unsigned long long)r[i] << 32) | (unsigned long long)(rbase + i);
-                ++cnt;
+            for (int i = 0; i < 32; ++i) {
+                if (__uint_as_float(r[i]) > thr && ((allowed >> i) & 1u)) {
+                    buf[cnt] = ((unsigned long long)r[i] << 32) | (unsigned long long)(rbase + i);
+                    ++cnt;
+                }
+            }
+        }
+    } else {
+        float m8[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a0 = fmaxf(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+            float a1 = fmaxf(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+            float a2 = fmaxf(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+            float a3 = fmaxf(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+            m8[j] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+        }
+        if (fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])) > thr) {
+            ++ec.nslow;
+            const uint32_t rbase = (uint32_t)(row0 + c * 32);
+            const uint32_t allowed = row_mask ? __ldg(row_mask + (rbase >> 5)) : 0xffffffffu;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (m8[j] > thr) {
+#pragma unroll
+                    for (int i = 8 * j; i < 8 * j + 8; ++i) {
+                        if (__uint_as_float(r[i]) > thr && ((allowed >> i) & 1u)) {
+                            buf[cnt] = ((unsigned long long)r[i] << 32) | (unsigned long long)(rbase + i);
+                            ++cnt;
+                        }
+                    }
+                }
             }
         }
     }
@@ -386,7 +421,7 @@ __device__ __forceinline__ void epi_make_room(float& thr, int& cnt, unsigned lon
 }
 
 // The 32-column TMEM loads are software pipelined: while one group of 32 scores is compared, the next is in flight.
-template <int NG>
+template <int NG, int VAR>
 __device__ __forceinline__ void epi_filter_tile(uint32_t taddr, int64_t row0, int64_t n_rows, float& thr, int& cnt,
                                                 unsigned long long* buf, unsigned int* my_gthr, int kp, int cap,
                                                 uint32_t scratch, int lane, EpiCounters& ec, const uint32_t* row_mask) {
@@ -399,11 +434,11 @@ __device__ __forceinline__ void epi_filter_tile(uint32_t taddr, int64_t row0, in
         epi_make_room(thr, cnt, buf, my_gthr, kp, cap, scratch, lane, ec);
         tmem_ld32_wait(ra);
         tmem_ld32_issue(taddr + (c + 1) * 32, rb);
-        epi_filter_group(ra, c, partial, row0, n_rows, thr, cnt, buf, ec, row_mask);
+        epi_filter_group<VAR>(ra, c, partial, row0, n_rows, thr, cnt, buf, ec, row_mask);
         epi_make_room(thr, cnt, buf, my_gthr, kp, cap, scratch, lane, ec);
         tmem_ld32_wait(rb);
         if (c + 2 < NG) tmem_ld32_issue(taddr + (c + 2) * 32, ra);
-        epi_filter_group(rb, c + 1, partial, row0, n_rows, thr, cnt, buf, ec, row_mask);
+        epi_filter_group<VAR>(rb, c + 1, partial, row0, n_rows, thr, cnt, buf, ec, row_mask);
     }
 }
 
