@@ -162,3 +162,61 @@ def test_retriever_without_a_gpu_fails_loudly_in_fusion():
     from b200rag.index_manager import B200IndexManager
     with pytest.raises(Exception):
         B200IndexManager(semantic_dim=8, domain_dim=8, device="cpu")
+
+
+class _StubManager:
+    """search_batch stand-in for the micro-batcher: echoes (collection, top_k, query checksum) per query."""
+
+    def __init__(self, fail=False):
+        self.calls, self.fail = [], fail
+
+    def search_batch(self, batch, collection, top_k, filters):
+        self.calls.append((collection, top_k, filters, len(batch)))
+        if self.fail:
+            raise RuntimeError("index down")
+        if collection == "sparse_index":
+            return [[{"id": f"s{sum(q['indices'])}", "score": float(top_k)}] for q in batch]
+        return [[{"id": f"d{int(row.sum())}", "score": float(top_k)}] for row in batch]
+
+
+def test_micro_batcher_groups_concurrent_requests_and_routes_results():
+    from b200rag.index_manager import _MicroBatcher
+    stub = _StubManager()
+    mb = _MicroBatcher(stub, max_batch=64, max_wait_s=0.02)
+
+    async def storm():
+        dense = [mb.submit(np.full(4, i, dtype=np.float32), "semantic_index", 10, None) for i in range(12)]
+        sparse = [mb.submit({"indices": [i, i + 1], "values": [1.0, 1.0]}, "sparse_index", 10, None) for i in range(5)]
+        other_k = [mb.submit(np.full(4, 7, dtype=np.float32), "semantic_index", 20, 'doc_id == "x"')]
+        return await asyncio.gather(*dense, *sparse, *other_k)
+
+    out = _run(storm())
+    assert [h[0]["id"] for h in out[:12]] == [f"d{4 * i}" for i in range(12)]
+    assert [h[0]["id"] for h in out[12:17]] == [f"s{2 * i + 1}" for i in range(5)]
+    assert out[17][0] == {"id": "d28", "score": 20.0}
+    assert sorted(stub.calls) == sorted([("semantic_index", 10, None, 12), ("sparse_index", 10, None, 5),
+                                         ("semantic_index", 20, 'doc_id == "x"', 1)])
+    assert mb.batches == 3
+    mb.close()
+
+
+def test_micro_batcher_flushes_at_max_batch_and_propagates_failures():
+    from b200rag.index_manager import _MicroBatcher
+    stub = _StubManager()
+    mb = _MicroBatcher(stub, max_batch=4, max_wait_s=5.0)          # only the size trigger can fire within the test
+
+    async def four():
+        return await asyncio.wait_for(asyncio.gather(*[mb.submit(np.zeros(4, np.float32), "semantic_index", 5, None)
+                                                       for _ in range(8)]), timeout=2.0)
+
+    assert len(_run(four())) == 8 and [c[3] for c in stub.calls] == [4, 4]
+    mb.close()
+    bad = _MicroBatcher(_StubManager(fail=True), max_batch=2, max_wait_s=5.0)
+
+    async def failing():
+        return await asyncio.gather(*[bad.submit(np.zeros(4, np.float32), "semantic_index", 5, None) for _ in range(2)],
+                                    return_exceptions=True)
+
+    res = _run(failing())
+    assert all(isinstance(e, RuntimeError) and "index down" in str(e) for e in res)
+    bad.close()
