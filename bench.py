@@ -14,7 +14,7 @@ rank scans its shard, one NCCL all-gather carries the k candidates per query, th
   e2e       same metric through the public Python API with HOST buffers: pinned fp32 queries -> H2D -> search ->
             D2H of ids + scores, every step, consumed by a double-buffered host loop (results of step i are on the host
             before step i+2 is issued).
-  roofline  the dominant kernel (dense_scan_kernel): algorithmic FLOPs per launch / its CUDA-event duration, measured
+  roofline  the dominant kernel (dense_scan3_kernel, the full scan): algorithmic FLOPs per launch / its CUDA-event duration, measured
             live inside the timed region through the b200rag_profile_next_scan hook.
   cpu_baseline / --impl reference: the same exact search on the box's host cores (numpy BLAS sgemm + partial sort,
             "Milvus mocked" -- see oracle/oracle.py) on a bounded row sample, extrapolated linearly in rows.
