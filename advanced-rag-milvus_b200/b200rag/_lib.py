@@ -39,6 +39,7 @@ SIGNATURES = {
                                                  c_void_p, c_size_t, c_int32, c_void_p]),
     "b200rag_profile_next_scan": (ctypes.c_int, [c_void_p, c_void_p]),
     "b200rag_debug_scan_stats": (ctypes.c_int, [c_int32, c_void_p, c_int32]),
+    "b200rag_debug_sparse_stats": (ctypes.c_int, [c_int32, c_void_p, c_int32]),
     "b200rag_sparse_topk_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
     "b200rag_sparse_topk": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                            c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64,

@@ -89,8 +89,14 @@ struct BlockTopK {
         if (valid) {
             bool pass = !st->has_thr || key_gt<LoT>(h, l, st->thr_hi, (LoT)st->thr_lo);
             if (pass) {
-                int a = st->active;
-                int i = atomicAdd(&st->count, 1);
+                // lanes that arrive here together take their slots with one atomic
+                const unsigned act = __activemask();
+                const int lane = threadIdx.x & 31, leader = __ffs((int)act) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&st->count, __popc(act));
+                base = __shfl_sync(act, base, leader);
+                const int i = base + __popc(act & ((1u << lane) - 1u));
+                const int a = st->active;
                 hi[a][i] = h;
                 lo[a][i] = l;
             }
@@ -120,8 +126,12 @@ struct BlockTopK {
         return d >= NLO ? (int)((h >> ((d - NLO) * 8)) & 255) : (int)((l >> (d * 8)) & 255);
     }
 
-    // Keep exactly the k greatest entries (precondition: all threads call; entry/exit synchronised).
-    __device__ void compact() {
+    // Keep the k greatest entries (precondition: all threads call; entry/exit synchronised).
+    // exact = false (streaming use): up to reserve/2 further entries may stay -- the radix walk stops at the first digit
+    // whose boundary bucket overshoots k by no more than that.  Result lists are full of tied scores (equal BM25 weights,
+    // duplicated rows), and splitting a tie group exactly costs a walk over all the id digits as well; the final
+    // compaction (finalize) does that once.
+    __device__ void compact(bool exact = false) {
         const int tid = threadIdx.x;
         const int n = st->count;
         const int a = st->active;
@@ -132,6 +142,7 @@ struct BlockTopK {
         uint64_t sel_hi = 0, mask_hi = 0;
         LoT sel_lo = 0, mask_lo = 0;
         int want = k;
+        const int slack = exact ? 0 : reserve / 2;
         if (start_digit < TOP_DIGIT) {   // bytes above start_digit are identical for all entries: part of the prefix from the start
             mask_hi = ~uint64_t(0) << ((start_digit - NLO + 1) * 8);
             sel_hi = bh[0] & mask_hi;
@@ -140,10 +151,23 @@ struct BlockTopK {
         for (int d = start_digit; d >= 0; --d) {
             for (int i = tid; i < 256; i += THREADS) st->hist[i] = 0;
             __syncthreads();
-            for (int i = tid; i < n; i += THREADS) {
-                uint64_t h = bh[i];
-                LoT l = bl[i];
-                if ((h & mask_hi) == sel_hi && (l & mask_lo) == sel_lo) atomicAdd(&st->hist[key_digit(h, l, d)], 1);
+            // Scores of one result list share their top bytes, so the first passes put (nearly) every entry into one bin:
+            // lanes with equal bins are counted with a single atomic.
+            for (int i0 = 0; i0 < n; i0 += THREADS) {
+                const int i = i0 + tid;
+                bool ok = false;
+                int bin = 0;
+                if (i < n) {
+                    const uint64_t h = bh[i];
+                    const LoT l = bl[i];
+                    ok = (h & mask_hi) == sel_hi && (l & mask_lo) == sel_lo;
+                    bin = key_digit(h, l, d);
+                }
+                const unsigned act = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    const unsigned peers = __match_any_sync(act, bin);
+                    if ((int)(tid & 31) == __ffs((int)peers) - 1) atomicAdd(&st->hist[bin], __popc(peers));
+                }
             }
             __syncthreads();
             if (tid < 32) {
@@ -168,7 +192,7 @@ struct BlockTopK {
                     }
                     st->sel_digit = tid * 8 + b;
                     st->sel_want = want - cum;
-                    st->sel_exact = c[b] == want - cum;
+                    st->sel_exact = c[b] - (want - cum) <= slack;
                 }
             }
             __syncthreads();
@@ -187,27 +211,40 @@ struct BlockTopK {
             }
         }
         // complete walk: (sel_hi, sel_lo) is the k-th greatest key and `want` of the entries equal to it are kept.
-        // early stop:    entries whose masked key is >= the selected prefix are kept (exactly k of them).
+        // early stop:    entries whose masked key is >= the selected prefix are kept (k of them, plus at most `slack`).
         if (tid == 0) { st->out_count = 0; st->eq_taken = 0; }
         __syncthreads();
         uint64_t* oh = hi[a ^ 1];
         LoT* ol = lo[a ^ 1];
-        for (int i = tid; i < n; i += THREADS) {
-            uint64_t h = bh[i];
-            LoT l = bl[i];
-            bool keep;
-            if (early) {
-                const uint64_t mh = h & mask_hi;
-                const LoT ml = l & mask_lo;
-                keep = mh > sel_hi || (mh == sel_hi && ml >= sel_lo);
-            } else {
-                keep = key_gt<LoT>(h, l, sel_hi, sel_lo);
-                if (!keep && h == sel_hi && l == sel_lo) keep = atomicAdd(&st->eq_taken, 1) < want;
+        for (int i0 = 0; i0 < n; i0 += THREADS) {
+            const int i = i0 + tid;
+            uint64_t h = 0;
+            LoT l = 0;
+            bool keep = false;
+            if (i < n) {
+                h = bh[i];
+                l = bl[i];
+                if (early) {
+                    const uint64_t mh = h & mask_hi;
+                    const LoT ml = l & mask_lo;
+                    keep = mh > sel_hi || (mh == sel_hi && ml >= sel_lo);
+                } else {
+                    keep = key_gt<LoT>(h, l, sel_hi, sel_lo);
+                    if (!keep && h == sel_hi && l == sel_lo) keep = atomicAdd(&st->eq_taken, 1) < want;
+                }
             }
-            if (keep) {
-                int j = atomicAdd(&st->out_count, 1);
-                oh[j] = h;
-                ol[j] = l;
+            // one slot reservation per warp
+            const unsigned kept = __ballot_sync(0xffffffffu, keep);
+            if (kept) {
+                const int lane = tid & 31, leader = __ffs((int)kept) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&st->out_count, __popc(kept));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (keep) {
+                    const int j = base + __popc(kept & ((1u << lane) - 1u));
+                    oh[j] = h;
+                    ol[j] = l;
+                }
             }
         }
         if (early) {
@@ -228,7 +265,7 @@ struct BlockTopK {
 
     // Reduce to <= k entries and sort them best first.  Entry: synchronised.  Exit: synchronised.
     __device__ void finalize() {
-        compact();
+        compact(/*exact=*/true);
         const int tid = threadIdx.x;
         const int a = st->active;
         const int n = st->count;

@@ -8,9 +8,14 @@
 //     term id with a barrier between terms, so every document sees  acc = fmaf(qv, w, acc)  in the canonical order
 //     (bit-identical to oracle/exact_scan.c:orc_sparse_topk).  Postings of one term hit distinct documents: no atomics
 //     on the accumulators; a touched-bitmap marks the candidates;
-//   * candidates are collected from the bitmap (a thread owns one or two 32-document words), losers against the running
-//     k-th best are dropped on the spot, survivors go to the block-level streaming top-k (select.cuh), which lives for
-//     the whole walk, so later blocks are filtered by the threshold earlier blocks established.
+//   * candidates are collected in one of two ways, chosen per block from the running k-th best score `thr`:
+//       thr > 0  (the steady state): every thread reads 32+ accumulators with LDS.128, keeps the few that are >= thr and
+//                writes zeros back -- no bitmap, no atomics in the accumulate step (an untouched document holds exactly 0,
+//                so it can never pass a positive threshold);
+//       otherwise (first block(s), or < k positive candidates so far): a touched-bitmap marks the candidates and a
+//                thread walks the set bits of one or two 32-document words;
+//     survivors go to the block-level streaming top-k (select.cuh), which lives for the whole walk, so later blocks
+//     are filtered by the threshold earlier blocks established.
 // Algorithmic HBM traffic = 6 bytes per posting of the query's terms.  grid = (queries, slices): with fewer queries
 // than SMs the blocks are split into slices; merge_topk_kernel reduces the slices.
 // (Round 1 first ran one CTA per (query, block) that re-scanned all 32768 documents of the block: 4.1 ms for 256
@@ -23,17 +28,49 @@ namespace b200rag {
 int launch_merge(const double* cand_scores, const int64_t* cand_ids, int n_launch, const int32_t* q_list, int n_cand, int k,
                  double* out_scores_f64, float* out_scores_f32, int64_t* out_ids, int32_t* out_counts, cudaStream_t st);
 
+// Debug: per-CTA cycle counters by phase (b200rag_debug_sparse_stats).  Thread 0 keeps them in shared memory (no registers).
+constexpr int SP_NSTAT = 12;
+static unsigned long long* g_sparse_stats = nullptr;     // device buffer [SP_STAT_CTAS][SP_NSTAT], or null
+constexpr int SP_STAT_CTAS = 1024;
+#define SP_MARK(i)                                                                     \
+    do {                                                                               \
+        if (stats && tid == 0) {                                                       \
+            const long long now_ = clock64();                                          \
+            s_stat[i] += (unsigned long long)(now_ - s_last);                          \
+            s_last = now_;                                                             \
+        }                                                                              \
+    } while (0)
+
 constexpr int SP_THREADS = 512;     // with 16384-document blocks two CTAs fit per SM and overlap each other's latencies
 constexpr int SP_TG = 8;       // query terms fetched together (one register pair per term and thread)
+
+__device__ __forceinline__ void sp_cp_async8(void* smem_dst, const void* gsrc, unsigned src_bytes) {
+    // 8-byte asynchronous global -> shared copy; src_bytes = 0 writes zeros (nothing is read)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
+                 "r"(src_bytes)
+                 : "memory");
+}
 
 __global__ void __launch_bounds__(SP_THREADS, 2)
 sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __restrict__ post_doc,
                     const float* __restrict__ post_w, int64_t n_docs, int n_terms, int block_docs, int n_blocks, int n_slices,
                     const int64_t* __restrict__ q_ptr, const int32_t* __restrict__ q_terms, const float* __restrict__ q_vals,
                     int k, int cap, int64_t id_offset, double* __restrict__ part_scores, int64_t* __restrict__ part_ids,
-                    const uint32_t* __restrict__ doc_mask) {
+                    const uint32_t* __restrict__ doc_mask, int flags, unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(16) char smem[];
+    __shared__ unsigned long long s_stat[SP_NSTAT];
+    __shared__ long long s_last;
+    // posting ranges of the current term group: slots 0/1 = first group of block (blk & 1), filled one block ahead by
+    // cp.async; slot 2 = later groups (queries with more than SP_TG terms), filled synchronously
+    __shared__ __align__(16) long long s_beg[3][SP_TG], s_end[3][SP_TG];
+    __shared__ float s_qv[2][SP_TG];
+    __shared__ int s_total[2];                                                       // candidates of block (blk & 1)
     const int tid = threadIdx.x;
+    if (stats && tid == 0) {
+        for (int i = 0; i < SP_NSTAT; ++i) s_stat[i] = 0;
+        s_last = clock64();
+    }
+    const bool allow_dense = flags & 1, allow_bulk = flags & 2;
     const int q = blockIdx.x;
     const int slice = blockIdx.y;
     const int n_words = block_docs / 32;                                            // <= 2048
@@ -41,117 +78,213 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
     uint32_t* touched = reinterpret_cast<uint32_t*>(smem + (size_t)block_docs * 4);  // [n_words]
     char* p = smem + (size_t)block_docs * 4 + (size_t)n_words * 4;
     p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
-    __shared__ long long s_beg[SP_TG], s_end[SP_TG];
-    __shared__ float s_qv[SP_TG];
     BlockTopK<SP_THREADS, uint32_t> tk;
     tk.attach(p, cap, k, SP_THREADS, /*start_digit=*/BlockTopK<SP_THREADS, uint32_t>::NLO + 3);
     tk.init();
     for (int i = tid; i < block_docs; i += SP_THREADS) acc[i] = 0.0f;
     for (int i = tid; i < n_words; i += SP_THREADS) touched[i] = 0u;
-    __syncthreads();
+    if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
 
     const int64_t qs = q_ptr[q];
     const int nq = (int)(q_ptr[q + 1] - qs);
     const int b0 = (int)((int64_t)slice * n_blocks / n_slices), b1 = (int)((int64_t)(slice + 1) * n_blocks / n_slices);
-    // ranges of the first term group of the NEXT block are fetched one block ahead (pointer -> postings is a dependent chain)
-    long long pre_s = 0, pre_e = 0;
-    float pre_qv = 0.f;
+    // The chain block -> term pointers -> postings is two dependent trips to HBM.  Lanes 0..SP_TG-1 copy the NEXT block's
+    // ranges of the first term group straight into shared memory (cp.async: no registers, nothing waits on it) while the
+    // current block is accumulated.
     int my_t = -1;
-    if (tid < SP_TG && tid < nq) {
-        const int t = q_terms[qs + tid];
-        if (t >= 0 && t < n_terms) { my_t = t; pre_qv = q_vals[qs + tid]; }
+    if (tid < SP_TG) {
+        float qv = 0.f;
+        if (tid < nq) {
+            const int t = q_terms[qs + tid];
+            if (t >= 0 && t < n_terms) { my_t = t; qv = q_vals[qs + tid]; }
+        }
+        s_qv[0][tid] = qv;
     }
-    if (my_t >= 0 && b0 < b1) {
-        const int64_t* tp0 = blk_term_ptr + (size_t)b0 * (n_terms + 1);
-        pre_s = tp0[my_t]; pre_e = tp0[my_t + 1];
+    auto stage_ranges = [&](int blk) {          // lanes 0..SP_TG-1
+        const int64_t* src = blk_term_ptr + (size_t)blk * (n_terms + 1) + (my_t >= 0 ? my_t : 0);
+        const unsigned sz = my_t >= 0 ? 8u : 0u;
+        sp_cp_async8(&s_beg[blk & 1][tid], src, sz);
+        sp_cp_async8(&s_end[blk & 1][tid], src + 1, sz);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (tid < SP_TG && b0 < b1 && nq > 0) {
+        stage_ranges(b0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
+    __syncthreads();
+    SP_MARK(0);                                           // init
+    bool acc_busy = false;      // CTA-uniform: the previous block's survivors may still be read out of (and zeroed in) `acc`
     for (int blk = b0; blk < b1; ++blk) {
         const int64_t doc0 = (int64_t)blk * block_docs;
         const int64_t* tp = blk_term_ptr + (size_t)blk * (n_terms + 1);
+        const int cur = blk & 1;
+        float thr_f = tk.threshold_hi32_as_float();      // stable here: the previous collect ended on a barrier
+        const bool dense = allow_dense && thr_f > 0.0f;  // CTA-uniform
+        const bool have_next = blk + 1 < b1 && nq > 0;
+        // slot cur^1 was last read while block blk-1 was accumulated; every thread has passed a barrier since
+        if (tid < SP_TG && have_next) stage_ranges(blk + 1);
         // ---- accumulate, SP_TG terms at a time ---------------------------------------------------------------
         for (int g0 = 0; g0 < nq; g0 += SP_TG) {
-            if (tid < SP_TG) {
-                long long s = 0, e = 0;
-                float qv = 0.f;
-                if (g0 == 0) {
-                    s = pre_s; e = pre_e; qv = pre_qv;
-                    if (my_t >= 0 && blk + 1 < b1) {                  // issue the next block's pointer loads now
-                        const int64_t* tpn = tp + (n_terms + 1);
-                        pre_s = tpn[my_t]; pre_e = tpn[my_t + 1];
+            const int slot = g0 == 0 ? cur : 2, qslot = g0 == 0 ? 0 : 1;
+            if (g0 > 0) {
+                if (tid < SP_TG) {
+                    long long s = 0, e = 0;
+                    float qv = 0.f;
+                    if (g0 + tid < nq) {
+                        const int t = q_terms[qs + g0 + tid];
+                        if (t >= 0 && t < n_terms) { s = tp[t]; e = tp[t + 1]; qv = q_vals[qs + g0 + tid]; }
                     }
-                } else if (g0 + tid < nq) {
-                    const int t = q_terms[qs + g0 + tid];
-                    if (t >= 0 && t < n_terms) { s = tp[t]; e = tp[t + 1]; qv = q_vals[qs + g0 + tid]; }
+                    s_beg[2][tid] = s; s_end[2][tid] = e; s_qv[1][tid] = qv;
                 }
-                s_beg[tid] = s; s_end[tid] = e; s_qv[tid] = qv;
+                __syncthreads();
             }
-            __syncthreads();
             int dreg[SP_TG];
             float wreg[SP_TG];
 #pragma unroll
             for (int j = 0; j < SP_TG; ++j) {
-                const long long i = s_beg[j] + tid;
+                const long long i = s_beg[slot][j] + tid;
                 dreg[j] = -1;
                 wreg[j] = 0.f;
-                if (i < s_end[j]) { dreg[j] = post_doc[i]; wreg[j] = post_w[i]; }
+                if (i < s_end[slot][j]) { dreg[j] = post_doc[i]; wreg[j] = post_w[i]; }
+            }
+            if (acc_busy) {                               // (waits while the postings are in flight)
+                __syncthreads();
+                acc_busy = false;
             }
 #pragma unroll
             for (int j = 0; j < SP_TG; ++j) {
-                const float qv = s_qv[j];
+                const float qv = s_qv[qslot][j];
                 if (dreg[j] >= 0) {
                     const int d = dreg[j];
                     acc[d] = fmaf(qv, wreg[j], acc[d]);
-                    atomicOr(&touched[d >> 5], 1u << (d & 31));
+                    if (!dense) atomicOr(&touched[d >> 5], 1u << (d & 31));
                 }
-                for (long long i = s_beg[j] + tid + SP_THREADS; i < s_end[j]; i += SP_THREADS) {     // long posting lists
-                    const int d = post_doc[i];
-                    acc[d] = fmaf(qv, post_w[i], acc[d]);
-                    atomicOr(&touched[d >> 5], 1u << (d & 31));
+                const long long e = s_end[slot][j];
+                for (long long i = s_beg[slot][j] + tid + SP_THREADS; i < e; i += 2 * SP_THREADS) {     // long posting lists, two in flight
+                    const long long i1 = i + SP_THREADS;
+                    const int d0 = post_doc[i];
+                    const float w0 = post_w[i];
+                    int d1 = -1;
+                    float w1 = 0.f;
+                    if (i1 < e) { d1 = post_doc[i1]; w1 = post_w[i1]; }
+                    acc[d0] = fmaf(qv, w0, acc[d0]);
+                    if (!dense) atomicOr(&touched[d0 >> 5], 1u << (d0 & 31));
+                    if (d1 >= 0) {
+                        acc[d1] = fmaf(qv, w1, acc[d1]);
+                        if (!dense) atomicOr(&touched[d1 >> 5], 1u << (d1 & 31));
+                    }
                 }
+                // the next block's ranges were requested many barriers ago: make them visible with the group's last barrier
+                if (j == SP_TG - 1 && tid < SP_TG) asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncthreads();
+                if (j == 0) SP_MARK(2);                   // postings fetched, first term applied
             }
+            SP_MARK(3);                                   // remaining terms applied
         }
-        // ---- collect: a thread owns words tid and tid + SP_THREADS of the bitmap -----------------------------------
-        // Losers are dropped with ONE float compare against the running k-th best score (read once per block; the exact
-        // (score, id) comparison happens only for the few candidates at or above it).
+        // ---- collect -------------------------------------------------------------------------------------------------
+        // `m` = this thread's candidate positions.  Losers are dropped with ONE float compare against the running k-th best
+        // score; the exact (score, id) comparison happens only for the few candidates at or above it.
         unsigned long long m = 0;
-        if (tid < n_words) { m = touched[tid]; touched[tid] = 0u; }
-        if (tid + SP_THREADS < n_words) { m |= (unsigned long long)touched[tid + SP_THREADS] << 32; touched[tid + SP_THREADS] = 0u; }
-        if (doc_mask && m) {
-            // metadata filter: documents that are not allowed are dropped here (their accumulators still have to go back to
-            // zero).  block_docs is a multiple of 32, so a bitmap word of the block is a word of the mask.
-            unsigned long long allowed = 0;
-            const int64_t w0 = (doc0 >> 5) + tid, w1 = w0 + SP_THREADS, n_mask_words = (n_docs + 31) >> 5;
-            if (tid < n_words && w0 < n_mask_words) allowed = __ldg(doc_mask + w0);
-            if (tid + SP_THREADS < n_words && w1 < n_mask_words) allowed |= (unsigned long long)__ldg(doc_mask + w1) << 32;
-            unsigned long long drop = m & ~allowed;
-            while (drop) {
-                const int bpos = __ffsll((long long)drop) - 1;
-                drop &= drop - 1;
-                acc[bpos < 32 ? tid * 32 + bpos : (tid + SP_THREADS) * 32 + (bpos - 32)] = 0.0f;
+        if (dense) {
+            // bit 4*j + c  <->  document 4 * (j * SP_THREADS + tid) + c
+            float4* acc4 = reinterpret_cast<float4*>(acc);
+            const int nv = block_docs >> 2;
+            int sh = 0;
+            for (int v = tid; v < nv; v += SP_THREADS, sh += 4) {
+                const float4 x = acc4[v];
+                if ((__float_as_uint(x.x) | __float_as_uint(x.y) | __float_as_uint(x.z) | __float_as_uint(x.w)) == 0u) continue;
+                const unsigned b = (!(x.x < thr_f) ? 1u : 0u) | (!(x.y < thr_f) ? 2u : 0u) | (!(x.z < thr_f) ? 4u : 0u) |
+                                   (!(x.w < thr_f) ? 8u : 0u);
+                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (b) {
+                    m |= (unsigned long long)b << sh;
+                    if (b & 1u) z.x = x.x;
+                    if (b & 2u) z.y = x.y;
+                    if (b & 4u) z.z = x.z;
+                    if (b & 8u) z.w = x.w;
+                }
+                acc4[v] = z;
             }
-            m &= allowed;
+        } else {
+            // bits 0..31 <-> word tid of the bitmap, bits 32..63 <-> word tid + SP_THREADS
+            if (tid < n_words) { m = touched[tid]; touched[tid] = 0u; }
+            if (tid + SP_THREADS < n_words) { m |= (unsigned long long)touched[tid + SP_THREADS] << 32; touched[tid + SP_THREADS] = 0u; }
+            if (doc_mask && m) {
+                // metadata filter: documents that are not allowed are dropped here (their accumulators still have to go back
+                // to zero).  block_docs is a multiple of 32, so a bitmap word of the block is a word of the mask.
+                unsigned long long allowed = 0;
+                const int64_t w0 = (doc0 >> 5) + tid, w1 = w0 + SP_THREADS, n_mask_words = (n_docs + 31) >> 5;
+                if (tid < n_words && w0 < n_mask_words) allowed = __ldg(doc_mask + w0);
+                if (tid + SP_THREADS < n_words && w1 < n_mask_words) allowed |= (unsigned long long)__ldg(doc_mask + w1) << 32;
+                unsigned long long drop = m & ~allowed;
+                while (drop) {
+                    const int bpos = __ffsll((long long)drop) - 1;
+                    drop &= drop - 1;
+                    acc[bpos < 32 ? tid * 32 + bpos : (tid + SP_THREADS) * 32 + (bpos - 32)] = 0.0f;
+                }
+                m &= allowed;
+            }
         }
-        float thr_f = tk.threshold_hi32_as_float();
-        while (__syncthreads_or(m != 0ull)) {
-            bool have = false;
-            uint64_t h = 0;
-            uint32_t l = 0;
+        // next candidate of this thread at or above the threshold (and allowed): true + its key, or false with m == 0
+        auto next_candidate = [&](uint64_t& h, uint32_t& l) -> bool {
             while (m) {
-                const uint32_t lo32 = (uint32_t)m;
-                const int bpos = lo32 ? __ffs((int)lo32) - 1 : 32 + __ffs((int)(uint32_t)(m >> 32)) - 1;
+                const int bpos = __ffsll((long long)m) - 1;
                 m &= m - 1;
-                const int d = bpos < 32 ? tid * 32 + bpos : (tid + SP_THREADS) * 32 + (bpos - 32);
+                const int d = dense ? ((((bpos >> 2) * SP_THREADS + tid) << 2) | (bpos & 3))
+                                    : (bpos < 32 ? tid * 32 + bpos : (tid + SP_THREADS) * 32 + (bpos - 32));
                 const float sc = acc[d];
                 acc[d] = 0.0f;
                 if (sc < thr_f) continue;
+                if (dense && doc_mask) {            // (the bitmap path filtered its words above)
+                    const int64_t g = doc0 + d;
+                    if (!((__ldg(doc_mask + (g >> 5)) >> (g & 31)) & 1u)) continue;
+                }
                 h = (uint64_t)mono32(sc);
                 l = ~(uint32_t)(doc0 + d);
-                if (tk.passes(h, l)) { have = true; break; }
+                if (tk.passes(h, l)) return true;
             }
-            tk.offer(have, h, l);
-            tk.settle();
+            return false;
+        };
+        {
+            int c = __popcll(m);
+            c = __reduce_add_sync(0xffffffffu, c);
+            if ((tid & 31) == 0 && c) atomicAdd(&s_total[cur], c);
+        }
+        int held = tk.count();                            // nobody appends between the last settle and the next barrier
+        __syncthreads();
+        const int total = s_total[cur];
+        if (tid == 0) s_total[cur ^ 1] = 0;               // the previous block's counter: its readers are barriers behind
+        SP_MARK(4);                                       // accumulators scanned
+        if (total == 0) continue;
+        if (held + total > cap && held > k) {
+            // no room for this block's survivors: keep the k best now (raises the threshold, so fewer of them survive)
+            tk.compact();
+            held = tk.count();
             thr_f = tk.threshold_hi32_as_float();
+            if (stats && tid == 0) s_stat[9] += 1;
+            SP_MARK(1);                                   // compaction
+        }
+        if (allow_bulk && held + total <= cap) {
+            // everything fits: every thread appends all its survivors at once.  The barrier that must separate this from the
+            // next block's accumulation is taken there, under the postings' latency; the count and the threshold are next
+            // read behind the term barriers.
+            uint64_t h = 0;
+            uint32_t l = 0;
+            while (next_candidate(h, l)) tk.offer(true, h, l);
+            if (stats && tid == 0) { s_stat[7] += 1; s_stat[10] += total; }
+            acc_busy = true;
+            SP_MARK(5);                                   // bulk append
+        } else {
+            while (__syncthreads_or(m != 0ull)) {
+                if (stats && tid == 0) s_stat[7] += 1;                  // candidate rounds
+                uint64_t h = 0;
+                uint32_t l = 0;
+                const bool have = next_candidate(h, l);
+                tk.offer(have, h, l);
+                tk.settle();
+                thr_f = tk.threshold_hi32_as_float();
+            }
+            SP_MARK(8);                                   // candidate rounds (offer + settle, one candidate per thread)
         }
     }
     __syncthreads();
@@ -170,6 +303,12 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
             pi[i] = -1;
         }
     }
+    SP_MARK(6);                                           // finalize + output
+    if (stats && tid == 0) {
+        const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+        if (cta < SP_STAT_CTAS)
+            for (int i = 0; i < SP_NSTAT; ++i) stats[(size_t)cta * SP_NSTAT + i] = s_stat[i];
+    }
 }
 
 static size_t sparse_smem(int block_docs, int k, int* cap_out) {
@@ -184,6 +323,23 @@ static size_t sparse_smem(int block_docs, int k, int* cap_out) {
 using namespace b200rag;
 
 extern "C" {
+
+int b200rag_debug_sparse_stats(int32_t enable, uint64_t* out_host, int32_t max_ctas) {
+    const size_t bytes = (size_t)SP_STAT_CTAS * SP_NSTAT * sizeof(unsigned long long);
+    if (out_host && g_sparse_stats) {
+        B200_CUDA_CHECK(cudaDeviceSynchronize());
+        const int n = max_ctas < SP_STAT_CTAS ? max_ctas : SP_STAT_CTAS;
+        B200_CUDA_CHECK(cudaMemcpy(out_host, g_sparse_stats, (size_t)n * SP_NSTAT * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    if (enable && !g_sparse_stats) {
+        B200_CUDA_CHECK(cudaMalloc(&g_sparse_stats, bytes));
+        B200_CUDA_CHECK(cudaMemset(g_sparse_stats, 0, bytes));
+    } else if (!enable && g_sparse_stats) {
+        B200_CUDA_CHECK(cudaFree(g_sparse_stats));
+        g_sparse_stats = nullptr;
+    }
+    return B200RAG_OK;
+}
 
 size_t b200rag_sparse_topk_workspace_bytes(int64_t n_docs, int32_t block_docs, int32_t n_queries, int32_t k) {
     if (block_docs <= 0) return 0;
@@ -239,12 +395,17 @@ int b200rag_sparse_topk_masked(const int64_t* blk_term_ptr, const uint16_t* post
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     int64_t n_slices = (2 * (int64_t)sm_count) / n_queries;
     if (n_slices < 1) n_slices = 1;
+    // A/B switches (tools/sparse_ab.py): slices per query, and the dense collect mode
+    if (const char* e = getenv("B200RAG_SPARSE_SLICES")) { if (atoi(e) > 0) n_slices = atoi(e); }
+    // bit 0: dense collect mode, bit 1: bulk append
+    const char* ed = getenv("B200RAG_SPARSE_DENSE");
+    const int flags = ed ? atoi(ed) : 3;
     if (n_slices > n_blocks) n_slices = n_blocks;
     B200_REQUIRE(n_slices <= 65535, "sparse_topk: too many slices");
     dim3 grid((unsigned)n_queries, (unsigned)n_slices);
     sparse_query_kernel<<<grid, SP_THREADS, smem, st>>>(blk_term_ptr, post_doc, post_w, n_docs, n_terms, block_docs,
                                                        (int)n_blocks, (int)n_slices, q_ptr, q_terms, q_vals, k, cap, id_offset,
-                                                       part_scores, part_ids, doc_mask); count_launch();
+                                                       part_scores, part_ids, doc_mask, flags, g_sparse_stats); count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return launch_merge(part_scores, part_ids, n_queries, nullptr, (int)(n_slices * k), k, nullptr, out_scores, out_ids,
                         out_counts, st);

@@ -120,6 +120,12 @@ int b200rag_profile_next_scan(void* start_event, void* stop_event);
  * With out_host != NULL the counters of the last scan are copied to host memory (synchronous). */
 int b200rag_debug_scan_stats(int32_t enable, uint64_t* out_host, int32_t max_ctas);
 
+/* Debug/profiling: per-CTA cycle counters of the sparse scan (12 u64 slots per CTA, first 1024 CTAs: init, compaction
+ * after a bulk append, postings fetched + first term applied, remaining terms applied, accumulators scanned, bulk
+ * append, finalize + output, #collects with candidates, candidate rounds, #compactions, #candidates appended in bulk,
+ * unused).  Same protocol as b200rag_debug_scan_stats. */
+int b200rag_debug_sparse_stats(int32_t enable, uint64_t* out_host, int32_t max_ctas);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Sparse inner-product top-k over doc-range-blocked postings (K3).  Replaces Collection.search on
  * "sparse_index" (reference indexing.py:472,487-498,505-523, reached from retrieval.py:367-395).

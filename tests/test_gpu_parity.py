@@ -123,6 +123,38 @@ def test_sparse_matches_oracle(eng, oracle_lib, n_docs, vocab, n_q, k, block):
     assert np.array_equal(s.cpu().numpy().view(np.uint32), ref_s.view(np.uint32))      # bit exact fp32
 
 
+@pytest.mark.parametrize("signed", [False, True])
+def test_sparse_long_walk_both_collect_modes(eng, oracle_lib, signed):
+    """Enough queries that a CTA walks ALL blocks of its query (no slicing): after the first blocks the running k-th best
+    is positive and the collect switches from the touched-bitmap walk to the dense threshold scan.  With signed query
+    values many queries keep a non-positive threshold and stay on the bitmap path.  Also with a document filter."""
+    from b200rag import synth
+    o = oracle_lib
+    n_docs, vocab, n_q, k = 40000, 1500, 320, 12
+    dp, ti, w, qp, qt, qv = _sparse_case(n_docs, vocab, n_q, seed=77, mean_len=40)
+    rng = np.random.default_rng(5)
+    qv = (qv * rng.uniform(0.25, 2.0, qv.size)).astype(np.float32)
+    if signed:
+        qv = (qv * np.where(rng.random(qv.size) < 0.6, -1.0, 1.0)).astype(np.float32)
+    tp, pd, pw = synth.doc_major_to_term_major(dp, ti, w, vocab)
+    idx = eng.SparseIndex(dp, ti, w, vocab, DEV, block_docs=2048)
+    ref_s, ref_i, ref_c = o.sparse_topk(tp, pd, pw, n_docs, qp, qt, qv, k)
+    s, i, c = idx.search(qp, qt, qv, k)
+    assert np.array_equal(c.cpu().numpy(), ref_c)
+    assert np.array_equal(i.cpu().numpy(), ref_i)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), ref_s.view(np.uint32))
+    # the same walk with a filter: exact top-k of the allowed documents
+    allowed = rng.random(n_docs) < 0.3
+    rs, ri, rc = o.sparse_topk(tp, pd, pw, n_docs, qp[:41], qt, qv, n_docs)
+    s, i, c = idx.search(qp, qt, qv, k, doc_mask=eng.pack_row_mask(torch.from_numpy(allowed).to(DEV)))
+    s, i, c = s.cpu().numpy(), i.cpu().numpy(), c.cpu().numpy()
+    for q in range(40):
+        keep = [j for j in range(rc[q]) if allowed[ri[q, j]]][:k]
+        assert c[q] == len(keep), q
+        assert list(i[q, : c[q]]) == [int(ri[q, j]) for j in keep], q
+        assert list(s[q, : c[q]]) == [rs[q, j] for j in keep], q
+
+
 def test_sparse_edge_cases(eng, oracle_lib):
     o = oracle_lib
     # doc-major CSR: doc0 {t0:1}, doc1 {t1:2}, doc2 {t0:1, t2:.5}; term 3 unused

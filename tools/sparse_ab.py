@@ -1,0 +1,120 @@
+"""Same-box A/B of the sparse scan (BASELINE config 4's BM25 side: 1M documents, 100K-term Zipf vocabulary, 256 queries of
+8 terms, top-500) under the kernel's switches:
+
+    B200RAG_SPARSE_DENSE=bits   1 = dense collect mode, 2 = bulk append (default 3)
+    B200RAG_SPARSE_SLICES=n      slices per query (default: 2 * SMs / queries)
+    --block-docs a,b,...         documents per postings block
+
+Every variant must return the same ids / scores as the first one (bit exact); times are CUDA-event medians.
+No oracle use: this is a profiling helper, parity lives in tests/.
+
+    python tools/sparse_ab.py [--docs 1000000] [--variants dense:slices,...]
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import ctypes
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "advanced-rag-milvus_b200")]
+from b200rag import _lib, bm25, engine, synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--docs", type=int, default=1_000_000)
+ap.add_argument("--vocab", type=int, default=100_000)
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--k", type=int, default=500)
+ap.add_argument("--reps", type=int, default=15)
+ap.add_argument("--block-docs", default="16384")
+ap.add_argument("--variants", default="0:0,1:0,3:0")
+ap.add_argument("--stats", action="store_true", help="per-phase cycle counters of one launch (b200rag_debug_sparse_stats)")
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+
+
+def corpus(n_docs, vocab, seed, mean_len=128, s=1.07):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    lens = torch.poisson(torch.full((n_docs,), float(mean_len), device=dev), generator=g).to(torch.int64)
+    p = 1.0 / torch.arange(1, vocab + 1, dtype=torch.float64, device=dev) ** s
+    cdf = torch.cumsum(p / p.sum(), 0)
+    keys = []
+    for d0 in range(0, n_docs, 100_000):
+        ln = lens[d0:d0 + 100_000]
+        tot = int(ln.sum())
+        toks = torch.searchsorted(cdf, torch.rand(tot, generator=g, device=dev, dtype=torch.float64), right=True).clamp_(max=vocab - 1)
+        doc_of = torch.repeat_interleave(torch.arange(d0, d0 + ln.numel(), device=dev), ln, output_size=tot)
+        keys.append(doc_of * vocab + toks)
+    key, tf = torch.unique(torch.cat(keys), sorted=True, return_counts=True)
+    doc_ptr = torch.zeros(n_docs + 1, dtype=torch.int64, device=dev)
+    doc_ptr[1:] = torch.cumsum(torch.bincount(key // vocab, minlength=n_docs), 0)
+    return doc_ptr, key % vocab, tf
+
+
+def timed(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts), min(ts), r
+
+
+doc_ptr, term_ids, tf = corpus(args.docs, args.vocab, 0)
+w = bm25.bm25_weights_device(doc_ptr, term_ids, tf, args.vocab)
+qs = [synth.zipf_queries(args.batch, args.vocab, 100 + i, n_terms=8, skip_top=100) for i in range(4)]
+ref = None
+for bd in [int(x) for x in args.block_docs.split(",")]:
+    idx = engine.SparseIndex(doc_ptr, term_ids, w, args.vocab, dev, block_docs=bd)
+    nbytes = statistics.mean(idx.query_bytes(q[0], q[1]) for q in qs)
+    for var in args.variants.split(","):
+        dense, slices = var.split(":")
+        os.environ["B200RAG_SPARSE_DENSE"] = dense
+        os.environ["B200RAG_SPARSE_SLICES"] = slices
+        it = [0]
+
+        def fn():
+            it[0] += 1
+            qp, qt, qv = qs[it[0] % 4]
+            return idx.search(qp, qt, qv, args.k)
+
+        med, best, _ = timed(fn, args.reps)
+        s, i, c = idx.search(*qs[0], args.k)
+        got = (s.cpu(), i.cpu(), c.cpu())
+        same = True
+        if ref is None:
+            ref = got
+        else:
+            same = all(torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a, b.view(torch.int32) if b.dtype == torch.float32 else b)
+                       for a, b in zip(got, ref))
+        print(json.dumps({"block_docs": bd, "dense": int(dense), "slices": int(slices), "ms": round(med, 4), "best_ms": round(best, 4),
+                          "gbs": round(nbytes / med / 1e6, 1), "same_as_first": bool(same)}), flush=True)
+        if args.stats:
+            lib = _lib.load()
+            lib.b200rag_debug_sparse_stats(1, None, 0)
+            idx.search(*qs[0], args.k)
+            buf = np.zeros((1024, 12), dtype=np.uint64)
+            lib.b200rag_debug_sparse_stats(0, buf.ctypes.data_as(ctypes.c_void_p), 1024)
+            used = buf[buf.sum(1) > 0].astype(np.float64)
+            phases = [(0, "init"), (2, "fetch + term 1"), (3, "terms 2.."), (4, "scan accumulators"), (5, "bulk append"),
+                      (1, "compaction"), (8, "candidate rounds"), (6, "finalize")]
+            tot = used[:, [i for i, _ in phases]].sum(1)
+            print(f"    {len(used)} CTAs; cycles per CTA: mean {tot.mean():.0f}  min {tot.min():.0f}  max {tot.max():.0f}; per CTA: "
+                  f"{used[:, 7].mean():.1f} collects with candidates, {used[:, 9].mean():.1f} bulk compactions, "
+                  f"{used[:, 10].mean():.0f} candidates appended in bulk")
+            for i, n_ in phases:
+                v = used[:, i].mean()
+                print(f"    {n_:18s} {v:10.0f} cycles  {100 * v / tot.mean():5.1f}%")
+    del idx
+    torch.cuda.empty_cache()
