@@ -371,7 +371,10 @@ __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishPa
     } else {
         tk.init();
         __syncthreads();
-        for (int i = tid; i < n; i += FN_THREADS) tk.offer(true, mono64(exact[i]), ~rows[i]);
+        for (int i0 = 0; i0 < n; i0 += FN_THREADS) {              // (offer() wants whole warps)
+            const int i = i0 + tid;
+            tk.offer(i < n, i < n ? mono64(exact[i]) : 0, i < n ? ~rows[i] : 0);
+        }
         __syncthreads();
         tk.finalize();
         const uint64_t* sh = tk.out_hi();

@@ -6,7 +6,8 @@
 //
 // Usage (all threads of the block, in lock step):
 //   tk.attach(...); tk.init(); __syncthreads();
-//   loop { tk.offer(valid, hi, lo); [more offers]; tk.settle(); }   // settle() = barrier + compaction when nearly full
+//   loop { tk.offer(valid, hi, lo); [more offers]; tk.settle(); }   // settle() = barrier + compaction when nearly full;
+//                                                                   // offer() is called by whole warps (valid = false to skip)
 //   __syncthreads(); tk.finalize();   // <= k entries, sorted best first, in tk.out_hi()/out_lo(), count in tk.count()
 //
 // Capacity contract: cap >= k + reserve and cap >= next_pow2(k), where `reserve` bounds the number of offers the
@@ -85,22 +86,56 @@ struct BlockTopK {
             st->thr_lo = 0;
         }
     }
+    // Whole warps call this together (converged; `valid` false for lanes with nothing to offer): the accepted lanes of a
+    // warp take their slots with one atomic.
     __device__ __forceinline__ void offer(bool valid, uint64_t h, LoT l) {
-        if (valid) {
-            bool pass = !st->has_thr || key_gt<LoT>(h, l, st->thr_hi, (LoT)st->thr_lo);
+        const bool pass = valid && (!st->has_thr || key_gt<LoT>(h, l, st->thr_hi, (LoT)st->thr_lo));
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (bal) {
+            const int lane = threadIdx.x & 31, leader = __ffs((int)bal) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&st->count, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, leader);
             if (pass) {
-                // lanes that arrive here together take their slots with one atomic
-                const unsigned act = __activemask();
-                const int lane = threadIdx.x & 31, leader = __ffs((int)act) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(&st->count, __popc(act));
-                base = __shfl_sync(act, base, leader);
-                const int i = base + __popc(act & ((1u << lane) - 1u));
+                const int i = base + __popc(bal & ((1u << lane) - 1u));
                 const int a = st->active;
                 hi[a][i] = h;
                 lo[a][i] = l;
             }
         }
+    }
+    // Register copy of what offer() reads, for loops that make many offers between two settles (nothing changes meanwhile).
+    struct View {
+        int has_thr, active;
+        uint64_t thr_hi;
+        LoT thr_lo;
+    };
+    __device__ __forceinline__ View view() const {
+        View v;
+        v.has_thr = st->has_thr;
+        v.active = st->active;
+        v.thr_hi = st->thr_hi;
+        v.thr_lo = (LoT)st->thr_lo;
+        return v;
+    }
+    __device__ __forceinline__ bool passes(const View& v, uint64_t h, LoT l) const {
+        return !v.has_thr || key_gt<LoT>(h, l, v.thr_hi, v.thr_lo);
+    }
+    // offer() against a view: whole warps call it together, `have` = this lane holds a key that passes(v, ...).
+    // Returns false when no lane of the warp had one (the warp-uniform exit of an append loop).
+    __device__ __forceinline__ bool append(const View& v, bool have, uint64_t h, LoT l) {
+        const unsigned bal = __ballot_sync(0xffffffffu, have);
+        if (!bal) return false;
+        const int lane = threadIdx.x & 31, leader = __ffs((int)bal) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&st->count, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (have) {
+            const int i = base + __popc(bal & ((1u << lane) - 1u));
+            hi[v.active][i] = h;
+            lo[v.active][i] = l;
+        }
+        return true;
     }
     // Would offer() accept this key?  (Lets callers skip losers before spending one of their `reserve` offers.)
     __device__ __forceinline__ bool passes(uint64_t h, LoT l) const {

@@ -190,20 +190,29 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
             float4* acc4 = reinterpret_cast<float4*>(acc);
             const int nv = block_docs >> 2;
             int sh = 0;
-            for (int v = tid; v < nv; v += SP_THREADS, sh += 4) {
-                const float4 x = acc4[v];
-                if ((__float_as_uint(x.x) | __float_as_uint(x.y) | __float_as_uint(x.z) | __float_as_uint(x.w)) == 0u) continue;
-                const unsigned b = (!(x.x < thr_f) ? 1u : 0u) | (!(x.y < thr_f) ? 2u : 0u) | (!(x.z < thr_f) ? 4u : 0u) |
-                                   (!(x.w < thr_f) ? 8u : 0u);
-                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (b) {
-                    m |= (unsigned long long)b << sh;
-                    if (b & 1u) z.x = x.x;
-                    if (b & 2u) z.y = x.y;
-                    if (b & 4u) z.z = x.z;
-                    if (b & 8u) z.w = x.w;
+            for (int v0 = tid; v0 < nv; v0 += 4 * SP_THREADS) {              // four LDS.128 in flight
+                float4 x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int v = v0 + u * SP_THREADS;
+                    x[u] = v < nv ? acc4[v] : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                acc4[v] = z;
+#pragma unroll
+                for (int u = 0; u < 4; ++u, sh += 4) {
+                    const float4 y = x[u];
+                    if ((__float_as_uint(y.x) | __float_as_uint(y.y) | __float_as_uint(y.z) | __float_as_uint(y.w)) == 0u) continue;
+                    const unsigned b = (!(y.x < thr_f) ? 1u : 0u) | (!(y.y < thr_f) ? 2u : 0u) | (!(y.z < thr_f) ? 4u : 0u) |
+                                       (!(y.w < thr_f) ? 8u : 0u);
+                    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b) {
+                        m |= (unsigned long long)b << sh;
+                        if (b & 1u) z.x = y.x;
+                        if (b & 2u) z.y = y.y;
+                        if (b & 4u) z.z = y.z;
+                        if (b & 8u) z.w = y.w;
+                    }
+                    acc4[v0 + u * SP_THREADS] = z;
+                }
             }
         } else {
             // bits 0..31 <-> word tid of the bitmap, bits 32..63 <-> word tid + SP_THREADS
@@ -226,7 +235,7 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
             }
         }
         // next candidate of this thread at or above the threshold (and allowed): true + its key, or false with m == 0
-        auto next_candidate = [&](uint64_t& h, uint32_t& l) -> bool {
+        auto next_candidate = [&](const BlockTopK<SP_THREADS, uint32_t>::View& tv, uint64_t& h, uint32_t& l) -> bool {
             while (m) {
                 const int bpos = __ffsll((long long)m) - 1;
                 m &= m - 1;
@@ -241,7 +250,7 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
                 }
                 h = (uint64_t)mono32(sc);
                 l = ~(uint32_t)(doc0 + d);
-                if (tk.passes(h, l)) return true;
+                if (tk.passes(tv, h, l)) return true;
             }
             return false;
         };
@@ -270,7 +279,8 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
             // read behind the term barriers.
             uint64_t h = 0;
             uint32_t l = 0;
-            while (next_candidate(h, l)) tk.offer(true, h, l);
+            const auto tv = tk.view();
+            while (tk.append(tv, next_candidate(tv, h, l), h, l)) {}      // (warp-uniform exit)
             if (stats && tid == 0) { s_stat[7] += 1; s_stat[10] += total; }
             acc_busy = true;
             SP_MARK(5);                                   // bulk append
@@ -279,8 +289,8 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
                 if (stats && tid == 0) s_stat[7] += 1;                  // candidate rounds
                 uint64_t h = 0;
                 uint32_t l = 0;
-                const bool have = next_candidate(h, l);
-                tk.offer(have, h, l);
+                const auto tv = tk.view();
+                tk.append(tv, next_candidate(tv, h, l), h, l);
                 tk.settle();
                 thr_f = tk.threshold_hi32_as_float();
             }
