@@ -137,6 +137,18 @@ struct BlockTopK {
         }
         return true;
     }
+    // Bulk form for a warp that knows how many keys it is going to add: lane 0 takes `n_warp` consecutive slots (warp-uniform
+    // argument, whole warp calls), every lane then put()s its keys at first + (its offset inside the warp's range).
+    // Keys at or below the threshold may be put as well: the next compaction drops them.
+    __device__ __forceinline__ int reserve_warp(int n_warp) {
+        int base = 0;
+        if ((threadIdx.x & 31) == 0) base = atomicAdd(&st->count, n_warp);
+        return __shfl_sync(0xffffffffu, base, 0);
+    }
+    __device__ __forceinline__ void put(const View& v, int i, uint64_t h, LoT l) {
+        hi[v.active][i] = h;
+        lo[v.active][i] = l;
+    }
     // Would offer() accept this key?  (Lets callers skip losers before spending one of their `reserve` offers.)
     __device__ __forceinline__ bool passes(uint64_t h, LoT l) const {
         return !st->has_thr || key_gt<LoT>(h, l, st->thr_hi, (LoT)st->thr_lo);

@@ -60,9 +60,10 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
     extern __shared__ __align__(16) char smem[];
     __shared__ unsigned long long s_stat[SP_NSTAT];
     __shared__ long long s_last;
-    // posting ranges of the current term group: slots 0/1 = first group of block (blk & 1), filled one block ahead by
-    // cp.async; slot 2 = later groups (queries with more than SP_TG terms), filled synchronously
-    __shared__ __align__(16) long long s_beg[3][SP_TG], s_end[3][SP_TG];
+    // posting ranges [s_beg, s_end) of the query's terms inside a block: slots 0..2 = the first SP_TG terms of block
+    // (blk % 3), filled two blocks ahead by cp.async; slot 3 = four later terms at a time (queries with more than SP_TG
+    // terms), filled synchronously
+    __shared__ __align__(16) long long s_beg[4][SP_TG], s_end[4][SP_TG];
     __shared__ float s_qv[2][SP_TG];
     __shared__ int s_total[2];                                                       // candidates of block (blk & 1)
     const int tid = threadIdx.x;
@@ -88,9 +89,13 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
     const int64_t qs = q_ptr[q];
     const int nq = (int)(q_ptr[q + 1] - qs);
     const int b0 = (int)((int64_t)slice * n_blocks / n_slices), b1 = (int)((int64_t)(slice + 1) * n_blocks / n_slices);
-    // The chain block -> term pointers -> postings is two dependent trips to HBM.  Lanes 0..SP_TG-1 copy the NEXT block's
-    // ranges of the first term group straight into shared memory (cp.async: no registers, nothing waits on it) while the
-    // current block is accumulated.
+    // The chain block -> term pointers -> postings is two dependent trips to HBM, and nothing else in a block is long
+    // enough to hide one.  Both are taken ahead of time:
+    //   * lanes 0..SP_TG-1 copy the ranges of block blk+2 straight into shared memory (cp.async: no registers, nothing
+    //     waits on it) at the top of block blk;
+    //   * the postings travel in two register sets of SP_TG/2 terms: set A (terms 0..3) of block blk+1 is requested in
+    //     the middle of block blk and is in flight during the rest of the block and its whole collect; set B (terms 4..7)
+    //     is requested at the top of its block and has the four term steps of set A to arrive.
     int my_t = -1;
     if (tid < SP_TG) {
         float qv = 0.f;
@@ -100,86 +105,115 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
         }
         s_qv[0][tid] = qv;
     }
-    auto stage_ranges = [&](int blk) {          // lanes 0..SP_TG-1
+    auto stage_ranges = [&](int blk, int slot) {          // lanes 0..SP_TG-1
         const int64_t* src = blk_term_ptr + (size_t)blk * (n_terms + 1) + (my_t >= 0 ? my_t : 0);
         const unsigned sz = my_t >= 0 ? 8u : 0u;
-        sp_cp_async8(&s_beg[blk & 1][tid], src, sz);
-        sp_cp_async8(&s_end[blk & 1][tid], src + 1, sz);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        sp_cp_async8(&s_beg[slot][tid], src, sz);
+        sp_cp_async8(&s_end[slot][tid], src + 1, sz);
     };
-    if (tid < SP_TG && b0 < b1 && nq > 0) {
-        stage_ranges(b0);
+    constexpr int SP_H = SP_TG / 2;
+    auto load_half = [&](int (&d)[SP_H], float (&w)[SP_H], int slot, int first) {
+#pragma unroll
+        for (int j = 0; j < SP_H; ++j) {
+            const long long i = s_beg[slot][first + j] + tid;
+            d[j] = -1;
+            w[j] = 0.f;
+            if (i < s_end[slot][first + j]) { d[j] = post_doc[i]; w[j] = post_w[i]; }
+        }
+    };
+    const bool walk = nq > 0 && b0 < b1;
+    if (tid < SP_TG && walk) {
+        stage_ranges(b0, 0);
+        if (b0 + 1 < b1) stage_ranges(b0 + 1, 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    int dA[SP_H];
+    float wA[SP_H];
+#pragma unroll
+    for (int j = 0; j < SP_H; ++j) { dA[j] = -1; wA[j] = 0.f; }
+    if (walk) load_half(dA, wA, 0, 0);
     SP_MARK(0);                                           // init
     bool acc_busy = false;      // CTA-uniform: the previous block's survivors may still be read out of (and zeroed in) `acc`
+    int sl_cur = 0, sl_nxt = 1, sl_nx2 = 2;
     for (int blk = b0; blk < b1; ++blk) {
         const int64_t doc0 = (int64_t)blk * block_docs;
         const int64_t* tp = blk_term_ptr + (size_t)blk * (n_terms + 1);
         const int cur = blk & 1;
         float thr_f = tk.threshold_hi32_as_float();      // stable here: the previous collect ended on a barrier
         const bool dense = allow_dense && thr_f > 0.0f;  // CTA-uniform
-        const bool have_next = blk + 1 < b1 && nq > 0;
-        // slot cur^1 was last read while block blk-1 was accumulated; every thread has passed a barrier since
-        if (tid < SP_TG && have_next) stage_ranges(blk + 1);
-        // ---- accumulate, SP_TG terms at a time ---------------------------------------------------------------
-        for (int g0 = 0; g0 < nq; g0 += SP_TG) {
-            const int slot = g0 == 0 ? cur : 2, qslot = g0 == 0 ? 0 : 1;
-            if (g0 > 0) {
-                if (tid < SP_TG) {
+        // one term: first SP_THREADS postings from registers, the rest of a long list straight from memory (two in flight)
+        auto apply = [&](int d, float w, float qv, long long beg, long long e) {
+            if (d >= 0) {
+                acc[d] = fmaf(qv, w, acc[d]);
+                if (!dense) atomicOr(&touched[d >> 5], 1u << (d & 31));
+            }
+            for (long long i = beg + tid + SP_THREADS; i < e; i += 2 * SP_THREADS) {
+                const long long i1 = i + SP_THREADS;
+                const int d0 = post_doc[i];
+                const float w0 = post_w[i];
+                int d1 = -1;
+                float w1 = 0.f;
+                if (i1 < e) { d1 = post_doc[i1]; w1 = post_w[i1]; }
+                acc[d0] = fmaf(qv, w0, acc[d0]);
+                if (!dense) atomicOr(&touched[d0 >> 5], 1u << (d0 & 31));
+                if (d1 >= 0) {
+                    acc[d1] = fmaf(qv, w1, acc[d1]);
+                    if (!dense) atomicOr(&touched[d1 >> 5], 1u << (d1 & 31));
+                }
+            }
+        };
+        // ---- accumulate, in ascending term order with a barrier after every term ---------------------------------------
+        if (nq > 0) {
+            if (tid < SP_TG) {
+                // slot sl_nx2 held block blk-1: last read before that block's final term barrier
+                if (blk + 2 < b1) stage_ranges(blk + 2, sl_nx2);
+                asm volatile("cp.async.commit_group;" ::: "memory");          // (one group per block, possibly empty)
+            }
+            int dB[SP_H];
+            float wB[SP_H];
+            load_half(dB, wB, sl_cur, SP_H);
+            if (acc_busy) {                               // (waits while the postings are in flight)
+                __syncthreads();
+                acc_busy = false;
+            }
+#pragma unroll
+            for (int j = 0; j < SP_H; ++j) {
+                apply(dA[j], wA[j], s_qv[0][j], s_beg[sl_cur][j], s_end[sl_cur][j]);
+                // the ranges of block blk+1 were requested a whole block ago: everything but the newest group has landed
+                if (j == SP_H - 1 && tid < SP_TG) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                __syncthreads();
+                if (j == 0) SP_MARK(2);                   // first term applied
+            }
+            if (blk + 1 < b1) load_half(dA, wA, sl_nxt, 0);
+            if (nq > SP_H) {
+#pragma unroll
+                for (int j = 0; j < SP_H; ++j) {
+                    apply(dB[j], wB[j], s_qv[0][SP_H + j], s_beg[sl_cur][SP_H + j], s_end[sl_cur][SP_H + j]);
+                    __syncthreads();
+                }
+            }
+            for (int g0 = SP_TG; g0 < nq; g0 += SP_H) {   // queries with more than SP_TG terms: four more at a time, unpipelined
+                if (tid < SP_H) {
                     long long s = 0, e = 0;
                     float qv = 0.f;
                     if (g0 + tid < nq) {
                         const int t = q_terms[qs + g0 + tid];
                         if (t >= 0 && t < n_terms) { s = tp[t]; e = tp[t + 1]; qv = q_vals[qs + g0 + tid]; }
                     }
-                    s_beg[2][tid] = s; s_end[2][tid] = e; s_qv[1][tid] = qv;
+                    s_beg[3][tid] = s; s_end[3][tid] = e; s_qv[1][tid] = qv;
                 }
                 __syncthreads();
-            }
-            int dreg[SP_TG];
-            float wreg[SP_TG];
+                load_half(dB, wB, 3, 0);
 #pragma unroll
-            for (int j = 0; j < SP_TG; ++j) {
-                const long long i = s_beg[slot][j] + tid;
-                dreg[j] = -1;
-                wreg[j] = 0.f;
-                if (i < s_end[slot][j]) { dreg[j] = post_doc[i]; wreg[j] = post_w[i]; }
-            }
-            if (acc_busy) {                               // (waits while the postings are in flight)
-                __syncthreads();
-                acc_busy = false;
-            }
-#pragma unroll
-            for (int j = 0; j < SP_TG; ++j) {
-                const float qv = s_qv[qslot][j];
-                if (dreg[j] >= 0) {
-                    const int d = dreg[j];
-                    acc[d] = fmaf(qv, wreg[j], acc[d]);
-                    if (!dense) atomicOr(&touched[d >> 5], 1u << (d & 31));
+                for (int j = 0; j < SP_H; ++j) {
+                    apply(dB[j], wB[j], s_qv[1][j], s_beg[3][j], s_end[3][j]);
+                    __syncthreads();
                 }
-                const long long e = s_end[slot][j];
-                for (long long i = s_beg[slot][j] + tid + SP_THREADS; i < e; i += 2 * SP_THREADS) {     // long posting lists, two in flight
-                    const long long i1 = i + SP_THREADS;
-                    const int d0 = post_doc[i];
-                    const float w0 = post_w[i];
-                    int d1 = -1;
-                    float w1 = 0.f;
-                    if (i1 < e) { d1 = post_doc[i1]; w1 = post_w[i1]; }
-                    acc[d0] = fmaf(qv, w0, acc[d0]);
-                    if (!dense) atomicOr(&touched[d0 >> 5], 1u << (d0 & 31));
-                    if (d1 >= 0) {
-                        acc[d1] = fmaf(qv, w1, acc[d1]);
-                        if (!dense) atomicOr(&touched[d1 >> 5], 1u << (d1 & 31));
-                    }
-                }
-                // the next block's ranges were requested many barriers ago: make them visible with the group's last barrier
-                if (j == SP_TG - 1 && tid < SP_TG) asm volatile("cp.async.wait_group 0;" ::: "memory");
-                __syncthreads();
-                if (j == 0) SP_MARK(2);                   // postings fetched, first term applied
             }
             SP_MARK(3);                                   // remaining terms applied
+            const int t_ = sl_cur; sl_cur = sl_nxt; sl_nxt = sl_nx2; sl_nx2 = t_;
         }
         // ---- collect -------------------------------------------------------------------------------------------------
         // `m` = this thread's candidate positions.  Losers are dropped with ONE float compare against the running k-th best
@@ -277,10 +311,46 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
             // everything fits: every thread appends all its survivors at once.  The barrier that must separate this from the
             // next block's accumulation is taken there, under the postings' latency; the count and the threshold are next
             // read behind the term barriers.
-            uint64_t h = 0;
-            uint32_t l = 0;
             const auto tv = tk.view();
-            while (tk.append(tv, next_candidate(tv, h, l), h, l)) {}      // (warp-uniform exit)
+            if (!dense || doc_mask) {
+                // the dense scan kept exactly the scores >= thr_f; the bitmap walk and the document filter still have to drop theirs
+                unsigned long long keep = 0;
+                while (m) {
+                    const int bpos = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const int d = dense ? ((((bpos >> 2) * SP_THREADS + tid) << 2) | (bpos & 3))
+                                        : (bpos < 32 ? tid * 32 + bpos : (tid + SP_THREADS) * 32 + (bpos - 32));
+                    bool ok = !(acc[d] < thr_f);
+                    if (ok && dense && doc_mask) {      // (the bitmap path filtered its words above)
+                        const int64_t g = doc0 + d;
+                        ok = (__ldg(doc_mask + (g >> 5)) >> (g & 31)) & 1u;
+                    }
+                    if (ok) keep |= 1ull << bpos;
+                    else acc[d] = 0.0f;
+                }
+                m = keep;
+            }
+            // one slot reservation per warp, then every lane moves its survivors out of `acc` on its own
+            const int c = __popcll(m);
+            int incl = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, off);
+                if ((tid & 31) >= off) incl += v;
+            }
+            const int n_warp = __shfl_sync(0xffffffffu, incl, 31);
+            if (n_warp) {
+                int slot = tk.reserve_warp(n_warp) + incl - c;
+                while (m) {
+                    const int bpos = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const int d = dense ? ((((bpos >> 2) * SP_THREADS + tid) << 2) | (bpos & 3))
+                                        : (bpos < 32 ? tid * 32 + bpos : (tid + SP_THREADS) * 32 + (bpos - 32));
+                    const float sc = acc[d];
+                    acc[d] = 0.0f;
+                    tk.put(tv, slot++, (uint64_t)mono32(sc), ~(uint32_t)(doc0 + d));
+                }
+            }
             if (stats && tid == 0) { s_stat[7] += 1; s_stat[10] += total; }
             acc_busy = true;
             SP_MARK(5);                                   // bulk append
