@@ -38,6 +38,29 @@ def zipf_corpus(n_docs: int, vocab: int, seed: int, mean_len: int = 128, s: floa
     return doc_ptr, (key % vocab).astype(np.int64), tf.astype(np.int64)
 
 
+def zipf_corpus_device(n_docs: int, vocab: int, seed: int, device, mean_len: int = 128, s: float = 1.07):
+    """zipf_corpus on a CUDA device (same law, different random stream), for corpora too large to build on the host in a
+    test: -> doc-major CSR as device tensors (doc_ptr i64, term_ids i64 ascending per doc, tf i64)."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    lens = torch.poisson(torch.full((n_docs,), float(mean_len), device=dev), generator=g).to(torch.int64)
+    p = 1.0 / torch.arange(1, vocab + 1, dtype=torch.float64, device=dev) ** s
+    cdf = torch.cumsum(p / p.sum(), 0)
+    keys = []
+    step = 100_000
+    for d0 in range(0, n_docs, step):
+        ln = lens[d0:d0 + step]
+        tot = int(ln.sum())
+        toks = torch.searchsorted(cdf, torch.rand(tot, generator=g, device=dev, dtype=torch.float64), right=True).clamp_(max=vocab - 1)
+        doc_of = torch.repeat_interleave(torch.arange(d0, d0 + ln.numel(), device=dev), ln, output_size=tot)
+        keys.append(doc_of * vocab + toks)
+    key, tf = torch.unique(torch.cat(keys), sorted=True, return_counts=True)
+    doc_ptr = torch.zeros(n_docs + 1, dtype=torch.int64, device=dev)
+    doc_ptr[1:] = torch.cumsum(torch.bincount(key // vocab, minlength=n_docs), 0)
+    return doc_ptr, key % vocab, tf
+
+
 def zipf_queries(n_q: int, vocab: int, seed: int, n_terms: int = 8, skip_top: int = 100, s: float = 1.07
                  ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """-> CSR queries (q_ptr i64, q_terms i32 ascending per query, q_vals f32 = 1)."""

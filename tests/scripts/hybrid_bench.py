@@ -50,34 +50,13 @@ def timed(fn, reps):
     return statistics.median(ts), r
 
 
-def zipf_corpus_device(n_docs, vocab, seed, mean_len=128, s=1.07):
-    """synth.zipf_corpus on the GPU (same law, different random stream): doc-major CSR as device tensors."""
-    g = torch.Generator(device=dev).manual_seed(seed)
-    lens = torch.poisson(torch.full((n_docs,), float(mean_len), device=dev), generator=g).to(torch.int64)
-    p = 1.0 / torch.arange(1, vocab + 1, dtype=torch.float64, device=dev) ** s
-    cdf = torch.cumsum(p / p.sum(), 0)
-    keys = []
-    step = 100_000
-    for d0 in range(0, n_docs, step):
-        ln = lens[d0:d0 + step]
-        tot = int(ln.sum())
-        toks = torch.searchsorted(cdf, torch.rand(tot, generator=g, device=dev, dtype=torch.float64), right=True).clamp_(max=vocab - 1)
-        doc_of = torch.repeat_interleave(torch.arange(d0, d0 + ln.numel(), device=dev), ln, output_size=tot)
-        keys.append(doc_of * vocab + toks)
-    key, tf = torch.unique(torch.cat(keys), sorted=True, return_counts=True)
-    d = key // vocab
-    doc_ptr = torch.zeros(n_docs + 1, dtype=torch.int64, device=dev)
-    doc_ptr[1:] = torch.cumsum(torch.bincount(d, minlength=n_docs), 0)
-    return doc_ptr, key % vocab, tf
-
-
 if "c4" not in args.skip:
     t0 = time.time()
     g = torch.Generator(device=dev).manual_seed(0)
     dense = engine.DenseIndex(args.dim, "bf16", "COSINE", dev, capacity=args.docs)
     for s in range(0, args.docs, 250_000):
         dense.add(torch.randn(min(250_000, args.docs - s), args.dim, generator=g, device=dev))
-    doc_ptr, term_ids, tf = zipf_corpus_device(args.docs, args.vocab, 0)
+    doc_ptr, term_ids, tf = synth.zipf_corpus_device(args.docs, args.vocab, 0, dev)
     w = bm25.bm25_weights_device(doc_ptr, term_ids, tf, args.vocab)
     sparse = engine.SparseIndex(doc_ptr, term_ids, w, args.vocab, dev, block_docs=args.block_docs)
     nnz = int(term_ids.numel())

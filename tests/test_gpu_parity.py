@@ -155,6 +155,46 @@ def test_sparse_long_walk_both_collect_modes(eng, oracle_lib, signed):
         assert list(s[q, : c[q]]) == [rs[q, j] for j in keep], q
 
 
+def test_sparse_full_size_collect_paths_agree(eng, monkeypatch):
+    """BASELINE config 4's sparse side at full size (1M documents, 100K-term Zipf vocabulary, 256 queries of 8 terms, top-500;
+    too large for the CPU oracle inside a test): the kernel's collect paths -- touched-bitmap walk with one candidate per
+    thread and round (B200RAG_SPARSE_DENSE=0, the form the oracle-checked small tests pin), dense threshold scan, bulk
+    append, and both -- must return bit-identical lists; the lists are sorted by (score desc, id asc); and the scores
+    agree with an fp64 recomputation from the CSR."""
+    from b200rag import bm25, synth
+    n_docs, vocab, n_q, k = 1_000_000, 100_000, 256, 500
+    doc_ptr, term_ids, tf = synth.zipf_corpus_device(n_docs, vocab, 0, DEV)
+    w = bm25.bm25_weights_device(doc_ptr, term_ids, tf, vocab)
+    idx = eng.SparseIndex(doc_ptr, term_ids, w, vocab, DEV)
+    qp, qt, qv = synth.zipf_queries(n_q, vocab, 100, n_terms=8, skip_top=100)
+    qv = (qv * np.random.default_rng(1).uniform(0.5, 2.0, qv.size)).astype(np.float32)
+    got = {}
+    for flags in ("0", "1", "2", "3"):
+        monkeypatch.setenv("B200RAG_SPARSE_DENSE", flags)
+        s, i, c = idx.search(qp, qt, qv, k)
+        torch.cuda.synchronize()
+        got[flags] = (s.cpu().numpy(), i.cpu().numpy(), c.cpu().numpy())
+    monkeypatch.delenv("B200RAG_SPARSE_DENSE")
+    s0, i0, c0 = got["0"]
+    for flags in ("1", "2", "3"):
+        s, i, c = got[flags]
+        assert np.array_equal(c, c0) and np.array_equal(i, i0), flags
+        assert np.array_equal(s.view(np.uint32), s0.view(np.uint32)), flags
+    assert (c0 == k).all()
+    assert (s0[:, :-1] >= s0[:, 1:]).all()
+    ties = s0[:, :-1] == s0[:, 1:]
+    assert (i0[:, :-1][ties] < i0[:, 1:][ties]).all()
+    # fp64 scores of the first queries from the doc-major CSR
+    d_of = torch.repeat_interleave(torch.arange(n_docs, device=DEV), doc_ptr[1:] - doc_ptr[:-1])
+    for q in range(4):
+        wq = torch.zeros(vocab, dtype=torch.float64, device=DEV)
+        wq[torch.from_numpy(qt[qp[q]:qp[q + 1]].astype(np.int64)).to(DEV)] = torch.from_numpy(qv[qp[q]:qp[q + 1]].astype(np.float64)).to(DEV)
+        full = torch.zeros(n_docs, dtype=torch.float64, device=DEV).index_add_(0, d_of, wq[term_ids] * w.double())
+        ref_s, _ = torch.topk(full, k)
+        assert np.allclose(full[torch.from_numpy(i0[q]).to(DEV)].cpu().numpy(), s0[q], rtol=1e-5)
+        assert np.allclose(ref_s.cpu().numpy(), s0[q], rtol=1e-5)
+
+
 def test_sparse_edge_cases(eng, oracle_lib):
     o = oracle_lib
     # doc-major CSR: doc0 {t0:1}, doc1 {t1:2}, doc2 {t0:1, t2:.5}; term 3 unused

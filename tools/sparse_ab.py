@@ -38,24 +38,6 @@ args = ap.parse_args()
 dev = torch.device("cuda:0")
 
 
-def corpus(n_docs, vocab, seed, mean_len=128, s=1.07):
-    g = torch.Generator(device=dev).manual_seed(seed)
-    lens = torch.poisson(torch.full((n_docs,), float(mean_len), device=dev), generator=g).to(torch.int64)
-    p = 1.0 / torch.arange(1, vocab + 1, dtype=torch.float64, device=dev) ** s
-    cdf = torch.cumsum(p / p.sum(), 0)
-    keys = []
-    for d0 in range(0, n_docs, 100_000):
-        ln = lens[d0:d0 + 100_000]
-        tot = int(ln.sum())
-        toks = torch.searchsorted(cdf, torch.rand(tot, generator=g, device=dev, dtype=torch.float64), right=True).clamp_(max=vocab - 1)
-        doc_of = torch.repeat_interleave(torch.arange(d0, d0 + ln.numel(), device=dev), ln, output_size=tot)
-        keys.append(doc_of * vocab + toks)
-    key, tf = torch.unique(torch.cat(keys), sorted=True, return_counts=True)
-    doc_ptr = torch.zeros(n_docs + 1, dtype=torch.int64, device=dev)
-    doc_ptr[1:] = torch.cumsum(torch.bincount(key // vocab, minlength=n_docs), 0)
-    return doc_ptr, key % vocab, tf
-
-
 def timed(fn, reps):
     for _ in range(3):
         fn()
@@ -71,7 +53,7 @@ def timed(fn, reps):
     return statistics.median(ts), min(ts), r
 
 
-doc_ptr, term_ids, tf = corpus(args.docs, args.vocab, 0)
+doc_ptr, term_ids, tf = synth.zipf_corpus_device(args.docs, args.vocab, 0, dev)
 w = bm25.bm25_weights_device(doc_ptr, term_ids, tf, args.vocab)
 qs = [synth.zipf_queries(args.batch, args.vocab, 100 + i, n_terms=8, skip_top=100) for i in range(4)]
 ref = None
