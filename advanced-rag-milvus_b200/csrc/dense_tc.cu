@@ -547,18 +547,19 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     // strided SAMPLE pass that seeds the per-query thresholds: every s_stride-th tile is scored, the epilogue keeps the
     // TC_SAMPLE_R best 32-row group maxima per (chunk, query) in registers, and the s_rank-th best over all chunks becomes
     // the query's starting threshold.  About s_rank * s_stride rows of the whole corpus beat it; that product is held
-    // near 12 k' (see below).
+    // near 8 k' (see below).
     // Sizing.  The threshold is the r-th best of a 1/stride sample, so the number of corpus rows above it is about
-    // stride * Gamma(r): with r = 16 and r * stride = 12 k' the chance that fewer than k' rows survive (the query is then
-    // flagged and re-run on the slow exact path) is P(Gamma(16) < 4/3) ~ 1e-12 per query; at r = 8, 6 k' it was 6e-5 and
-    // showed up as a handful of fallbacks per thousand batches.  Small corpora cap the stride (>= 4 sampled tiles); below
-    // r * stride = 8 k' the pass is skipped.
+    // stride * Gamma(r): with r = 16 and r * stride = 8 k' the chance that fewer than k' rows survive (the query is then
+    // flagged and re-run on the slow exact path) is P(Gamma(16) < 2) ~ 5e-10 per query; at r = 8, 6 k' it was 6e-5 and
+    // showed up as a handful of fallbacks per thousand batches.  12 k' (1e-12) cost 5 % of the scan at 1.25M-row shards:
+    // every survivor is appended by the epilogue and gathered again by the finish kernel.  Small corpora cap the stride
+    // (>= 4 sampled tiles); below r * stride = 6 k' (2e-8) the pass is skipped.
     pl.s_rank = TC_SAMPLE_R;
-    pl.s_stride = 12 * pl.kprime / TC_SAMPLE_R;
+    pl.s_stride = env_int("B200RAG_SAMPLE_MULT", 8) * pl.kprime / TC_SAMPLE_R;       // (A/B knob: rows above the threshold, in k')
     if (pl.s_stride > pl.n_tiles / 4) pl.s_stride = pl.n_tiles / 4;
     if (pl.s_stride < 1) pl.s_stride = 1;
     pl.s_tiles = pl.n_tiles / pl.s_stride;
-    pl.sample = pl.s_tiles >= 4 && pl.s_rank * pl.s_stride >= 8 * pl.kprime && env_int("B200RAG_NO_SAMPLE", 0) == 0;
+    pl.sample = pl.s_tiles >= 4 && pl.s_rank * pl.s_stride >= 6 * pl.kprime && env_int("B200RAG_NO_SAMPLE", 0) == 0;
     pl.s_chunks = want < pl.s_tiles ? want : (pl.s_tiles > 0 ? pl.s_tiles : 1);
     pl.s_items = qgroups * pl.s_chunks;
     pl.s_kprime = TC_SAMPLE_R;

@@ -339,7 +339,7 @@ struct EpiCounters { long long compact = 0, ncompact = 0, nslow = 0; };
 //   VAR 0: a 32-long chain of compares decides "anything above?"; the survivor path then walks all 32 columns.
 //   VAR 1: maxima of the four 8-column sub-groups (a tree) decide, and the survivor path only walks the sub-groups whose
 //          maximum beats the threshold.  A warp takes the survivor path when ANY of its 32 queries has a survivor in the
-//          group, which is most groups on small shards (12 k' survivors spread over few tiles), so its cost matters.
+//          group, which is most groups on small shards (8 k' survivors spread over few tiles), so its cost matters.
 template <int VAR>
 __device__ __forceinline__ void epi_filter_group(uint32_t (&r)[32], int c, bool partial, int64_t row0, int64_t n_rows, float& thr,
                                                  int& cnt, unsigned long long* buf, EpiCounters& ec, const uint32_t* row_mask) {

@@ -38,7 +38,8 @@ mode = engine.DENSE_AUTO if args.mode == "auto" else engine.DENSE_TENSOR
 flops = 2.0 * args.batch * args.rows * args.dim
 print(f"{args.dtype} rows={args.rows} dim={args.dim} B={args.batch} k={args.k} reps={args.reps} mode={args.mode}")
 for cfg in args.configs.split(","):
-    ver, cs, span = (cfg.split(":") + ["0"])[:3]
+    ver, cs, span, mult = (cfg.split(":") + ["0", "8"])[:4] if cfg.count(":") >= 3 else (cfg.split(":") + ["0"])[:3] + ["8"]
+    os.environ["B200RAG_SAMPLE_MULT"] = mult            # fourth field: expected rows above the sampled threshold, in k'
     os.environ["B200RAG_EPI"] = cs                      # second field: epilogue variant (0 = compare chain, 1 = sub-group maxima)
     os.environ["B200RAG_SCAN_VERSION"] = ver
     os.environ["B200RAG_CLUSTER"] = cs
@@ -70,6 +71,6 @@ for cfg in args.configs.split(","):
     last_scan = evs[-1][0].elapsed_time(evs[-1][1])
     mma_total = used[:, 0].mean() if len(used) else float("nan")
     mma_busy = 1.0 - (used[:, 1].mean() + used[:, 2].mean() + used[:, 3].mean()) / mma_total if len(used) else float("nan")
-    print(f"v{ver} epi={cs} span={span}: scan median {sm:6.2f} ms = {flops / sm / 1e9:5.0f} TFLOP/s (min {min(scan):.2f} max {max(scan):.2f}); "
+    print(f"v{ver} epi={cs} span={span} mult={mult}: scan median {sm:6.2f} ms = {flops / sm / 1e9:5.0f} TFLOP/s (min {min(scan):.2f} max {max(scan):.2f}); "
           f"search {st:6.2f} ms = {args.batch / st * 1e3:7.0f} QPS; clock ~{mma_total / last_scan / 1e6:.3f} GHz, "
           f"MMA issue busy {100 * mma_busy:.0f}%, CTAs with MMA {len(used)}, flagged(last) {flagged}")
