@@ -195,6 +195,33 @@ def test_sparse_full_size_collect_paths_agree(eng, monkeypatch):
         assert np.allclose(ref_s.cpu().numpy(), s0[q], rtol=1e-5)
 
 
+@pytest.mark.parametrize("block", [1024, 16384])
+def test_sparse_many_terms_per_query(eng, oracle_lib, block):
+    """Queries with more than eight terms (several term groups per block) and with very few, enough queries that a CTA walks
+    all blocks of its query."""
+    from b200rag import bm25, synth
+    o = oracle_lib
+    n_docs, vocab, k = 30000, 800, 17
+    dp, ti, tf = synth.zipf_corpus(n_docs, vocab, 21, mean_len=30)
+    w = bm25.bm25_weights(dp, ti, tf, vocab)
+    rng = np.random.default_rng(8)
+    terms, ptr = [], [0]
+    for q in range(310):
+        nt = int(rng.choice([1, 2, 8, 9, 16, 20, 27]))
+        terms.append(np.sort(rng.choice(vocab, size=nt, replace=False)))
+        ptr.append(ptr[-1] + nt)
+    qp = np.asarray(ptr, np.int64)
+    qt = np.concatenate(terms).astype(np.int32)
+    qv = rng.uniform(0.2, 2.0, qt.size).astype(np.float32)
+    tp, pd, pw = synth.doc_major_to_term_major(dp, ti, w, vocab)
+    ref_s, ref_i, ref_c = o.sparse_topk(tp, pd, pw, n_docs, qp, qt, qv, k)
+    idx = eng.SparseIndex(dp, ti, w, vocab, DEV, block_docs=block)
+    s, i, c = idx.search(qp, qt, qv, k)
+    assert np.array_equal(c.cpu().numpy(), ref_c)
+    assert np.array_equal(i.cpu().numpy(), ref_i)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), ref_s.view(np.uint32))
+
+
 def test_sparse_edge_cases(eng, oracle_lib):
     o = oracle_lib
     # doc-major CSR: doc0 {t0:1}, doc1 {t1:2}, doc2 {t0:1, t2:.5}; term 3 unused
