@@ -4,10 +4,10 @@
 //   * the block's per-document accumulators live in shared memory (fp32, block_docs <= 32768 -> 128 KB) and are zeroed
 //     once per CTA; collecting a block's candidates puts them back to zero;
 //   * the postings of up to 8 query terms inside the block are fetched TOGETHER (one coalesced u16 doc + f32 weight per
-//     thread and term, a single exposed memory latency per block instead of one per term) and then applied in ascending
-//     term id with a barrier between terms, so every document sees  acc = fmaf(qv, w, acc)  in the canonical order
-//     (bit-identical to oracle/exact_scan.c:orc_sparse_topk).  Postings of one term hit distinct documents: no atomics
-//     on the accumulators; a touched-bitmap marks the candidates;
+//     thread and term; the ranges come from a shared-memory ring filled two blocks ahead with cp.async, the first four
+//     terms of the NEXT block are requested in the middle of the current one) and then applied in ascending term id with
+//     a barrier between terms, so every document sees  acc = fmaf(qv, w, acc)  in the canonical order (bit-identical to
+//     oracle/exact_scan.c:orc_sparse_topk).  Postings of one term hit distinct documents: no atomics on the accumulators;
 //   * candidates are collected in one of two ways, chosen per block from the running k-th best score `thr`:
 //       thr > 0  (the steady state): every thread reads 32+ accumulators with LDS.128, keeps the few that are >= thr and
 //                writes zeros back -- no bitmap, no atomics in the accumulate step (an untouched document holds exactly 0,
@@ -15,7 +15,8 @@
 //       otherwise (first block(s), or < k positive candidates so far): a touched-bitmap marks the candidates and a
 //                thread walks the set bits of one or two 32-document words;
 //     survivors go to the block-level streaming top-k (select.cuh), which lives for the whole walk, so later blocks
-//     are filtered by the threshold earlier blocks established.
+//     are filtered by the threshold earlier blocks established: appended in bulk (one slot reservation per warp, no
+//     barrier until the next block's postings are in flight) whenever they fit, compacted only when the buffer is full.
 // Algorithmic HBM traffic = 6 bytes per posting of the query's terms.  grid = (queries, slices): with fewer queries
 // than SMs the blocks are split into slices; merge_topk_kernel reduces the slices.
 // (Round 1 first ran one CTA per (query, block) that re-scanned all 32768 documents of the block: 4.1 ms for 256
