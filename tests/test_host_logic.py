@@ -220,3 +220,41 @@ def test_micro_batcher_flushes_at_max_batch_and_propagates_failures():
     res = _run(failing())
     assert all(isinstance(e, RuntimeError) and "index down" in str(e) for e in res)
     bad.close()
+
+
+# ------------------------------------------------------------------------------------------------ BM25 encoder
+def test_bm25_weights_follow_the_stated_formula():
+    """w = idf * tf * (k1 + 1) / (tf + k1 * (1 - b + b * len / avgdl)), idf = ln(1 + (N - df + .5) / (df + .5)), fp64 in this
+    order, one rounding to fp32 (b200rag/bm25.py docstring) -- against a scalar restatement."""
+    import math
+    from b200rag import bm25
+    texts = ["the cat sat on the mat", "The dog sat", "a cat and a dog and a bird", "", "mat mat mat"]
+    enc = bm25.Bm25Encoder()
+    dp, ti, tf = enc.fit_transform(texts)
+    w = bm25.bm25_weights(dp, ti, tf, len(enc.vocab))
+    n = len(texts)
+    lens = [sum(tf[dp[d]:dp[d + 1]]) for d in range(n)]
+    avgdl = sum(lens) / n
+    df = np.bincount(ti, minlength=len(enc.vocab))
+    for d in range(n):
+        for p in range(dp[d], dp[d + 1]):
+            idf = math.log(1.0 + (n - float(df[ti[p]]) + 0.5) / (float(df[ti[p]]) + 0.5))
+            norm = 1.2 * (1.0 - 0.75 + 0.75 * float(lens[d]) / avgdl)
+            ref = np.float32(idf * float(tf[p]) * (1.2 + 1.0) / (float(tf[p]) + norm))
+            assert w[p] == ref, (d, p)
+    assert dp.tolist() == [0, 5, 8, 13, 13, 14] and w.dtype == np.float32
+
+
+def test_bm25_encoder_tokenises_like_the_reference_mmr():
+    """Tokeniser = text.lower().split() (reference retrieval.py:497), ids ascending per document, query value 1.0 per
+    unique known term, unknown terms dropped; token_sets (the MMR side) shares the vocabulary."""
+    from b200rag import bm25
+    enc = bm25.Bm25Encoder()
+    dp, ti, tf = enc.fit_transform(["Alpha beta  ALPHA\tgamma", "beta delta"])
+    assert enc.vocab == {"alpha": 0, "beta": 1, "gamma": 2, "delta": 3}
+    assert ti.tolist() == [0, 1, 2, 1, 3] and tf.tolist() == [2, 1, 1, 1, 1]
+    q = enc.encode_sparse("delta ALPHA alpha unknown")
+    assert q == {"indices": [0, 3], "values": [1.0, 1.0]}
+    tp, tids = enc.token_sets(["gamma gamma beta", "new token"])
+    assert tp.tolist() == [0, 2, 4] and tids.tolist() == [1, 2, 4, 5] and tids.dtype == np.int32
+    assert bm25.tokenize(None) == [] and bm25.tokenize("  ") == []
