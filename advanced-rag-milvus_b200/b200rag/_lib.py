@@ -15,6 +15,14 @@ LIB_PATH = os.path.join(_HERE, "libb200rag.so")
 F16, BF16 = 0, 1
 DENSE_AUTO, DENSE_EXACT, DENSE_TENSOR = 0, 1, 2
 E_INVALID, E_WORKSPACE, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4
+OP_EQ, OP_NE, OP_GE, OP_LE, OP_GT, OP_LT = range(6)
+COL_F64, COL_I64, COL_I64_AS_F64, COL_CODE, COL_NEVER = range(5)
+
+
+class FilterTerm(ctypes.Structure):
+    """b200rag_filter_term (include/b200rag.h)."""
+    _fields_ = [("column", c_void_p), ("lut", c_void_p), ("fvalue", c_double), ("ivalue", c_int64),
+                ("kind", c_int32), ("op", c_int32), ("lut_size", c_int32), ("reserved", c_int32)]
 
 
 class B200RagError(RuntimeError):
@@ -38,8 +46,10 @@ SIGNATURES = {
                                                  c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p,
                                                  c_void_p, c_size_t, c_int32, c_void_p]),
     "b200rag_profile_next_scan": (ctypes.c_int, [c_void_p, c_void_p]),
-    "b200rag_debug_scan_stats": (ctypes.c_int, [c_int32, c_void_p, c_int32]),
-    "b200rag_debug_sparse_stats": (ctypes.c_int, [c_int32, c_void_p, c_int32]),
+    "b200rag_debug_set_stats_buffer": (ctypes.c_int, [c_int32, c_void_p, c_size_t]),
+    "b200rag_set_option": (ctypes.c_int, [ctypes.c_char_p, c_int64]),
+    "b200rag_get_option": (c_int64, [ctypes.c_char_p]),
+    "b200rag_filter_mask": (ctypes.c_int, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200rag_sparse_topk_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
     "b200rag_sparse_topk": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                            c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64,
@@ -77,6 +87,11 @@ def load() -> ctypes.CDLL:
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def set_option(name: str, value: int) -> None:
+    """A/B knob of the library (include/b200rag.h: b200rag_set_option); value < 0 restores the default."""
+    check(load().b200rag_set_option(name.encode(), int(value)))
 
 
 def check(rc: int) -> None:

@@ -28,8 +28,9 @@ def bm25_idf(n_docs: int, df: np.ndarray) -> np.ndarray:
 
 
 def bm25_weights(doc_ptr: np.ndarray, term_ids: np.ndarray, tf: np.ndarray, n_terms: int,
-                 k1: float = K1, b: float = B) -> np.ndarray:
-    """Doc-major CSR of term frequencies -> fp32 BM25 weights (same nnz order)."""
+                 k1: float = K1, b: float = B, stats=None) -> np.ndarray:
+    """Doc-major CSR of term frequencies -> fp32 BM25 weights (same nnz order).  stats = (n_docs, df, total_length) of the
+    WHOLE corpus when this CSR is one row shard of it (distributed.bm25_global_stats): idf and avgdl are global statistics."""
     doc_ptr = np.asarray(doc_ptr, dtype=np.int64)
     term_ids = np.asarray(term_ids, dtype=np.int64)
     tf = np.asarray(tf, dtype=np.float64)
@@ -39,15 +40,18 @@ def bm25_weights(doc_ptr: np.ndarray, term_ids: np.ndarray, tf: np.ndarray, n_te
     counts = np.diff(doc_ptr)
     doc_of = np.repeat(np.arange(n_docs, dtype=np.int64), counts)
     doc_len = np.bincount(doc_of, weights=tf, minlength=n_docs)          # sum of tf, exact in fp64
-    avgdl = doc_len.sum() / n_docs
-    df = np.bincount(term_ids, minlength=n_terms)
-    idf = bm25_idf(n_docs, df)
+    if stats is None:
+        n_all, df, total_len = n_docs, np.bincount(term_ids, minlength=n_terms), doc_len.sum()
+    else:
+        n_all, df, total_len = int(stats[0]), np.asarray(stats[1].cpu() if hasattr(stats[1], "cpu") else stats[1]), float(stats[2])
+    avgdl = total_len / n_all
+    idf = bm25_idf(n_all, df)
     norm = k1 * (1.0 - b + b * doc_len[doc_of] / avgdl)
     w = idf[term_ids] * tf * (k1 + 1.0) / (tf + norm)
     return w.astype(np.float32)
 
 
-def bm25_weights_device(doc_ptr, term_ids, tf, n_terms: int, k1: float = K1, b: float = B):
+def bm25_weights_device(doc_ptr, term_ids, tf, n_terms: int, k1: float = K1, b: float = B, stats=None):
     """bm25_weights for CSR arrays that already live on a CUDA device (torch tensors): same fp64 operation order, so
     the fp32 result is bit-identical to the numpy version (idf, the only transcendental, is evaluated on the host for
     the n_terms vocabulary entries; +, *, / are correctly rounded on both sides)."""
@@ -60,9 +64,12 @@ def bm25_weights_device(doc_ptr, term_ids, tf, n_terms: int, k1: float = K1, b: 
     doc_of = torch.repeat_interleave(torch.arange(n_docs, device=dev), counts, output_size=term_ids.numel())
     tf64 = tf.to(torch.float64)
     doc_len = torch.zeros(n_docs, dtype=torch.float64, device=dev).index_add_(0, doc_of, tf64)   # integers: exact in fp64
-    avgdl = float(doc_len.sum().item()) / n_docs
-    df = torch.bincount(term_ids, minlength=n_terms).cpu().numpy()
-    idf = torch.as_tensor(bm25_idf(n_docs, df)).to(dev)
+    if stats is None:
+        n_all, df, total_len = n_docs, torch.bincount(term_ids, minlength=n_terms).cpu().numpy(), float(doc_len.sum().item())
+    else:                                  # one row shard of a larger corpus: global n_docs / df / total length
+        n_all, df, total_len = int(stats[0]), np.asarray(stats[1].cpu() if hasattr(stats[1], "cpu") else stats[1]), float(stats[2])
+    avgdl = total_len / n_all
+    idf = torch.as_tensor(bm25_idf(n_all, df)).to(dev)
     norm = k1 * (1.0 - b + b * doc_len[doc_of] / avgdl)
     w = idf[term_ids] * tf64 * (k1 + 1.0) / (tf64 + norm)
     return w.to(torch.float32)

@@ -10,8 +10,9 @@ libb200rag.so.  There is no CPU path: tensors must live on a CUDA device and the
 """
 from __future__ import annotations
 
+import threading
 from dataclasses import dataclass
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -43,18 +44,27 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
 
 
 class _Workspace:
-    """Grow-only scratch buffer per device, handed to the C ABI (the library never allocates)."""
+    """Grow-only scratch buffers handed to the C ABI (the library never allocates), one per (device, CUDA stream, host
+    thread): the multi-kernel sequences behind dense_topk / sparse_topk keep state in their workspace between launches, so
+    two host threads -- or two streams -- must never share one (the micro-batcher's worker thread and the event
+    loop thread used to).  Work queued on ONE stream by one thread is ordered by the stream."""
 
     def __init__(self):
         self._buf = {}
+        self._lock = threading.Lock()
 
     def get(self, device: torch.device, nbytes: int) -> torch.Tensor:
-        key = (device.type, device.index)
-        buf = self._buf.get(key)
-        if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-            self._buf[key] = buf
-        return buf
+        key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
+        with self._lock:
+            buf = self._buf.get(key)
+            if buf is None or buf.numel() < nbytes:
+                buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+                self._buf[key] = buf
+            return buf
+
+    def release(self) -> None:
+        with self._lock:
+            self._buf.clear()
 
 
 _WS = _Workspace()
@@ -97,11 +107,29 @@ def pack_row_mask(allowed: torch.Tensor) -> torch.Tensor:
     return torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).contiguous()
 
 
+def filter_mask(terms: Sequence["_lib.FilterTerm"], n_rows: int, device, and_mask: Optional[torch.Tensor] = None
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Parsed predicate terms over device columns -> (bit mask int32 [ceil(n/32)], number of allowed rows as a device i64
+    scalar).  The columns / tables the terms point to must stay alive until the stream has run the kernel."""
+    import ctypes
+    dev = torch.device(device)
+    words = torch.empty(((n_rows + 31) // 32,), dtype=torch.int32, device=dev)
+    count = torch.empty((1,), dtype=torch.int64, device=dev)
+    arr = (_lib.FilterTerm * max(1, len(terms)))(*terms)
+    with torch.cuda.device(dev):
+        check(_lib.load().b200rag_filter_mask(ctypes.cast(arr, ctypes.c_void_p), len(terms), n_rows,
+                                              and_mask.data_ptr() if and_mask is not None else None,
+                                              words.data_ptr(), count.data_ptr(), _stream_ptr(dev)))
+    return words, count
+
+
 def dense_topk(corpus16: torch.Tensor, queries16: torch.Tensor, k: int, id_offset: int = 0, mode: int = DENSE_AUTO,
                n_rows: Optional[int] = None, row_norm_bound: float = 1.001, out_err: Optional[torch.Tensor] = None,
-               row_mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+               row_mask: Optional[torch.Tensor] = None, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Exact top-k of stored rows (of the rows `row_mask` allows, see pack_row_mask).  Returns (scores f64 [B,k],
-    ids i64 [B,k], flags i32 [B])."""
+    ids i64 [B,k], flags i32 [B]).  `out` = preallocated (scores, ids) to write into (e.g. the two planes of an all-gather
+    send buffer)."""
     _require_cuda(corpus16, "corpus")
     _require_cuda(queries16, "queries")
     code = dtype_code(corpus16.dtype)
@@ -113,8 +141,14 @@ def dense_topk(corpus16: torch.Tensor, queries16: torch.Tensor, k: int, id_offse
     if queries16.shape[1] != dim:
         raise ValueError(f"query dim {queries16.shape[1]} != corpus dim {dim}")
     dev = corpus16.device
-    scores = torch.empty((b, k), dtype=torch.float64, device=dev)
-    ids = torch.empty((b, k), dtype=torch.int64, device=dev)
+    if out is not None:
+        scores, ids = out
+        if (scores.dtype, ids.dtype) != (torch.float64, torch.int64) or tuple(scores.shape) != (b, k) or tuple(ids.shape) != (b, k) \
+                or not (scores.is_contiguous() and ids.is_contiguous() and scores.is_cuda and ids.is_cuda):
+            raise ValueError("out must be contiguous CUDA (f64 [B,k], i64 [B,k]) tensors")
+    else:
+        scores = torch.empty((b, k), dtype=torch.float64, device=dev)
+        ids = torch.empty((b, k), dtype=torch.int64, device=dev)
     if b == 0:
         return scores, ids, torch.zeros((0,), dtype=torch.int32, device=dev)
     flags = torch.empty((b,), dtype=torch.int32, device=dev)      # every mode writes all b entries
@@ -154,11 +188,11 @@ def merge_topk(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tup
 
 
 def merge_gathered(gathered: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """All-gather buffer i64 [G, B, 2k] (k fp64 score bit patterns, then k ids, per rank and query) -> global top-k."""
+    """All-gather buffer i64 [G, 2, B, k] (per rank a plane of fp64 score bit patterns and a plane of ids) -> global top-k."""
     _require_cuda(gathered, "gathered")
-    if gathered.dtype != torch.int64 or gathered.dim() != 3 or gathered.shape[2] != 2 * k:
-        raise ValueError("merge_gathered expects an int64 [G, B, 2k] tensor")
-    g, b, _ = gathered.shape
+    if gathered.dtype != torch.int64 or gathered.dim() != 4 or gathered.shape[1] != 2 or gathered.shape[3] != k:
+        raise ValueError("merge_gathered expects an int64 [G, 2, B, k] tensor")
+    g, _, b, _ = gathered.shape
     dev = gathered.device
     scores = torch.empty((b, k), dtype=torch.float64, device=dev)
     ids = torch.empty((b, k), dtype=torch.int64, device=dev)
@@ -210,7 +244,7 @@ def mmr_select(cand_doc: torch.Tensor, cand_rel: torch.Tensor, cand_n: torch.Ten
     dev = cand_doc.device
     picks = torch.empty((b, k_max), dtype=torch.int32, device=dev)
     n = torch.empty((b,), dtype=torch.int32, device=dev)
-    ws = _WS.get(dev, 256)
+    ws = _WS.get(dev, _lib.load().b200rag_mmr_select_workspace_bytes(b, nmax, int(vocab_size)))
     with torch.cuda.device(dev):
         check(_lib.load().b200rag_mmr_select(cand_doc.data_ptr(), cand_rel.data_ptr(), cand_n.data_ptr(), b, nmax,
                                              doc_tok_ptr.data_ptr(), doc_tok_ids.data_ptr(), int(vocab_size), lam.data_ptr(),
@@ -240,6 +274,7 @@ class DenseIndex:
             raise ValueError("DenseIndex lives on a CUDA device (b200rag has no CPU path)")
         self._rows = torch.empty((max(capacity, 0), dim), dtype=_TORCH_DTYPE[self.code], device=self.device)
         self.n = 0
+        self.last_flags: Optional[torch.Tensor] = None
         # upper bound on the stored rows' L2 norm (error margin of the tensor-core path's completeness proof)
         self.row_norm_bound = 1.001 if metric == "COSINE" else 0.0
 
@@ -285,16 +320,18 @@ class DenseIndex:
         return prepare_rows(q.contiguous(), self.code, self.metric == "COSINE")
 
     def search(self, queries_f32: torch.Tensor, k: int, mode: int = DENSE_AUTO, out_err: Optional[torch.Tensor] = None,
-               row_mask: Optional[torch.Tensor] = None):
+               row_mask: Optional[torch.Tensor] = None, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
         """queries fp32 [B, dim] (host or device) -> (scores f64 [B,k], ids i64 [B,k], flags i32 [B]) on device.
         row_mask (pack_row_mask) restricts the search to the allowed rows of this shard."""
         q16 = self.prepare_queries(queries_f32)
-        return self.search_prepared(q16, k, mode, out_err, row_mask)
+        return self.search_prepared(q16, k, mode, out_err, row_mask, out)
 
     def search_prepared(self, queries16: torch.Tensor, k: int, mode: int = DENSE_AUTO, out_err: Optional[torch.Tensor] = None,
-                        row_mask: Optional[torch.Tensor] = None):
-        return dense_topk(self._rows, queries16, k, self.id_offset, mode, n_rows=self.n,
-                          row_norm_bound=max(self.row_norm_bound, 1e-30), out_err=out_err, row_mask=row_mask)
+                        row_mask: Optional[torch.Tensor] = None, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        res = dense_topk(self._rows, queries16, k, self.id_offset, mode, n_rows=self.n,
+                         row_norm_bound=max(self.row_norm_bound, 1e-30), out_err=out_err, row_mask=row_mask, out=out)
+        self.last_flags = res[2]                 # per-query "needed the exact fallback" flags of the last search (device)
+        return res
 
 
 class SparseIndex:
@@ -302,7 +339,9 @@ class SparseIndex:
 
     Built from a doc-major CSR (rows = documents, columns = term ids, values = fp32 weights) -- the layout the
     reference assembles for its sparse collection (indexing.py:379-404).  The re-blocking runs on the GPU with torch
-    sort/scan ops (ingest side, not the hot path).
+    sort/scan ops (ingest side, not the hot path).  Blocks are independent of each other, so `append` re-blocks only the
+    new documents plus the last, partially filled block; earlier blocks are never touched (incremental ingest, the
+    reference's per-batch `collection.insert`, indexing.py:372,419,426).
     """
 
     def __init__(self, doc_ptr, term_ids, weights, n_terms: int, device="cuda", block_docs: int = 16384,
@@ -312,45 +351,122 @@ class SparseIndex:
             raise ValueError("SparseIndex lives on a CUDA device (b200rag has no CPU path)")
         if block_docs % 32 or not 0 < block_docs <= 32768:
             raise ValueError("block_docs must be a multiple of 32 in (0, 32768]")
-        def _t(a, np_dtype, t_dtype):           # numpy / list / torch (any device) -> torch tensor of the wanted dtype
-            return a.to(t_dtype) if torch.is_tensor(a) else torch.as_tensor(np.asarray(a, dtype=np_dtype))
-
-        doc_ptr = _t(doc_ptr, np.int64, torch.int64).cpu()
-        self.n_docs = int(doc_ptr.numel() - 1)
         self.n_terms = int(n_terms)
         self.block_docs = int(block_docs)
         self.id_offset = int(id_offset)
-        self.n_blocks = max(1, -(-self.n_docs // block_docs))
+        self.n_docs = 0
+        self.nnz = 0
+        self._n_blocks = 0                       # block rows in use (0 while the index is empty)
         dev = self.device
-        t = _t(term_ids, np.int64, torch.int64).to(dev)
-        w = _t(weights, np.float32, torch.float32).to(dev)
-        nnz = t.numel()
-        counts = (doc_ptr[1:] - doc_ptr[:-1]).to(dev)
-        d = torch.repeat_interleave(torch.arange(self.n_docs, device=dev, dtype=torch.int64), counts, output_size=nnz)
-        if nnz and (int(t.min()) < 0 or int(t.max()) >= n_terms):
+        self._post_doc = torch.empty(0, dtype=torch.int16, device=dev)      # capacity buffers, valid prefix = nnz
+        self._post_w = torch.empty(0, dtype=torch.float32, device=dev)
+        self._ptr = torch.zeros((1, n_terms + 1), dtype=torch.int64, device=dev)   # [block capacity, V + 1]
+        self.df = torch.zeros(n_terms, dtype=torch.int64, device=dev)        # document frequency per term (statistics)
+        self.blocks_built = 0                    # blocks (re)built so far: observability for the incremental-ingest test
+        self.append(doc_ptr, term_ids, weights)
+
+    @property
+    def n_blocks(self) -> int:
+        return max(1, self._n_blocks)
+
+    @property
+    def post_doc(self) -> torch.Tensor:
+        return self._post_doc[: self.nnz]
+
+    @property
+    def post_w(self) -> torch.Tensor:
+        return self._post_w[: self.nnz]
+
+    @property
+    def blk_term_ptr(self) -> torch.Tensor:
+        return self._ptr[: self.n_blocks]
+
+    @staticmethod
+    def _t(a, np_dtype, t_dtype):                # numpy / list / torch (any device) -> torch tensor of the wanted dtype
+        return a.to(t_dtype) if torch.is_tensor(a) else torch.as_tensor(np.asarray(a, dtype=np_dtype))
+
+    def append(self, doc_ptr, term_ids, weights) -> None:
+        """Append documents (doc-major CSR over the NEW documents only); they get rows n_docs, n_docs + 1, ..."""
+        dev, V, bd = self.device, self.n_terms, self.block_docs
+        doc_ptr = self._t(doc_ptr, np.int64, torch.int64).cpu()
+        n_new = int(doc_ptr.numel() - 1)
+        if n_new <= 0:
+            return
+        t = self._t(term_ids, np.int64, torch.int64).to(dev)
+        w = self._t(weights, np.float32, torch.float32).to(dev)
+        nnz_new = int(t.numel())
+        if int(doc_ptr[-1]) != nnz_new or w.numel() != nnz_new:
+            raise ValueError("CSR arrays are inconsistent (doc_ptr[-1] != nnz)")
+        if nnz_new and (int(t.min()) < 0 or int(t.max()) >= V):
             raise ValueError("term id out of range")
-        blk = d // block_docs
-        key = (blk * n_terms + t) * block_docs + (d - blk * block_docs)
+        counts = (doc_ptr[1:] - doc_ptr[:-1]).to(dev)
+        d = self.n_docs + torch.repeat_interleave(torch.arange(n_new, device=dev, dtype=torch.int64), counts, output_size=nnz_new)
+        first_blk = self.n_docs // bd              # first block that changes
+        keep_nnz = self.nnz
+        if self.n_docs % bd:
+            # the last block is partially filled: pull its postings back out (term of a posting = its position in the block's
+            # pointer row) and re-block them together with the new documents
+            row = self._ptr[first_blk]
+            keep_nnz = int(row[0])
+            cnt_old = row[1:] - row[:-1]
+            t_old = torch.repeat_interleave(torch.arange(V, device=dev, dtype=torch.int64), cnt_old, output_size=self.nnz - keep_nnz)
+            d_old = first_blk * bd + (self._post_doc[keep_nnz: self.nnz].to(torch.int64) & 0xffff)
+            d = torch.cat([d_old, d])
+            t_all = torch.cat([t_old, t])
+            w_all = torch.cat([self._post_w[keep_nnz: self.nnz], w])
+        else:
+            t_all, w_all = t, w
+        n_total = self.n_docs + n_new
+        n_blocks_total = -(-n_total // bd)
+        nb = n_blocks_total - first_blk            # blocks (re)built by this call
+        blk = d // bd - first_blk
+        key = (blk * V + t_all) * bd + (d % bd)
         key, order = torch.sort(key)
-        if nnz > 1 and bool((key[1:] == key[:-1]).any()):
+        if key.numel() > 1 and bool((key[1:] == key[:-1]).any()):
             raise ValueError("duplicate (document, term) pair in the CSR")
-        local = key % block_docs
+        local = key % bd
+        nnz_total = keep_nnz + int(key.numel())
+        self._reserve(nnz_total, n_blocks_total)
         # u16 bit patterns held in an int16 tensor (values >= 32768 wrap; the kernel reads uint16_t)
-        self.post_doc = (((local + 32768) % 65536) - 32768).to(torch.int16).contiguous()
-        self.post_w = w[order].contiguous()
-        seg = key // block_docs                                      # blk * n_terms + term
-        # blk_term_ptr[b*(V+1) + t] : start of (block b, term t); one extra entry per block
-        cnt = torch.bincount(seg, minlength=self.n_blocks * n_terms) if nnz else torch.zeros(
-            self.n_blocks * n_terms, dtype=torch.int64, device=dev)
-        cnt = cnt.view(self.n_blocks, n_terms)
-        start = torch.cumsum(cnt.view(-1), 0) - cnt.view(-1)
-        ptr = torch.empty((self.n_blocks, n_terms + 1), dtype=torch.int64, device=dev)
-        ptr[:, :n_terms] = start.view(self.n_blocks, n_terms)
-        ptr[:, n_terms] = torch.cumsum(cnt.sum(1), 0)
-        self.blk_term_ptr = ptr.contiguous()
-        self.nnz = int(nnz)
-        # term-major global view kept for statistics (df per term)
-        self.df = torch.bincount(t, minlength=n_terms) if nnz else torch.zeros(n_terms, dtype=torch.int64, device=dev)
+        self._post_doc[keep_nnz: nnz_total] = (((local + 32768) % 65536) - 32768).to(torch.int16)
+        self._post_w[keep_nnz: nnz_total] = w_all[order]
+        seg = key // bd                            # blk * V + term
+        cnt = torch.bincount(seg, minlength=nb * V) if key.numel() else torch.zeros(nb * V, dtype=torch.int64, device=dev)
+        start = keep_nnz + torch.cumsum(cnt, 0) - cnt
+        self._ptr[first_blk: n_blocks_total, :V] = start.view(nb, V)
+        self._ptr[first_blk: n_blocks_total, V] = keep_nnz + torch.cumsum(cnt.view(nb, V).sum(1), 0)
+        if nnz_new:
+            self.df += torch.bincount(t, minlength=V)
+        self.n_docs, self.nnz, self._n_blocks = n_total, nnz_total, n_blocks_total
+        self.blocks_built += nb
+
+    def to_doc_major(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """The index as a doc-major CSR again (device tensors: doc_ptr i64 [n_docs+1], term ids i64 ascending per document,
+        weights f32) -- checkpointing and compaction read the postings back instead of keeping a host copy of them."""
+        dev, V, bd = self.device, self.n_terms, self.block_docs
+        ptr = self.blk_term_ptr
+        cnt = (ptr[:, 1:] - ptr[:, :-1]).reshape(-1)                              # postings per (block, term)
+        seg = torch.repeat_interleave(torch.arange(cnt.numel(), device=dev, dtype=torch.int64), cnt, output_size=self.nnz)
+        d = (seg // V) * bd + (self.post_doc.to(torch.int64) & 0xffff)
+        key, order = torch.sort(d * V + seg % V)
+        doc_ptr = torch.zeros(self.n_docs + 1, dtype=torch.int64, device=dev)
+        if self.nnz:
+            doc_ptr[1:] = torch.cumsum(torch.bincount(key // V, minlength=self.n_docs), 0)
+        return doc_ptr, key % V, self.post_w[order]
+
+    def _reserve(self, nnz: int, n_blocks: int) -> None:
+        if nnz > self._post_doc.numel():
+            cap = max(nnz, int(self._post_doc.numel() * 1.5))
+            for name in ("_post_doc", "_post_w"):
+                old = getattr(self, name)
+                new = torch.empty(cap, dtype=old.dtype, device=self.device)
+                new[: self.nnz] = old[: self.nnz]
+                setattr(self, name, new)
+        if n_blocks > self._ptr.shape[0]:
+            cap = max(n_blocks, int(self._ptr.shape[0] * 1.5))
+            new = torch.zeros((cap, self.n_terms + 1), dtype=torch.int64, device=self.device)
+            new[: self._n_blocks] = self._ptr[: self._n_blocks]
+            self._ptr = new
 
     def search(self, q_ptr, q_terms, q_vals, k: int, doc_mask: Optional[torch.Tensor] = None):
         """CSR queries (q_ptr i64 [B+1], q_terms i32 ascending per query, q_vals f32) ->
@@ -367,7 +483,7 @@ class SparseIndex:
         with torch.cuda.device(dev):
             nbytes = L.b200rag_sparse_topk_workspace_bytes(self.n_docs, self.block_docs, b, k)
             ws = _WS.get(dev, nbytes)
-            check(L.b200rag_sparse_topk_masked(self.blk_term_ptr.data_ptr(), self.post_doc.data_ptr(), self.post_w.data_ptr(),
+            check(L.b200rag_sparse_topk_masked(self.blk_term_ptr.data_ptr(), self._post_doc.data_ptr(), self._post_w.data_ptr(),
                                                self.n_docs, self.n_terms, self.block_docs, q_ptr.data_ptr(), q_terms.data_ptr(),
                                                q_vals.data_ptr(), b, k, self.id_offset, scores.data_ptr(), ids.data_ptr(),
                                                counts.data_ptr(), doc_mask.data_ptr() if doc_mask is not None else None,

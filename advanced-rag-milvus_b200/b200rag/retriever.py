@@ -293,7 +293,39 @@ class B200HybridRetriever:
         """RRF (+ MMR where a query's profile enables it) for a batch, entirely on the device.
 
         lists: per retrieval method (semantic, sparse[, domain]) a triple (scores f64 [B,K_l], row ids i64 [B,K_l]
-        with -1 padding, valid counts i32 [B]); configs: one RetrievalConfig per query."""
+        with -1 padding, valid counts i32 [B]); configs: one RetrievalConfig per query.
+
+        On a row-sharded manager every rank holds the same merged candidate lists; the fusion work is then split BY QUERY:
+        rank r fuses a contiguous slice of the batch and one all-gather hands every rank the whole result."""
+        b = len(configs)
+        t_max = max(c.top_k for c in configs)
+        m = self.index_manager
+        world, rank = getattr(m, "world", 1), getattr(m, "rank", 0)
+        if world <= 1 or b < 2 * world:
+            return self._fuse_local(lists, configs, t_max)
+        import torch.distributed as dist
+        per = -(-b // world)
+        lo, hi = min(b, rank * per), min(b, (rank + 1) * per)
+        dev = self.device
+        msg = torch.zeros((per, 4 * t_max + 1), dtype=torch.int64, device=dev)
+        if hi > lo:
+            r = self._fuse_local([(s[lo:hi], i[lo:hi], c[lo:hi]) for s, i, c in lists], configs[lo:hi], t_max)
+            n = hi - lo
+            msg[:n, :t_max] = r.rows
+            msg[:n, t_max: 2 * t_max] = r.scores.view(torch.int64)
+            msg[:n, 2 * t_max: 3 * t_max] = r.original_score.view(torch.int64)
+            msg[:n, 3 * t_max: 4 * t_max] = (r.mask.to(torch.int64) << 32) | r.first_method.to(torch.int64)
+            msg[:n, 4 * t_max] = r.n.to(torch.int64)
+        out = torch.empty((world * per, 4 * t_max + 1), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, msg, group=getattr(m, "group", None))
+        out = out[:b]
+        packed = out[:, 3 * t_max: 4 * t_max]
+        return BatchResult(out[:, :t_max].contiguous(), out[:, t_max: 2 * t_max].contiguous().view(torch.float64),
+                           (packed >> 32).to(torch.int32), out[:, 4 * t_max].to(torch.int32),
+                           (packed & 0xffffffff).to(torch.int32), out[:, 2 * t_max: 3 * t_max].contiguous().view(torch.float64))
+
+    def _fuse_local(self, lists: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]], configs: Sequence[RetrievalConfig],
+                    t_max: int) -> "BatchResult":
         dev = self.device
         b = len(configs)
         kmax = max(int(ids.shape[1]) for _, ids, _ in lists)
@@ -308,7 +340,6 @@ class B200HybridRetriever:
                          dtype=torch.float64, device=dev)
         fused = engine.rrf_fuse(lid.contiguous(), llen.contiguous(), w, RRF_K)
         top = torch.tensor([c.top_k for c in configs], dtype=torch.int32, device=dev)
-        t_max = max(c.top_k for c in configs)
         tot = fused.ids.shape[1]
         pos = torch.arange(t_max, device=dev)[None, :].expand(b, t_max).clone()
         n_out = torch.minimum(fused.n, top)
@@ -373,15 +404,20 @@ class B200HybridRetriever:
         res_dev = self.retrieve_batch_embedded(sem, spa, configs, dom, expr)
         rows_h, sc_h, mk_h, n_h = (t.cpu().numpy() for t in (res_dev.rows, res_dev.scores, res_dev.mask, res_dev.n))
         first_h, orig_h = res_dev.first_method.cpu().numpy(), res_dev.original_score.cpu().numpy()
+        # result dicts for the whole batch from one gather per payload column (indexing.py:534-551 shape), then the tags the
+        # reference adds on the way (retrieval.py:361-363, 469-470, 473-483, 332)
+        valid = np.arange(rows_h.shape[1])[None, :] < n_h[:, None]
+        flat = m.payload.hits(rows_h[valid], sc_h[valid])
+        first_f, orig_f, mk_f = first_h[valid].tolist(), orig_h[valid].tolist(), mk_h[valid].tolist()
         now = datetime.utcnow()
-        out = []
+        out, pos = [], 0
         for b, nm in enumerate(names):
-            res = []
-            for r in range(int(n_h[b])):
-                hit = m.payload.hit(int(rows_h[b, r]), float(sc_h[b, r]))
-                hit["method"] = METHODS[int(first_h[b, r])]
-                hit["original_score"] = float(orig_h[b, r])
-                hit["retrieval_methods"] = [mm for bit, mm in enumerate(METHODS) if mk_h[b, r] >> bit & 1]
+            res = flat[pos: pos + int(n_h[b])]
+            for j, hit in enumerate(res, start=pos):
+                hit["method"] = METHODS[first_f[j]]
+                hit["original_score"] = orig_f[j]
+                mk = mk_f[j]
+                hit["retrieval_methods"] = [mm for bit, mm in enumerate(METHODS) if mk >> bit & 1]
                 meta = hit["metadata"]
                 if meta.get("timestamp") is not None:
                     try:
@@ -390,6 +426,6 @@ class B200HybridRetriever:
                     except Exception:  # noqa: BLE001
                         pass
                 meta.setdefault("retrieval_profile", nm)
-                res.append(hit)
+            pos += int(n_h[b])
             out.append(res)
         return out

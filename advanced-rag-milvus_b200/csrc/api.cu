@@ -21,6 +21,29 @@ static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+// ---- options -----------------------------------------------------------------------------------
+static std::atomic<int> g_opt[OPT_COUNT];
+static const char* const kOptNames[OPT_COUNT] = {"scan_version", "qg_span", "epi", "no_sample", "stage_rows", "sample_mult",
+                                                 "mmr_path", "sparse_slices", "sparse_flags", "no_tier0", "finish_version"};
+static struct OptInit { OptInit() { for (auto& o : g_opt) o.store(-1, std::memory_order_relaxed); } } g_opt_init;
+int option(Option o, int dflt) {
+    const int v = g_opt[o].load(std::memory_order_relaxed);
+    return v < 0 ? dflt : v;
+}
+static int option_index(const char* name) {
+    if (!name) return -1;
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (strcmp(name, kOptNames[i]) == 0) return i;
+    return -1;
+}
+
+// ---- caller-owned debug buffers (thread local: two threads profiling at once do not see each other) ----
+static thread_local unsigned long long* g_stats_ptr[STATS_KINDS] = {nullptr, nullptr};
+static thread_local size_t g_stats_cap[STATS_KINDS] = {0, 0};
+unsigned long long* stats_buffer(StatsKind k, size_t need_slots) {
+    return (g_stats_ptr[k] && g_stats_cap[k] >= need_slots) ? g_stats_ptr[k] : nullptr;
+}
+
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return B200RAG_E_CUDA;
@@ -89,6 +112,25 @@ const char* b200rag_last_error(void) { return g_err; }
 
 int b200rag_abi_version(void) { return B200RAG_ABI_VERSION; }
 uint64_t b200rag_kernel_launch_count(void) { return b200rag::launch_count(); }
+
+int b200rag_set_option(const char* name, int64_t value) {
+    const int i = option_index(name);
+    B200_REQUIRE(i >= 0, "set_option: unknown option '%s'", name ? name : "(null)");
+    g_opt[i].store(value < 0 ? -1 : (int)value, std::memory_order_relaxed);
+    return B200RAG_OK;
+}
+
+int64_t b200rag_get_option(const char* name) {
+    const int i = option_index(name);
+    return i < 0 ? -2 : (int64_t)g_opt[i].load(std::memory_order_relaxed);
+}
+
+int b200rag_debug_set_stats_buffer(int32_t kind, uint64_t* device_buf, size_t n_slots) {
+    B200_REQUIRE(kind >= 0 && kind < STATS_KINDS, "debug_set_stats_buffer: bad kind %d", kind);
+    g_stats_ptr[kind] = reinterpret_cast<unsigned long long*>(device_buf);
+    g_stats_cap[kind] = device_buf ? n_slots : 0;
+    return B200RAG_OK;
+}
 
 int b200rag_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;

@@ -15,6 +15,15 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 void count_launch();   // bumps the process-wide kernel-launch counter (b200rag_kernel_launch_count)
 
+// A/B options (b200rag_set_option): integer knobs set through an explicit API call and read with relaxed atomic loads;
+// -1 = "not set, use the built-in default".  They replace the per-call getenv() lookups of round 1.
+enum Option { OPT_SCAN_VERSION = 0, OPT_QG_SPAN, OPT_EPI, OPT_NO_SAMPLE, OPT_STAGE_ROWS, OPT_SAMPLE_MULT, OPT_MMR_PATH,
+              OPT_SPARSE_SLICES, OPT_SPARSE_FLAGS, OPT_NO_TIER0, OPT_FINISH_VERSION, OPT_COUNT };
+int option(Option o, int dflt);
+// Per-thread debug buffers owned by the CALLER (b200rag_debug_set_stats_buffer): device pointer + capacity in u64 slots.
+enum StatsKind { STATS_SCAN = 0, STATS_SPARSE = 1, STATS_KINDS };
+unsigned long long* stats_buffer(StatsKind k, size_t need_slots);
+
 #define B200_CUDA_CHECK(expr)                                            \
     do {                                                                 \
         cudaError_t _e = (expr);                                         \

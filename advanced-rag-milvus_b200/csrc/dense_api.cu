@@ -15,7 +15,6 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
                float* out_err, int with_fallback, void* workspace, size_t workspace_bytes, cudaStream_t st,
                const uint32_t* row_mask);
 void profile_next_scan(void* a, void* b);
-int scan_stats(int enable, unsigned long long* out_host, int max_ctas);
 }  // namespace b200rag
 
 using namespace b200rag;
@@ -25,10 +24,6 @@ extern "C" {
 int b200rag_profile_next_scan(void* start_event, void* stop_event) {
     profile_next_scan(start_event, stop_event);
     return B200RAG_OK;
-}
-
-int b200rag_debug_scan_stats(int32_t enable, uint64_t* out_host, int32_t max_ctas) {
-    return scan_stats(enable, reinterpret_cast<unsigned long long*>(out_host), max_ctas);
 }
 
 size_t b200rag_dense_topk_workspace_bytes(int64_t n_rows, int32_t dim, int32_t n_queries, int32_t k, int32_t mode) {

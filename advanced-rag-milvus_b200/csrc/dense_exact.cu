@@ -169,8 +169,9 @@ merge_topk_kernel(const double* __restrict__ cand_scores, const int64_t* __restr
     if (out_counts && tid == 0) out_counts[q] = n;
 }
 
-// Merge straight out of the all-gather buffer: gathered i64 [n_ranks][n_queries][2k] holds, per rank and query, k fp64
-// score bit patterns followed by k ids (b200rag/distributed.py packs it that way).  Same ranking rule as above.
+// Merge straight out of the all-gather buffer: gathered i64 [n_ranks][2][n_queries][k] holds, per rank, a plane of fp64
+// score bit patterns and a plane of ids -- the two output arrays of the rank's local search, which writes them directly
+// into its send buffer (b200rag/distributed.py; no pack pass between the search and the collective).  Same ranking rule.
 __global__ void __launch_bounds__(MG_THREADS)
 merge_gathered_kernel(const int64_t* __restrict__ gathered, int n_ranks, int n_queries, int k, int cap,
                       double* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
@@ -189,9 +190,9 @@ merge_gathered_kernel(const int64_t* __restrict__ gathered, int n_ranks, int n_q
         double sc = 0.0;
         if (valid) {
             const int g = i / k, j = i - g * k;
-            const int64_t* rec = gathered + ((size_t)g * n_queries + q) * (2 * (size_t)k);
-            id = rec[k + j];
-            sc = __longlong_as_double(rec[j]);
+            const int64_t* plane = gathered + (size_t)g * 2 * n_queries * k + (size_t)q * k + j;
+            id = plane[(size_t)n_queries * k];
+            sc = __longlong_as_double(plane[0]);
         }
         valid = valid && id >= 0;
         tk.offer(valid, valid ? mono64(sc) : 0, ~(uint64_t)id);

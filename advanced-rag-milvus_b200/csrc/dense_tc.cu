@@ -438,14 +438,15 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static PFN_tmapEncodeTiled get_encode() {
-    static PFN_tmapEncodeTiled fn = nullptr;
-    if (!fn) {
+    // function-local static: initialised once, thread-safe (C++11)
+    static const PFN_tmapEncodeTiled fn = []() -> PFN_tmapEncodeTiled {
         void* ptr = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
-    }
+            return reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
+        return nullptr;
+    }();
     return fn;
 }
 
@@ -485,19 +486,16 @@ struct TensorPlan {
 static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
 
 static int sm_count_cached() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
+    // one rank drives one GPU model (B200): initialised once, thread-safe (C++11 static)
+    static const int n = []() {
+        int dev = 0, v = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+        return v;
+    }();
     return n;
 }
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
 
 static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     TensorPlan pl;
@@ -510,7 +508,7 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     // (A generation 2 -- query block resident in TMEM, TS-mode MMA with N = 64 accumulators, multicast corpus tiles -- was
     // measured at 0.8 PFLOP/s, MMA-issue bound, and removed; it is in the history at commit 1cee701.)
     pl.version = pl.nqb >= 2 ? 3 : 1;
-    int forced = env_int("B200RAG_SCAN_VERSION", 0);
+    int forced = option(OPT_SCAN_VERSION, 0);
     if (forced == 1 || forced == 3) pl.version = forced;
     int units;                                              // co-resident scheduling units (CTAs or clusters)
     int qgroups;
@@ -521,7 +519,7 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
         pl.nqb = qgroups * 2;                               // candidate / threshold buffers cover the padded block too
         // tile-major span: as many query-block pairs per work item as fit next to the stage ring in shared memory
         pl.qg_span = qgroups < TC_QG_SPAN_MAX ? qgroups : TC_QG_SPAN_MAX;
-        int fs = env_int("B200RAG_QG_SPAN", 0);
+        int fs = option(OPT_QG_SPAN, 0);
         if (fs >= 1 && fs <= TC_QG_SPAN_MAX) pl.qg_span = fs < qgroups ? fs : qgroups;
         while (pl.qg_span > 1 && scan3_smem_bytes(pl.cap, pl.qg_span) > TC_SMEM_LIMIT) --pl.qg_span;
         units = scan3_max_clusters(pl.cap, pl.qg_span, pl.sm_count);
@@ -555,11 +553,11 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     // every survivor is appended by the epilogue and gathered again by the finish kernel.  Small corpora cap the stride
     // (>= 4 sampled tiles); below r * stride = 6 k' (2e-8) the pass is skipped.
     pl.s_rank = TC_SAMPLE_R;
-    pl.s_stride = env_int("B200RAG_SAMPLE_MULT", 8) * pl.kprime / TC_SAMPLE_R;       // (A/B knob: rows above the threshold, in k')
+    pl.s_stride = option(OPT_SAMPLE_MULT, 8) * pl.kprime / TC_SAMPLE_R;       // (A/B knob: rows above the threshold, in k')
     if (pl.s_stride > pl.n_tiles / 4) pl.s_stride = pl.n_tiles / 4;
     if (pl.s_stride < 1) pl.s_stride = 1;
     pl.s_tiles = pl.n_tiles / pl.s_stride;
-    pl.sample = pl.s_tiles >= 4 && pl.s_rank * pl.s_stride >= 6 * pl.kprime && env_int("B200RAG_NO_SAMPLE", 0) == 0;
+    pl.sample = pl.s_tiles >= 4 && pl.s_rank * pl.s_stride >= 6 * pl.kprime && option(OPT_NO_SAMPLE, 0) == 0;
     pl.s_chunks = want < pl.s_tiles ? want : (pl.s_tiles > 0 ? pl.s_tiles : 1);
     pl.s_items = qgroups * pl.s_chunks;
     pl.s_kprime = TC_SAMPLE_R;
@@ -569,7 +567,7 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     pl.finish_smem = (size_t)dim * 8 + (size_t)pl.kprime * (8 + 4) + (size_t)pl.n_chunks * 4 + 32 +
                      BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.topk_cap) + 64;
     pl.stage_rows = FN_THREADS / 8;                             // staged candidate rows of one re-score batch
-    { int sr = env_int("B200RAG_STAGE_ROWS", 0); if (sr == 8 || sr == 16 || sr == 32) pl.stage_rows = sr; }
+    { int sr = option(OPT_STAGE_ROWS, 0); if (sr == 8 || sr == 16 || sr == 32) pl.stage_rows = sr; }
     while (pl.stage_rows > 1 && pl.finish_smem + (size_t)pl.stage_rows * ((size_t)dim * 2 + 16) > 160 * 1024) pl.stage_rows /= 2;
     pl.finish_smem += (size_t)pl.stage_rows * ((size_t)dim * 2 + 16);
     size_t off = 0;
@@ -601,16 +599,6 @@ bool tensor_supported(int64_t n_rows, int dim, int n_q, int k) {
     return !(pl.cap > TC_MAX_C || pl.scan_smem > TC_SMEM_LIMIT || n_rows >= ((int64_t)1 << 32) - TC_BN);
 }
 
-static bool g_stats_enabled = false;
-static unsigned long long* g_stats_last = nullptr;
-int scan_stats(int enable, unsigned long long* out_host, int max_ctas) {
-    g_stats_enabled = enable != 0;
-    if (out_host && g_stats_last && max_ctas > 0) {
-        if (max_ctas > 256) max_ctas = 256;
-        B200_CUDA_CHECK(cudaMemcpy(out_host, g_stats_last, (size_t)max_ctas * ST_N * 8, cudaMemcpyDeviceToHost));
-    }
-    return B200RAG_OK;
-}
 
 static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
 void profile_next_scan(void* a, void* b) { g_prof_start = static_cast<cudaEvent_t>(a); g_prof_stop = static_cast<cudaEvent_t>(b); }
@@ -660,11 +648,9 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
         }
         sp.queries = static_cast<const uint16_t*>(q_scan);
         sp.row_mask = row_mask;
-        sp.stats = g_stats_enabled ? reinterpret_cast<unsigned long long*>(ws + pl.off_stats) : nullptr;
-        if (g_stats_enabled) {
-            B200_CUDA_CHECK(cudaMemsetAsync(sp.stats, 0, (size_t)256 * ST_N * 8, st));
-            g_stats_last = sp.stats;
-        }
+        // per-role cycle counters go to the caller's buffer of this thread (b200rag_debug_set_stats_buffer), if any
+        sp.stats = stats_buffer(STATS_SCAN, (size_t)256 * ST_N);
+        if (sp.stats) B200_CUDA_CHECK(cudaMemsetAsync(sp.stats, 0, (size_t)256 * ST_N * 8, st));
         CUtensorMap map_q, map_x;
         if (pl.version == 1) {
             int rc = make_tensor_map(&map_q, q_scan, n_q_scan, dim, dtype, TC_BM);   // whole blocks

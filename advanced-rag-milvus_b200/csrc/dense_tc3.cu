@@ -21,6 +21,7 @@
 //               owns one query, threshold filter, append of the rare survivors, warp-cooperative compaction.  The
 //               accumulator is handed back by arriving on the LEADER's tmem-empty barrier (8 arrivals: 4 warps x 2 CTAs).
 #include <cstdlib>
+#include <mutex>
 
 #include "tc_common.cuh"
 
@@ -269,7 +270,10 @@ size_t scan3_smem_bytes(int cap, int span) {
 int scan3_max_clusters_query(int cap, int span, int sm_count);
 // Number of CTA pairs that can be co-resident (the kernel is persistent: every pair must be resident at once).
 int scan3_max_clusters(int cap, int span, int sm_count) {
-    static int cached_cap = -1, cached_span = -1, cached_sm = -1, cached_val = 0;      // the occupancy query costs tens of microseconds per call
+    // the occupancy query costs tens of microseconds per call: one cached answer, guarded (the C ABI is reentrant)
+    static std::mutex mu;
+    static int cached_cap = -1, cached_span = -1, cached_sm = -1, cached_val = 0;
+    std::lock_guard<std::mutex> lock(mu);
     if (cap == cached_cap && span == cached_span && sm_count == cached_sm) return cached_val;
     const int val = scan3_max_clusters_query(cap, span, sm_count);
     cached_cap = cap; cached_span = span; cached_sm = sm_count; cached_val = val;
@@ -303,8 +307,7 @@ int launch_scan3(const void* corpus16, int dtype, const ScanParams& sp, int max_
     rc = make_tensor_map(&map_x, corpus16, sp.n_rows, sp.dim, dtype, T3_HALF);
     if (rc) return rc;
     const size_t smem = scan3_smem_bytes(sp.cap > span_cap ? sp.cap : span_cap, span_max);
-    const char* ev = getenv("B200RAG_EPI");                 // A/B switch of the epilogue variant (tc_common.cuh: epi_filter_group)
-    const bool var0 = ev && ev[0] == '0';
+    const bool var0 = option(OPT_EPI, 1) == 0;             // A/B switch of the epilogue variant (tc_common.cuh: epi_filter_group)
     if (var0) B200_CUDA_CHECK(cudaFuncSetAttribute(dense_scan3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else B200_CUDA_CHECK(cudaFuncSetAttribute(dense_scan3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int n_clusters = sp.n_items < max_clusters ? sp.n_items : max_clusters;

@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(MMR_MAX_THREADS)
 mmr_select_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict__ cand_rel, const int32_t* __restrict__ cand_n,
                   int n_max, const int64_t* __restrict__ doc_tok_ptr, const int32_t* __restrict__ doc_tok_ids, int vocab_words,
                   const double* __restrict__ lambda, const int32_t* __restrict__ k_sel, int k_max,
-                  int32_t* __restrict__ out_pick, int32_t* __restrict__ out_n, int cache_cap, int n_hi) {
+                  int32_t* __restrict__ out_pick, int32_t* __restrict__ out_n, int cache_cap, int n_hi,
+                  uint32_t* __restrict__ bits_global) {
     extern __shared__ __align__(16) char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
@@ -46,11 +47,15 @@ mmr_select_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict
     int64_t* tok_begin = reinterpret_cast<int64_t*>(max_sim + n_max);   // [n_max] start of the candidate's token list
     int* tok_len = reinterpret_cast<int*>(tok_begin + n_max);      // [n_max]
     int* alive = tok_len + n_max;                                  // [n_max]
-    uint32_t* bits = reinterpret_cast<uint32_t*>(alive + n_max);   // [vocab_words]
+    // the vocabulary bitset: in shared memory when it fits; for very large vocabularies (> ~1.2M tokens) a per-query slice of
+    // the caller's workspace (vocab_smem_words = 0).  This CTA is the only reader and writer of its slice, plain stores /
+    // ld.cg loads around the pick loop's barriers keep it coherent.
+    const int vocab_smem_words = bits_global ? 0 : vocab_words;
+    uint32_t* bits = bits_global ? bits_global + (size_t)q * vocab_words : reinterpret_cast<uint32_t*>(alive + n_max);
     // token cache: the low 16 bits of the candidates' token ids, list after list, for as many leading candidates as
     // fit; hi_bnd[c][b] = number of tokens of candidate c whose id is < (b + 1) << 16 (lists are sorted), which gives
     // the high bits back.  Reading the lists from L2 on every pick (100 picks x 360 KB per query) was the bound.
-    int* cache_off = reinterpret_cast<int*>(bits + vocab_words);                        // [n_max]
+    int* cache_off = reinterpret_cast<int*>(reinterpret_cast<uint32_t*>(alive + n_max) + vocab_smem_words);   // [n_max]
     uint16_t* hi_bnd = reinterpret_cast<uint16_t*>(cache_off + n_max);                  // [n_max][n_hi]
     uint16_t* cache = hi_bnd + (size_t)n_max * n_hi + ((n_max * n_hi) & 1);             // [cache_cap], 4-byte aligned
     __shared__ int s_ncached;
@@ -120,6 +125,11 @@ mmr_select_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict
     }
     __syncthreads();
 
+    // one bitset probe: shared memory, or (huge vocabularies) this query's slice of the workspace read around L1
+    auto probe = [&](int t) -> int {
+        const uint32_t w = bits_global ? __ldcg(bits + (t >> 5)) : bits[t >> 5];
+        return (int)((w >> (t & 31)) & 1u);
+    };
     for (int step = 0; step < k; ++step) {
         // ---- 1. argmax with "earliest wins" -------------------------------------------------------
         double best = -1e9;
@@ -191,14 +201,14 @@ mmr_select_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict
                             int hi = i >= b0;
                             for (int bb = 1; bb < n_hi; ++bb) hi += i >= bnd[bb];
                             const int t = (hi << 16) | src[i];
-                            inter += (bits[t >> 5] >> (t & 31)) & 1u;
+                            inter += probe(t);
                         }
                     }
                     for (int i = lane + 32 * MMR_R; i < len_c; i += 32) {
                         int hi = i >= b0;
                         for (int bb = 1; bb < n_hi; ++bb) hi += i >= bnd[bb];
                         const int t = (hi << 16) | src[i];
-                        inter += (bits[t >> 5] >> (t & 31)) & 1u;
+                        inter += probe(t);
                     }
                     inter = __reduce_add_sync(FULL, inter);
                     if (lane == j) { my_inter = inter; my_len = len_c; }
@@ -229,13 +239,13 @@ mmr_select_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict
 #pragma unroll
                         for (int r = 0; r < MMR_R; ++r) {
                             const int t = tt[g][r];
-                            if (t >= 0) inter += (bits[t >> 5] >> (t & 31)) & 1u;
+                            if (t >= 0) inter += probe(t);
                         }
                         if (lens[g] > 32 * MMR_R) {                       // long documents: the rest of the list
                             const int32_t* toks = doc_tok_ids + tok_begin[cb + (j0 + g) * nwarps];
                             for (int i = lane + 32 * MMR_R; i < lens[g]; i += 32) {
                                 const int t = __ldg(toks + i);
-                                inter += (bits[t >> 5] >> (t & 31)) & 1u;
+                                inter += probe(t);
                             }
                         }
                         inter = __reduce_add_sync(FULL, inter);
@@ -485,14 +495,25 @@ using namespace b200rag;
 
 extern "C" {
 
-size_t b200rag_mmr_select_workspace_bytes(int32_t, int32_t, int32_t) { return 256; }
+// Shared-memory plan of the general kernel (bytes): `fixed` = per-candidate state, `meta` = cache offsets + high-bit boundaries.
+static size_t mmr_fixed_bytes(int n_max) { return (size_t)n_max * (8 + 8 + 8 + 4 + 4) + 64; }
+// Does the vocabulary bitset fit into shared memory next to the per-candidate state?  If not it lives in the workspace.
+static bool mmr_bits_in_smem(int n_max, int vocab_words) {
+    return mmr_fixed_bytes(n_max) + (size_t)vocab_words * 4 + (size_t)n_max * 4 + 8 <= 200 * 1024;
+}
+
+size_t b200rag_mmr_select_workspace_bytes(int32_t n_queries, int32_t n_max, int32_t vocab_size) {
+    if (n_queries <= 0 || n_max <= 0 || vocab_size <= 0) return 256;
+    const int vocab_words = (vocab_size + 31) / 32;
+    if (mmr_bits_in_smem(n_max, vocab_words)) return 256;
+    return align_up((size_t)n_queries * vocab_words * 4, 256) + 256;      // one bitset slice per query
+}
 
 int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const int32_t* cand_n, int32_t n_queries,
                        int32_t n_max, const int64_t* doc_tok_ptr, const int32_t* doc_tok_ids, int32_t vocab_size,
                        const double* lambda, const int32_t* k_sel, int32_t k_max,
                        int32_t* out_pick, int32_t* out_n,
                        void* workspace, size_t workspace_bytes, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     B200_REQUIRE(cand_doc && cand_rel && cand_n && doc_tok_ptr && lambda && k_sel && out_pick && out_n, "mmr_select: null pointer");
     B200_REQUIRE(n_queries >= 0 && n_max >= 1 && vocab_size >= 1 && k_max >= 1, "mmr_select: bad sizes");
     if (n_queries == 0) return B200RAG_OK;
@@ -500,7 +521,7 @@ int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const in
     // tokens >= (n_hi << 16) do not exist; n_hi thresholds per candidate give the high bits of cached tokens back
     int n_hi = (vocab_size - 1) >> 16;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (n_max >= 32 && n_max <= MMT_THREADS && n_hi <= 2 && getenv("B200RAG_MMR_WARP") == nullptr) {
+    if (n_max >= 32 && n_max <= MMT_THREADS && n_hi <= 2 && option(OPT_MMR_PATH, 0) == 0) {
         // fast path: one thread per candidate, transposed token cache (static shared memory of the kernel: ~7 KB)
         const size_t limit = 227 * 1024 - 8192;
         const size_t bits_bytes = (size_t)vocab_words * 4;
@@ -515,27 +536,37 @@ int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const in
             return B200RAG_OK;
         }
     }
-    size_t fixed = (size_t)n_max * (8 + 8 + 8 + 4 + 4) + (size_t)vocab_words * 4 + 64;
-    size_t smem = fixed;
-    if (smem > 225 * 1024) {
-        set_error("mmr_select: n_max=%d vocab=%d needs %zu bytes of shared memory", n_max, vocab_size, smem);
+    // general kernel.  The launch always covers `meta` (cache offsets are written for every candidate even when nothing is
+    // cached -- round 1 launched without it when the cache was disabled and wrote past the allocation).
+    const bool bits_smem = mmr_bits_in_smem(n_max, vocab_words);
+    uint32_t* bits_global = nullptr;
+    if (!bits_smem) {
+        const size_t need = b200rag_mmr_select_workspace_bytes(n_queries, n_max, vocab_size);
+        if (!workspace || workspace_bytes < need) {
+            set_error("mmr_select: vocab=%d needs a %zu-byte workspace for the token bitsets (got %zu)", vocab_size, need, workspace_bytes);
+            return B200RAG_E_WORKSPACE;
+        }
+        bits_global = static_cast<uint32_t*>(workspace);
+    }
+    const size_t fixed = mmr_fixed_bytes(n_max) + (bits_smem ? (size_t)vocab_words * 4 : 0);
+    if (n_hi > 8) n_hi = 0;                            // token ids >= 2^19: no 16-bit token cache (lists are read through L2)
+    size_t meta = (size_t)n_max * 4 + (size_t)n_max * n_hi * 2 + 8;
+    const size_t limit = 227 * 1024 - 1024;            // static shared memory (reduction scratch) takes the rest
+    int cache_cap = 0;
+    if (n_hi > 0 || vocab_size <= 65536) {
+        if (fixed + meta + 4096 <= limit) cache_cap = (int)((limit - fixed - meta) / 2);
+    }
+    if (cache_cap == 0) { n_hi = 0; meta = (size_t)n_max * 4 + 8; }
+    const size_t smem = fixed + meta + (size_t)cache_cap * 2;
+    if (smem > limit) {
+        set_error("mmr_select: n_max=%d needs %zu bytes of shared memory", n_max, smem);
         return B200RAG_E_UNSUPPORTED;
     }
-    int cache_cap = 0;
-    if (n_hi <= 8) {
-        const size_t meta = (size_t)n_max * 4 + (size_t)n_max * n_hi * 2 + 8;
-        const size_t limit = 227 * 1024 - 1024;      // static shared memory (reduction scratch) takes the rest
-        if (fixed + meta + 4096 <= limit) {
-            cache_cap = (int)((limit - fixed - meta) / 2);
-            smem = fixed + meta + (size_t)cache_cap * 2;
-        }
-    }
-    if (cache_cap == 0) n_hi = 0;
     B200_CUDA_CHECK(cudaFuncSetAttribute(mmr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // one warp per candidate in the intersection phase: as many warps as there are candidates, up to 32
     const int threads = n_max >= 32 ? MMR_MAX_THREADS : (n_max >= 8 ? 256 : 128);
     mmr_select_kernel<<<n_queries, threads, smem, st>>>(cand_doc, cand_rel, cand_n, n_max, doc_tok_ptr, doc_tok_ids,
-                                                           vocab_words, lambda, k_sel, k_max, out_pick, out_n, cache_cap, n_hi); count_launch();
+                                                           vocab_words, lambda, k_sel, k_max, out_pick, out_n, cache_cap, n_hi, bits_global); count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;
 }

@@ -1,26 +1,29 @@
-// sparse_bm25.cu -- sparse inner-product (BM25-weighted) top-k over doc-range-blocked postings  (K3).
+// sparse_bm25.cu -- sparse inner-product (BM25-weighted) top-k over doc-range-blocked postings  (K3, second generation).
 //
-// One CTA (512 threads) owns one QUERY and walks the document blocks of its slice one after the other:
-//   * the block's per-document accumulators live in shared memory (fp32, block_docs <= 32768 -> 128 KB) and are zeroed
-//     once per CTA; collecting a block's candidates puts them back to zero;
-//   * the postings of up to 8 query terms inside the block are fetched TOGETHER (one coalesced u16 doc + f32 weight per
-//     thread and term; the ranges come from a shared-memory ring filled two blocks ahead with cp.async, the first four
-//     terms of the NEXT block are requested in the middle of the current one) and then applied in ascending term id with
-//     a barrier between terms, so every document sees  acc = fmaf(qv, w, acc)  in the canonical order (bit-identical to
-//     oracle/exact_scan.c:orc_sparse_topk).  Postings of one term hit distinct documents: no atomics on the accumulators;
-//   * candidates are collected in one of two ways, chosen per block from the running k-th best score `thr`:
-//       thr > 0  (the steady state): every thread reads 32+ accumulators with LDS.128, keeps the few that are >= thr and
-//                writes zeros back -- no bitmap, no atomics in the accumulate step (an untouched document holds exactly 0,
-//                so it can never pass a positive threshold);
-//       otherwise (first block(s), or < k positive candidates so far): a touched-bitmap marks the candidates and a
-//                thread walks the set bits of one or two 32-document words;
-//     survivors go to the block-level streaming top-k (select.cuh), which lives for the whole walk, so later blocks
-//     are filtered by the threshold earlier blocks established: appended in bulk (one slot reservation per warp, no
-//     barrier until the next block's postings are in flight) whenever they fit, compacted only when the buffer is full.
-// Algorithmic HBM traffic = 6 bytes per posting of the query's terms.  grid = (queries, slices): with fewer queries
-// than SMs the blocks are split into slices; merge_topk_kernel reduces the slices.
-// (Round 1 first ran one CTA per (query, block) that re-scanned all 32768 documents of the block: 4.1 ms for 256
-// queries over 1M documents = 0.8 % of the HBM roofline; see profiles/r1_hybrid_c4.md for this version.)
+// One 256-thread CTA owns one (query, slice of document blocks) and walks its blocks one after the other; two or three
+// CTAs share an SM.  The block's per-document accumulators live in shared memory (fp32, 64 KB at 16384-document blocks),
+// zeroed once per CTA -- collecting a block puts every touched accumulator back to zero.  Per block:
+//
+//   accumulate (ordered)  the first 256 postings of each of up to 8 query terms are requested TOGETHER (one u16 row + one f32
+//       weight per thread and term, all in flight at once), then applied in ascending term id so that every document sees
+//       acc = fmaf(qv, w, acc)  in the canonical order (bit-identical to oracle/exact_scan.c:orc_sparse_topk).  Only as many
+//       WARPS as a list has 32-posting pieces take part in its step (a 20-posting list costs one warp a dozen instructions,
+//       not the whole CTA), and the barrier between two steps shrinks to __syncwarp when both fit one warp.  Postings of one
+//       term hit distinct documents: no atomics on the accumulators.
+//   collect (unordered)   once the running k-th best score `thr` is positive -- after the first block or two -- the SAME
+//       postings are walked again as one flat index space spread evenly over the threads: s = atomicExch(&acc[row], 0);
+//       the first visitor of a document gets its final score, later visitors (other terms of the same document) get 0, and
+//       only s >= thr goes on.  The walk is proportional to the postings, it resets the accumulators as it goes, and there
+//       is no scan over the 16384 accumulators and no touched-bitmap (round 1 read 64 KB of shared memory per block to find
+//       ~2000 touched documents: 7.9 warp instructions per posting, see profiles/r1_sparse_ncu.md).  While thr <= 0 (first
+//       block, queries with non-positive scores) a touched-bitmap marks the candidates instead -- a document with score
+//       exactly 0 that shares a term with the query is still a hit.
+//   survivors go through a 1024-entry staging list into the CTA's streaming top-k (select.cuh), which lives for the whole
+//       walk.  If the list overflows (first blocks only) the overflowing documents keep their accumulator, the list is
+//       drained -- which raises thr -- and the collect pass runs again.
+// Slices of one query share their thresholds through a global atomicMax, so a slice that starts late does not repeat the
+// warm-up.  Algorithmic HBM traffic = 6 bytes per posting of the query's terms (the collect pass re-reads the 2-byte rows
+// from L1/L2).  grid = (queries, slices); merge_topk_kernel reduces the slices.
 #include "common.cuh"
 #include "select.cuh"
 
@@ -29,343 +32,319 @@ namespace b200rag {
 int launch_merge(const double* cand_scores, const int64_t* cand_ids, int n_launch, const int32_t* q_list, int n_cand, int k,
                  double* out_scores_f64, float* out_scores_f32, int64_t* out_ids, int32_t* out_counts, cudaStream_t st);
 
-// Debug: per-CTA cycle counters by phase (b200rag_debug_sparse_stats).  Thread 0 keeps them in shared memory (no registers).
-constexpr int SP_NSTAT = 12;
-static unsigned long long* g_sparse_stats = nullptr;     // device buffer [SP_STAT_CTAS][SP_NSTAT], or null
+constexpr int SP_THREADS = 256;
+constexpr int SP_WARPS = SP_THREADS / 32;
+constexpr int SP_TG = 8;            // query terms handled together (one register pair per term and thread)
+constexpr int SP_STAGE = 1024;      // survivors staged per collect pass
+constexpr int SP_NSTAT = 12;        // debug counters per CTA (b200rag_debug_set_stats_buffer kind 1)
 constexpr int SP_STAT_CTAS = 1024;
-#define SP_MARK(i)                                                                     \
-    do {                                                                               \
-        if (stats && tid == 0) {                                                       \
-            const long long now_ = clock64();                                          \
-            s_stat[i] += (unsigned long long)(now_ - s_last);                          \
-            s_last = now_;                                                             \
-        }                                                                              \
-    } while (0)
+constexpr int SP_MAX_SLICES = 32;
 
-constexpr int SP_THREADS = 512;     // with 16384-document blocks two CTAs fit per SM and overlap each other's latencies
-constexpr int SP_TG = 8;       // query terms fetched together (one register pair per term and thread)
+enum { SPS_TOTAL = 0, SPS_ACC, SPS_COLLECT, SPS_DRAIN, SPS_BLOCKS, SPS_STAGED, SPS_RESCANS, SPS_BITMAP_BLOCKS, SPS_POSTINGS };
 
-__device__ __forceinline__ void sp_cp_async8(void* smem_dst, const void* gsrc, unsigned src_bytes) {
-    // 8-byte asynchronous global -> shared copy; src_bytes = 0 writes zeros (nothing is read)
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
-                 "r"(src_bytes)
-                 : "memory");
-}
+struct SparseParams {
+    const int64_t* blk_term_ptr;
+    const uint16_t* post_doc;
+    const float* post_w;
+    int64_t n_docs;
+    int n_terms, block_docs, n_blocks, n_slices;
+    const int64_t* q_ptr;
+    const int32_t* q_terms;
+    const float* q_vals;
+    int k, cap;
+    int64_t id_offset;
+    double* part_scores;        // [n_queries][n_slices][k]   (n_slices > 1)
+    int64_t* part_ids;
+    float* out_scores;          // [n_queries][k]             (n_slices == 1: written directly)
+    int64_t* out_ids;
+    int32_t* out_counts;
+    unsigned int* gthr;         // [n_queries] mono32 keys of the best k-th score any slice has established (n_slices > 1)
+    const uint32_t* doc_mask;
+    int flags;                  // bit 0: never use the exchange collect (A/B)
+    unsigned long long* stats;
+};
 
-__global__ void __launch_bounds__(SP_THREADS, 2)
-sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __restrict__ post_doc,
-                    const float* __restrict__ post_w, int64_t n_docs, int n_terms, int block_docs, int n_blocks, int n_slices,
-                    const int64_t* __restrict__ q_ptr, const int32_t* __restrict__ q_terms, const float* __restrict__ q_vals,
-                    int k, int cap, int64_t id_offset, double* __restrict__ part_scores, int64_t* __restrict__ part_ids,
-                    const uint32_t* __restrict__ doc_mask, int flags, unsigned long long* __restrict__ stats) {
+__global__ void __launch_bounds__(SP_THREADS, 3) sparse_query_kernel(const SparseParams p) {
     extern __shared__ __align__(16) char smem[];
+    __shared__ long long s_beg[SP_TG];         // posting ranges of the current term group inside the current block
+    __shared__ int s_len[SP_TG];
+    __shared__ int s_off[SP_TG + 1];           // exclusive prefix of s_len: the flat index space of the collect pass
+    __shared__ float s_qv[SP_TG];
+    __shared__ int s_nstage;
+    __shared__ unsigned int s_gthr;
     __shared__ unsigned long long s_stat[SP_NSTAT];
     __shared__ long long s_last;
-    // posting ranges [s_beg, s_end) of the query's terms inside a block: slots 0..2 = the first SP_TG terms of block
-    // (blk % 3), filled two blocks ahead by cp.async; slot 3 = four later terms at a time (queries with more than SP_TG
-    // terms), filled synchronously
-    __shared__ __align__(16) long long s_beg[4][SP_TG], s_end[4][SP_TG];
-    __shared__ float s_qv[2][SP_TG];
-    __shared__ int s_total[2];                                                       // candidates of block (blk & 1)
-    const int tid = threadIdx.x;
-    if (stats && tid == 0) {
-        for (int i = 0; i < SP_NSTAT; ++i) s_stat[i] = 0;
-        s_last = clock64();
-    }
-    const bool allow_dense = flags & 1, allow_bulk = flags & 2;
-    const int q = blockIdx.x;
-    const int slice = blockIdx.y;
-    const int n_words = block_docs / 32;                                            // <= 2048
-    float* acc = reinterpret_cast<float*>(smem);                                    // [block_docs]
-    uint32_t* touched = reinterpret_cast<uint32_t*>(smem + (size_t)block_docs * 4);  // [n_words]
-    char* p = smem + (size_t)block_docs * 4 + (size_t)n_words * 4;
-    p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
-    BlockTopK<SP_THREADS, uint32_t> tk;
-    tk.attach(p, cap, k, SP_THREADS, /*start_digit=*/BlockTopK<SP_THREADS, uint32_t>::NLO + 3);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int q = blockIdx.x, slice = blockIdx.y;
+    const int block_docs = p.block_docs, n_words = block_docs >> 5;
+    float* acc = reinterpret_cast<float*>(smem);                                     // [block_docs]
+    uint32_t* touched = reinterpret_cast<uint32_t*>(acc + block_docs);                // [n_words]
+    uint32_t* stage_doc = touched + n_words;                                          // [SP_STAGE] row inside the block
+    float* stage_sc = reinterpret_cast<float*>(stage_doc + SP_STAGE);                 // [SP_STAGE]
+    char* tkmem = reinterpret_cast<char*>(stage_sc + SP_STAGE);
+    tkmem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tkmem) + 15) & ~uintptr_t(15));
+    using TopK = BlockTopK<SP_THREADS, uint32_t>;
+    TopK tk;
+    tk.attach(tkmem, p.cap, p.k, SP_THREADS, /*start_digit=*/TopK::NLO + 3);
     tk.init();
     for (int i = tid; i < block_docs; i += SP_THREADS) acc[i] = 0.0f;
     for (int i = tid; i < n_words; i += SP_THREADS) touched[i] = 0u;
-    if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
+    const bool stats = p.stats != nullptr;
+    if (tid == 0) {
+        s_nstage = 0;
+        s_gthr = 0u;
+        if (stats) {
+            for (int i = 0; i < SP_NSTAT; ++i) s_stat[i] = 0;
+            s_last = clock64();
+        }
+    }
+#define SP_MARK(i)                                                       \
+    do {                                                                 \
+        if (stats && tid == 0) {                                         \
+            const long long now_ = clock64();                            \
+            s_stat[i] += (unsigned long long)(now_ - s_last);            \
+            s_last = now_;                                               \
+        }                                                                \
+    } while (0)
 
-    const int64_t qs = q_ptr[q];
-    const int nq = (int)(q_ptr[q + 1] - qs);
-    const int b0 = (int)((int64_t)slice * n_blocks / n_slices), b1 = (int)((int64_t)(slice + 1) * n_blocks / n_slices);
-    // The chain block -> term pointers -> postings is two dependent trips to HBM, and nothing else in a block is long
-    // enough to hide one.  Both are taken ahead of time:
-    //   * lanes 0..SP_TG-1 copy the ranges of block blk+2 straight into shared memory (cp.async: no registers, nothing
-    //     waits on it) at the top of block blk;
-    //   * the postings travel in two register sets of SP_TG/2 terms: set A (terms 0..3) of block blk+1 is requested in
-    //     the middle of block blk and is in flight during the rest of the block and its whole collect; set B (terms 4..7)
-    //     is requested at the top of its block and has the four term steps of set A to arrive.
+    const int64_t qs = p.q_ptr[q];
+    const int nq = (int)(p.q_ptr[q + 1] - qs);
+    const int n_groups = (nq + SP_TG - 1) / SP_TG;
+    const bool multi = n_groups > 1;
+    const int b0 = (int)((int64_t)slice * p.n_blocks / p.n_slices), b1 = (int)((int64_t)(slice + 1) * p.n_blocks / p.n_slices);
+    const size_t row_stride = (size_t)p.n_terms + 1;
+
+    // ranges of term group g inside block blk: thread j < SP_TG owns term g * SP_TG + j
     int my_t = -1;
-    if (tid < SP_TG) {
-        float qv = 0.f;
-        if (tid < nq) {
-            const int t = q_terms[qs + tid];
-            if (t >= 0 && t < n_terms) { my_t = t; qv = q_vals[qs + tid]; }
-        }
-        s_qv[0][tid] = qv;
-    }
-    auto stage_ranges = [&](int blk, int slot) {          // lanes 0..SP_TG-1
-        const int64_t* src = blk_term_ptr + (size_t)blk * (n_terms + 1) + (my_t >= 0 ? my_t : 0);
-        const unsigned sz = my_t >= 0 ? 8u : 0u;
-        sp_cp_async8(&s_beg[slot][tid], src, sz);
-        sp_cp_async8(&s_end[slot][tid], src + 1, sz);
-    };
-    constexpr int SP_H = SP_TG / 2;
-    auto load_half = [&](int (&d)[SP_H], float (&w)[SP_H], int slot, int first) {
-#pragma unroll
-        for (int j = 0; j < SP_H; ++j) {
-            const long long i = s_beg[slot][first + j] + tid;
-            d[j] = -1;
-            w[j] = 0.f;
-            if (i < s_end[slot][first + j]) { d[j] = post_doc[i]; w[j] = post_w[i]; }
+    float my_qv = 0.f;
+    auto load_term = [&](int g) {
+        my_t = -1;
+        my_qv = 0.f;
+        const int j = g * SP_TG + tid;
+        if (tid < SP_TG && j < nq) {
+            const int t = p.q_terms[qs + j];
+            if (t >= 0 && t < p.n_terms) { my_t = t; my_qv = p.q_vals[qs + j]; }
         }
     };
-    const bool walk = nq > 0 && b0 < b1;
-    if (tid < SP_TG && walk) {
-        stage_ranges(b0, 0);
-        if (b0 + 1 < b1) stage_ranges(b0 + 1, 1);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    int dA[SP_H];
-    float wA[SP_H];
-#pragma unroll
-    for (int j = 0; j < SP_H; ++j) { dA[j] = -1; wA[j] = 0.f; }
-    if (walk) load_half(dA, wA, 0, 0);
-    SP_MARK(0);                                           // init
-    bool acc_busy = false;      // CTA-uniform: the previous block's survivors may still be read out of (and zeroed in) `acc`
-    int sl_cur = 0, sl_nxt = 1, sl_nx2 = 2;
-    for (int blk = b0; blk < b1; ++blk) {
-        const int64_t doc0 = (int64_t)blk * block_docs;
-        const int64_t* tp = blk_term_ptr + (size_t)blk * (n_terms + 1);
-        const int cur = blk & 1;
-        float thr_f = tk.threshold_hi32_as_float();      // stable here: the previous collect ended on a barrier
-        const bool dense = allow_dense && thr_f > 0.0f;  // CTA-uniform
-        // one term: first SP_THREADS postings from registers, the rest of a long list straight from memory (two in flight)
-        auto apply = [&](int d, float w, float qv, long long beg, long long e) {
-            if (d >= 0) {
-                acc[d] = fmaf(qv, w, acc[d]);
-                if (!dense) atomicOr(&touched[d >> 5], 1u << (d & 31));
-            }
-            for (long long i = beg + tid + SP_THREADS; i < e; i += 2 * SP_THREADS) {
-                const long long i1 = i + SP_THREADS;
-                const int d0 = post_doc[i];
-                const float w0 = post_w[i];
-                int d1 = -1;
-                float w1 = 0.f;
-                if (i1 < e) { d1 = post_doc[i1]; w1 = post_w[i1]; }
-                acc[d0] = fmaf(qv, w0, acc[d0]);
-                if (!dense) atomicOr(&touched[d0 >> 5], 1u << (d0 & 31));
-                if (d1 >= 0) {
-                    acc[d1] = fmaf(qv, w1, acc[d1]);
-                    if (!dense) atomicOr(&touched[d1 >> 5], 1u << (d1 & 31));
-                }
-            }
-        };
-        // ---- accumulate, in ascending term order with a barrier after every term ---------------------------------------
-        if (nq > 0) {
-            if (tid < SP_TG) {
-                // slot sl_nx2 held block blk-1: last read before that block's final term barrier
-                if (blk + 2 < b1) stage_ranges(blk + 2, sl_nx2);
-                asm volatile("cp.async.commit_group;" ::: "memory");          // (one group per block, possibly empty)
-            }
-            int dB[SP_H];
-            float wB[SP_H];
-            load_half(dB, wB, sl_cur, SP_H);
-            if (acc_busy) {                               // (waits while the postings are in flight)
-                __syncthreads();
-                acc_busy = false;
-            }
-#pragma unroll
-            for (int j = 0; j < SP_H; ++j) {
-                apply(dA[j], wA[j], s_qv[0][j], s_beg[sl_cur][j], s_end[sl_cur][j]);
-                // the ranges of block blk+1 were requested a whole block ago: everything but the newest group has landed
-                if (j == SP_H - 1 && tid < SP_TG) asm volatile("cp.async.wait_group 1;" ::: "memory");
-                __syncthreads();
-                if (j == 0) SP_MARK(2);                   // first term applied
-            }
-            if (blk + 1 < b1) load_half(dA, wA, sl_nxt, 0);
-            if (nq > SP_H) {
-#pragma unroll
-                for (int j = 0; j < SP_H; ++j) {
-                    apply(dB[j], wB[j], s_qv[0][SP_H + j], s_beg[sl_cur][SP_H + j], s_end[sl_cur][SP_H + j]);
-                    __syncthreads();
-                }
-            }
-            for (int g0 = SP_TG; g0 < nq; g0 += SP_H) {   // queries with more than SP_TG terms: four more at a time, unpipelined
-                if (tid < SP_H) {
-                    long long s = 0, e = 0;
-                    float qv = 0.f;
-                    if (g0 + tid < nq) {
-                        const int t = q_terms[qs + g0 + tid];
-                        if (t >= 0 && t < n_terms) { s = tp[t]; e = tp[t + 1]; qv = q_vals[qs + g0 + tid]; }
-                    }
-                    s_beg[3][tid] = s; s_end[3][tid] = e; s_qv[1][tid] = qv;
-                }
-                __syncthreads();
-                load_half(dB, wB, 3, 0);
-#pragma unroll
-                for (int j = 0; j < SP_H; ++j) {
-                    apply(dB[j], wB[j], s_qv[1][j], s_beg[3][j], s_end[3][j]);
-                    __syncthreads();
-                }
-            }
-            SP_MARK(3);                                   // remaining terms applied
-            const int t_ = sl_cur; sl_cur = sl_nxt; sl_nxt = sl_nx2; sl_nx2 = t_;
+    auto fetch_range = [&](int blk, long long& rb, int& rl) {
+        rb = 0;
+        rl = 0;
+        if (my_t >= 0) {
+            const int64_t* src = p.blk_term_ptr + (size_t)blk * row_stride + my_t;
+            rb = src[0];
+            rl = (int)(src[1] - rb);
         }
-        // ---- collect -------------------------------------------------------------------------------------------------
-        // `m` = this thread's candidate positions.  Losers are dropped with ONE float compare against the running k-th best
-        // score; the exact (score, id) comparison happens only for the few candidates at or above it.
-        unsigned long long m = 0;
-        if (dense) {
-            // bit 4*j + c  <->  document 4 * (j * SP_THREADS + tid) + c
-            float4* acc4 = reinterpret_cast<float4*>(acc);
-            const int nv = block_docs >> 2;
-            int sh = 0;
-            for (int v0 = tid; v0 < nv; v0 += 4 * SP_THREADS) {              // four LDS.128 in flight
-                float4 x[4];
+    };
+    auto publish_range = [&](long long rb, int rl) {          // threads < SP_TG, then a barrier, then thread 0 builds s_off
+        if (tid < SP_TG) { s_beg[tid] = rb; s_len[tid] = rl; s_qv[tid] = my_qv; }
+    };
+    auto build_offsets = [&]() {                              // after the barrier that follows publish_range
+        if (tid == 0) {
+            int o = 0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int v = v0 + u * SP_THREADS;
-                    x[u] = v < nv ? acc4[v] : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            for (int j = 0; j < SP_TG; ++j) { s_off[j] = o; o += s_len[j]; }
+            s_off[SP_TG] = o;
+            if (stats) s_stat[SPS_POSTINGS] += (unsigned long long)o;
+        }
+    };
+
+    // ---- ordered accumulate of the published term group; `prev_pw` = warps that took part in the previous non-empty step
+    auto accumulate_group = [&](bool bitmap, int& prev_pw) {
+        int dreg[SP_TG];
+        float wreg[SP_TG];
 #pragma unroll
-                for (int u = 0; u < 4; ++u, sh += 4) {
-                    const float4 y = x[u];
-                    if ((__float_as_uint(y.x) | __float_as_uint(y.y) | __float_as_uint(y.z) | __float_as_uint(y.w)) == 0u) continue;
-                    const unsigned b = (!(y.x < thr_f) ? 1u : 0u) | (!(y.y < thr_f) ? 2u : 0u) | (!(y.z < thr_f) ? 4u : 0u) |
-                                       (!(y.w < thr_f) ? 8u : 0u);
-                    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (b) {
-                        m |= (unsigned long long)b << sh;
-                        if (b & 1u) z.x = y.x;
-                        if (b & 2u) z.y = y.y;
-                        if (b & 4u) z.z = y.z;
-                        if (b & 8u) z.w = y.w;
-                    }
-                    acc4[v0 + u * SP_THREADS] = z;
-                }
-            }
-        } else {
-            // bits 0..31 <-> word tid of the bitmap, bits 32..63 <-> word tid + SP_THREADS
-            if (tid < n_words) { m = touched[tid]; touched[tid] = 0u; }
-            if (tid + SP_THREADS < n_words) { m |= (unsigned long long)touched[tid + SP_THREADS] << 32; touched[tid + SP_THREADS] = 0u; }
-            if (doc_mask && m) {
-                // metadata filter: documents that are not allowed are dropped here (their accumulators still have to go back
-                // to zero).  block_docs is a multiple of 32, so a bitmap word of the block is a word of the mask.
-                unsigned long long allowed = 0;
-                const int64_t w0 = (doc0 >> 5) + tid, w1 = w0 + SP_THREADS, n_mask_words = (n_docs + 31) >> 5;
-                if (tid < n_words && w0 < n_mask_words) allowed = __ldg(doc_mask + w0);
-                if (tid + SP_THREADS < n_words && w1 < n_mask_words) allowed |= (unsigned long long)__ldg(doc_mask + w1) << 32;
-                unsigned long long drop = m & ~allowed;
-                while (drop) {
-                    const int bpos = __ffsll((long long)drop) - 1;
-                    drop &= drop - 1;
-                    acc[bpos < 32 ? tid * 32 + bpos : (tid + SP_THREADS) * 32 + (bpos - 32)] = 0.0f;
-                }
-                m &= allowed;
+        for (int j = 0; j < SP_TG; ++j) {
+            dreg[j] = -1;
+            wreg[j] = 0.f;
+            if (tid < s_len[j]) {
+                const long long i = s_beg[j] + tid;
+                dreg[j] = p.post_doc[i];
+                wreg[j] = p.post_w[i];
             }
         }
-        // next candidate of this thread at or above the threshold (and allowed): true + its key, or false with m == 0
-        auto next_candidate = [&](const BlockTopK<SP_THREADS, uint32_t>::View& tv, uint64_t& h, uint32_t& l) -> bool {
-            while (m) {
-                const int bpos = __ffsll((long long)m) - 1;
-                m &= m - 1;
-                const int d = dense ? ((((bpos >> 2) * SP_THREADS + tid) << 2) | (bpos & 3))
-                                    : (bpos < 32 ? tid * 32 + bpos : (tid + SP_THREADS) * 32 + (bpos - 32));
-                const float sc = acc[d];
-                acc[d] = 0.0f;
-                if (sc < thr_f) continue;
-                if (dense && doc_mask) {            // (the bitmap path filtered its words above)
+#pragma unroll
+        for (int j = 0; j < SP_TG; ++j) {
+            const int len = s_len[j];
+            if (len == 0) continue;                                                  // CTA-uniform
+            const int pw = len >= SP_THREADS ? SP_WARPS : (len + 31) >> 5;
+            if (prev_pw) {
+                if (prev_pw > 1 || pw > 1) __syncthreads();
+                else __syncwarp();
+            }
+            prev_pw = pw;
+            if (warp < pw) {
+                const float qv = s_qv[j];
+                if (dreg[j] >= 0) {
+                    const int d = dreg[j];
+                    acc[d] = fmaf(qv, wreg[j], acc[d]);
+                    if (bitmap) atomicOr(&touched[d >> 5], 1u << (d & 31));
+                }
+                const long long beg = s_beg[j];
+                for (int i = tid + SP_THREADS; i < len; i += 2 * SP_THREADS) {      // long lists: two postings in flight
+                    const int i1 = i + SP_THREADS;
+                    const int d0 = p.post_doc[beg + i];
+                    const float w0 = p.post_w[beg + i];
+                    int d1 = -1;
+                    float w1 = 0.f;
+                    if (i1 < len) { d1 = p.post_doc[beg + i1]; w1 = p.post_w[beg + i1]; }
+                    acc[d0] = fmaf(qv, w0, acc[d0]);
+                    if (bitmap) atomicOr(&touched[d0 >> 5], 1u << (d0 & 31));
+                    if (d1 >= 0) {
+                        acc[d1] = fmaf(qv, w1, acc[d1]);
+                        if (bitmap) atomicOr(&touched[d1 >> 5], 1u << (d1 & 31));
+                    }
+                }
+            }
+        }
+    };
+
+    // a survivor goes to the staging list; false = the list is full (the caller keeps the document for the next pass)
+    auto stage = [&](int d, float sc) -> bool {
+        const int slot = atomicAdd(&s_nstage, 1);
+        if (slot >= SP_STAGE) return false;
+        stage_doc[slot] = (uint32_t)d;
+        stage_sc[slot] = sc;
+        return true;
+    };
+
+    // ---- exchange collect over the published term group: flat index space, every posting visited once
+    auto collect_group_exch = [&](float thr_f, int64_t doc0) {
+        const int total = s_off[SP_TG];
+        int j = 0;
+        for (int pos = tid; pos < total; pos += SP_THREADS) {
+            while (pos >= s_off[j + 1]) ++j;
+            const int d = p.post_doc[s_beg[j] + (pos - s_off[j])];
+            const float sc = atomicExch(&acc[d], 0.0f);
+            if (sc >= thr_f) {
+                bool ok = true;
+                if (p.doc_mask) {
                     const int64_t g = doc0 + d;
-                    if (!((__ldg(doc_mask + (g >> 5)) >> (g & 31)) & 1u)) continue;
+                    ok = (__ldg(p.doc_mask + (g >> 5)) >> (g & 31)) & 1u;
                 }
-                h = (uint64_t)mono32(sc);
-                l = ~(uint32_t)(doc0 + d);
-                if (tk.passes(tv, h, l)) return true;
+                if (ok && !stage(d, sc)) acc[d] = sc;         // list full: the document waits for the next pass
             }
-            return false;
-        };
-        {
-            int c = __popcll(m);
-            c = __reduce_add_sync(0xffffffffu, c);
-            if ((tid & 31) == 0 && c) atomicAdd(&s_total[cur], c);
         }
-        int held = tk.count();                            // nobody appends between the last settle and the next barrier
-        __syncthreads();
-        const int total = s_total[cur];
-        if (tid == 0) s_total[cur ^ 1] = 0;               // the previous block's counter: its readers are barriers behind
-        SP_MARK(4);                                       // accumulators scanned
-        if (total == 0) continue;
-        if (held + total > cap && held > k) {
-            // no room for this block's survivors: keep the k best now (raises the threshold, so fewer of them survive)
-            tk.compact();
-            held = tk.count();
-            thr_f = tk.threshold_hi32_as_float();
-            if (stats && tid == 0) s_stat[9] += 1;
-            SP_MARK(1);                                   // compaction
-        }
-        if (allow_bulk && held + total <= cap) {
-            // everything fits: every thread appends all its survivors at once.  The barrier that must separate this from the
-            // next block's accumulation is taken there, under the postings' latency; the count and the threshold are next
-            // read behind the term barriers.
-            const auto tv = tk.view();
-            if (!dense || doc_mask) {
-                // the dense scan kept exactly the scores >= thr_f; the bitmap walk and the document filter still have to drop theirs
-                unsigned long long keep = 0;
-                while (m) {
-                    const int bpos = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    const int d = dense ? ((((bpos >> 2) * SP_THREADS + tid) << 2) | (bpos & 3))
-                                        : (bpos < 32 ? tid * 32 + bpos : (tid + SP_THREADS) * 32 + (bpos - 32));
-                    bool ok = !(acc[d] < thr_f);
-                    if (ok && dense && doc_mask) {      // (the bitmap path filtered its words above)
-                        const int64_t g = doc0 + d;
-                        ok = (__ldg(doc_mask + (g >> 5)) >> (g & 31)) & 1u;
-                    }
-                    if (ok) keep |= 1ull << bpos;
-                    else acc[d] = 0.0f;
-                }
-                m = keep;
+    };
+    // ---- bitmap collect: every thread owns whole 32-document words
+    auto collect_bitmap = [&](float thr_f, int64_t doc0) {
+        const int64_t n_mask_words = (p.n_docs + 31) >> 5;
+        for (int w = tid; w < n_words; w += SP_THREADS) {
+            uint32_t m = touched[w];
+            if (!m) continue;
+            uint32_t allowed = 0xffffffffu;
+            if (p.doc_mask) {                                  // block_docs % 32 == 0: a bitmap word is a word of the mask
+                const int64_t gw = (doc0 >> 5) + w;
+                allowed = gw < n_mask_words ? __ldg(p.doc_mask + gw) : 0u;
             }
-            // one slot reservation per warp, then every lane moves its survivors out of `acc` on its own
-            const int c = __popcll(m);
-            int incl = c;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, off);
-                if ((tid & 31) >= off) incl += v;
-            }
-            const int n_warp = __shfl_sync(0xffffffffu, incl, 31);
-            if (n_warp) {
-                int slot = tk.reserve_warp(n_warp) + incl - c;
-                while (m) {
-                    const int bpos = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    const int d = dense ? ((((bpos >> 2) * SP_THREADS + tid) << 2) | (bpos & 3))
-                                        : (bpos < 32 ? tid * 32 + bpos : (tid + SP_THREADS) * 32 + (bpos - 32));
-                    const float sc = acc[d];
+            uint32_t keep = 0;
+            while (m) {
+                const int b = __ffs((int)m) - 1;
+                m &= m - 1;
+                const int d = w * 32 + b;
+                const float sc = acc[d];
+                if (!(sc < thr_f) && ((allowed >> b) & 1u)) {
+                    if (stage(d, sc)) acc[d] = 0.0f;
+                    else keep |= 1u << b;
+                } else {
                     acc[d] = 0.0f;
-                    tk.put(tv, slot++, (uint64_t)mono32(sc), ~(uint32_t)(doc0 + d));
                 }
             }
-            if (stats && tid == 0) { s_stat[7] += 1; s_stat[10] += total; }
-            acc_busy = true;
-            SP_MARK(5);                                   // bulk append
-        } else {
-            while (__syncthreads_or(m != 0ull)) {
-                if (stats && tid == 0) s_stat[7] += 1;                  // candidate rounds
+            touched[w] = keep;
+        }
+    };
+
+    load_term(0);
+    long long nb = 0;
+    int nl = 0;
+    if (b0 < b1) fetch_range(b0, nb, nl);
+    __syncthreads();
+    SP_MARK(SPS_TOTAL);
+    for (int blk = b0; blk < b1 && nq > 0; ++blk) {
+        const int64_t doc0 = (int64_t)blk * block_docs;
+        // ---- block top: publish the ranges fetched during the previous block, exchange thresholds with the other slices
+        publish_range(nb, nl);
+        if (tid == 0 && p.gthr) {
+            if (tk.st->has_thr) atomicMax(p.gthr + q, (unsigned int)tk.st->thr_hi);
+            unsigned int g;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(p.gthr + q) : "memory");
+            s_gthr = g;
+        }
+        __syncthreads();
+        build_offsets();
+        if (blk + 1 < b1) fetch_range(blk + 1, nb, nl);       // (group 0 of the next block: in flight during this one)
+        float thr_f = tk.threshold_hi32_as_float();
+        if (s_gthr) thr_f = fmaxf(thr_f, unmono32(s_gthr));
+        const bool bitmap = !(thr_f > 0.0f) || (p.flags & 1);  // CTA-uniform
+        // ---- accumulate, all term groups in ascending term order
+        int prev_pw = 0;
+        accumulate_group(bitmap, prev_pw);
+        for (int g = 1; g < n_groups; ++g) {                   // queries with more than SP_TG terms: unpipelined
+            __syncthreads();                                   // everyone is done with the published ranges
+            load_term(g);
+            long long rb;
+            int rl;
+            fetch_range(blk, rb, rl);
+            publish_range(rb, rl);
+            __syncthreads();
+            prev_pw = 0;                                       // (the barrier above already ordered the previous group)
+            accumulate_group(bitmap, prev_pw);
+        }
+        __syncthreads();
+        SP_MARK(SPS_ACC);
+        if (stats && tid == 0) { s_stat[SPS_BLOCKS] += 1; s_stat[SPS_BITMAP_BLOCKS] += bitmap ? 1 : 0; }
+        // ---- collect (repeated while the staging list overflows)
+        for (;;) {
+            if (bitmap) {
+                collect_bitmap(thr_f, doc0);
+            } else if (!multi) {
+                collect_group_exch(thr_f, doc0);               // (s_off was built at the block top)
+            } else {
+                for (int g = 0; g < n_groups; ++g) {
+                    __syncthreads();
+                    load_term(g);
+                    long long rb;
+                    int rl;
+                    fetch_range(blk, rb, rl);
+                    publish_range(rb, rl);
+                    __syncthreads();
+                    build_offsets();
+                    __syncthreads();
+                    collect_group_exch(thr_f, doc0);
+                }
+            }
+            __syncthreads();
+            const int staged_raw = s_nstage;
+            SP_MARK(SPS_COLLECT);
+            if (staged_raw == 0) break;
+            const int staged = staged_raw < SP_STAGE ? staged_raw : SP_STAGE;
+            for (int base = 0; base < staged; base += SP_THREADS) {
+                const int i = base + tid;
+                const auto tv = tk.view();
                 uint64_t h = 0;
                 uint32_t l = 0;
-                const auto tv = tk.view();
-                tk.append(tv, next_candidate(tv, h, l), h, l);
+                bool have = false;
+                if (i < staged) {
+                    h = (uint64_t)mono32(stage_sc[i]);
+                    l = ~(uint32_t)(doc0 + stage_doc[i]);
+                    have = tk.passes(tv, h, l);
+                }
+                tk.append(tv, have, h, l);
                 tk.settle();
-                thr_f = tk.threshold_hi32_as_float();
             }
-            SP_MARK(8);                                   // candidate rounds (offer + settle, one candidate per thread)
+            if (tid == 0) {
+                s_nstage = 0;
+                if (stats) { s_stat[SPS_STAGED] += staged; s_stat[SPS_RESCANS] += staged_raw > SP_STAGE ? 1 : 0; }
+            }
+            thr_f = fmaxf(thr_f, tk.threshold_hi32_as_float());
+            __syncthreads();
+            SP_MARK(SPS_DRAIN);
+            if (staged_raw <= SP_STAGE) break;
+        }
+        if (multi) {                                           // back to group 0 for the next block's prefetch
+            __syncthreads();
+            load_term(0);
+            if (blk + 1 < b1) fetch_range(blk + 1, nb, nl);
         }
     }
     __syncthreads();
@@ -373,30 +352,48 @@ sparse_query_kernel(const int64_t* __restrict__ blk_term_ptr, const uint16_t* __
     const int n = tk.count();
     const uint64_t* oh = tk.out_hi();
     const uint32_t* ol = tk.out_lo();
-    double* ps = part_scores + ((size_t)q * n_slices + slice) * k;
-    int64_t* pi = part_ids + ((size_t)q * n_slices + slice) * k;
-    for (int i = tid; i < k; i += SP_THREADS) {
-        if (i < n) {
-            ps[i] = (double)unmono32((uint32_t)oh[i]);
-            pi[i] = id_offset + (int64_t)(~ol[i]);
-        } else {
-            ps[i] = -CUDART_INF;
-            pi[i] = -1;
+    if (p.n_slices == 1) {
+        for (int i = tid; i < p.k; i += SP_THREADS) {
+            p.out_scores[(size_t)q * p.k + i] = i < n ? unmono32((uint32_t)oh[i]) : -CUDART_INF_F;
+            p.out_ids[(size_t)q * p.k + i] = i < n ? p.id_offset + (int64_t)(~ol[i]) : -1;
+        }
+        if (tid == 0) p.out_counts[q] = n;
+    } else {
+        double* ps = p.part_scores + ((size_t)q * p.n_slices + slice) * p.k;
+        int64_t* pi = p.part_ids + ((size_t)q * p.n_slices + slice) * p.k;
+        for (int i = tid; i < p.k; i += SP_THREADS) {
+            ps[i] = i < n ? (double)unmono32((uint32_t)oh[i]) : -CUDART_INF;
+            pi[i] = i < n ? p.id_offset + (int64_t)(~ol[i]) : -1;
         }
     }
-    SP_MARK(6);                                           // finalize + output
+    SP_MARK(SPS_TOTAL);                                        // init + finalize
     if (stats && tid == 0) {
         const int cta = blockIdx.y * gridDim.x + blockIdx.x;
         if (cta < SP_STAT_CTAS)
-            for (int i = 0; i < SP_NSTAT; ++i) stats[(size_t)cta * SP_NSTAT + i] = s_stat[i];
+            for (int i = 0; i < SP_NSTAT; ++i) p.stats[(size_t)cta * SP_NSTAT + i] = s_stat[i];
     }
+#undef SP_MARK
 }
 
 static size_t sparse_smem(int block_docs, int k, int* cap_out) {
-    int cap = BlockTopK<SP_THREADS, uint32_t>::capacity_for(k, SP_THREADS);
+    const int cap = BlockTopK<SP_THREADS, uint32_t>::capacity_for(k, SP_THREADS);
     if (cap_out) *cap_out = cap;
-    return (size_t)block_docs * 4 + (size_t)((block_docs + 31) / 32) * 4 + 16 +
+    return (size_t)block_docs * 4 + (size_t)(block_docs / 32) * 4 + (size_t)SP_STAGE * 8 + 16 +
            BlockTopK<SP_THREADS, uint32_t>::smem_bytes(cap) + 64;
+}
+
+static int sparse_slices(int64_t n_blocks, int n_queries) {
+    // enough (query, slice) work items to keep two to three CTAs per SM busy and to even out the queries' very different
+    // posting counts, but at least four blocks per slice (every slice pays its own top-k warm-up)
+    int sm_count = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    int64_t s = (3 * (int64_t)sm_count + n_queries - 1) / n_queries;
+    if (s > n_blocks / 4) s = n_blocks / 4;
+    const int forced = option(OPT_SPARSE_SLICES, 0);
+    if (forced > 0) s = forced;
+    if (s > n_blocks) s = n_blocks;
+    if (s > SP_MAX_SLICES) s = SP_MAX_SLICES;
+    return s < 1 ? 1 : (int)s;
 }
 
 }  // namespace b200rag
@@ -405,29 +402,13 @@ using namespace b200rag;
 
 extern "C" {
 
-int b200rag_debug_sparse_stats(int32_t enable, uint64_t* out_host, int32_t max_ctas) {
-    const size_t bytes = (size_t)SP_STAT_CTAS * SP_NSTAT * sizeof(unsigned long long);
-    if (out_host && g_sparse_stats) {
-        B200_CUDA_CHECK(cudaDeviceSynchronize());
-        const int n = max_ctas < SP_STAT_CTAS ? max_ctas : SP_STAT_CTAS;
-        B200_CUDA_CHECK(cudaMemcpy(out_host, g_sparse_stats, (size_t)n * SP_NSTAT * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    }
-    if (enable && !g_sparse_stats) {
-        B200_CUDA_CHECK(cudaMalloc(&g_sparse_stats, bytes));
-        B200_CUDA_CHECK(cudaMemset(g_sparse_stats, 0, bytes));
-    } else if (!enable && g_sparse_stats) {
-        B200_CUDA_CHECK(cudaFree(g_sparse_stats));
-        g_sparse_stats = nullptr;
-    }
-    return B200RAG_OK;
-}
-
 size_t b200rag_sparse_topk_workspace_bytes(int64_t n_docs, int32_t block_docs, int32_t n_queries, int32_t k) {
-    if (block_docs <= 0) return 0;
+    if (block_docs <= 0 || n_queries <= 0 || k <= 0) return 0;
     int64_t n_blocks = (n_docs + block_docs - 1) / block_docs;
     if (n_blocks < 1) n_blocks = 1;
-    return align_up((size_t)n_queries * n_blocks * k * sizeof(double), 256) +
-           align_up((size_t)n_queries * n_blocks * k * sizeof(int64_t), 256) + 512;
+    const int64_t s = n_blocks < SP_MAX_SLICES ? n_blocks : SP_MAX_SLICES;
+    return align_up((size_t)n_queries * s * k * sizeof(double), 256) + align_up((size_t)n_queries * s * k * sizeof(int64_t), 256) +
+           align_up((size_t)n_queries * 4, 256) + 512;
 }
 
 int b200rag_sparse_topk(const int64_t* blk_term_ptr, const uint16_t* post_doc, const float* post_w,
@@ -449,12 +430,12 @@ int b200rag_sparse_topk_masked(const int64_t* blk_term_ptr, const uint16_t* post
                                void* workspace, size_t workspace_bytes, void* stream) {
     B200_REQUIRE(blk_term_ptr && q_ptr && out_scores && out_ids && out_counts && workspace, "sparse_topk: null pointer");
     B200_REQUIRE(n_docs >= 0 && n_terms > 0 && n_queries >= 0 && k > 0, "sparse_topk: bad sizes");
-    B200_REQUIRE(block_docs > 0 && block_docs <= 64 * SP_THREADS && block_docs % 32 == 0,
-                 "sparse_topk: block_docs must be a multiple of 32 in (0, %d], got %d", 64 * SP_THREADS, block_docs);
+    B200_REQUIRE(block_docs > 0 && block_docs <= 32768 && block_docs % 32 == 0,
+                 "sparse_topk: block_docs must be a multiple of 32 in (0, 32768], got %d", block_docs);
     if (n_queries == 0) return B200RAG_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int cap = 0;
-    size_t smem = sparse_smem(block_docs, k, &cap);
+    SparseParams p;
+    size_t smem = sparse_smem(block_docs, k, &p.cap);
     if (smem > 225 * 1024) {
         set_error("sparse_topk: block_docs=%d with k=%d needs %zu bytes of shared memory (max 230400); use a smaller block",
                   block_docs, k, smem);
@@ -463,33 +444,43 @@ int b200rag_sparse_topk_masked(const int64_t* blk_term_ptr, const uint16_t* post
     int64_t n_blocks = (n_docs + block_docs - 1) / block_docs;
     if (n_blocks < 1) n_blocks = 1;
     B200_REQUIRE(n_queries <= 2147483647 && n_blocks <= 2147483647, "sparse_topk: too many blocks");
+    const int n_slices = sparse_slices(n_blocks, n_queries);
     Workspace ws(workspace, workspace_bytes);
-    double* part_scores = ws.take<double>((size_t)n_queries * n_blocks * k);
-    int64_t* part_ids = ws.take<int64_t>((size_t)n_queries * n_blocks * k);
+    p.part_scores = ws.take<double>((size_t)n_queries * n_slices * k);
+    p.part_ids = ws.take<int64_t>((size_t)n_queries * n_slices * k);
+    p.gthr = ws.take<unsigned int>((size_t)n_queries);
     if (!ws.ok()) {
         set_error("sparse_topk: workspace too small (%zu < %zu)", workspace_bytes, ws.off);
         return B200RAG_E_WORKSPACE;
     }
+    if (n_slices > 1) B200_CUDA_CHECK(cudaMemsetAsync(p.gthr, 0, (size_t)n_queries * 4, st));
+    else p.gthr = nullptr;
+    p.blk_term_ptr = blk_term_ptr;
+    p.post_doc = post_doc;
+    p.post_w = post_w;
+    p.n_docs = n_docs;
+    p.n_terms = n_terms;
+    p.block_docs = block_docs;
+    p.n_blocks = (int)n_blocks;
+    p.n_slices = n_slices;
+    p.q_ptr = q_ptr;
+    p.q_terms = q_terms;
+    p.q_vals = q_vals;
+    p.k = k;
+    p.id_offset = id_offset;
+    p.out_scores = out_scores;
+    p.out_ids = out_ids;
+    p.out_counts = out_counts;
+    p.doc_mask = doc_mask;
+    p.flags = option(OPT_SPARSE_FLAGS, 0);
+    p.stats = stats_buffer(STATS_SPARSE, (size_t)SP_STAT_CTAS * SP_NSTAT);
+    if (p.stats) B200_CUDA_CHECK(cudaMemsetAsync(p.stats, 0, (size_t)SP_STAT_CTAS * SP_NSTAT * 8, st));
     B200_CUDA_CHECK(cudaFuncSetAttribute(sparse_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // one CTA per query; with fewer queries than ~2 per SM the blocks are cut into slices to fill the machine
-    int sm_count = 148, dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    int64_t n_slices = (2 * (int64_t)sm_count) / n_queries;
-    if (n_slices < 1) n_slices = 1;
-    // A/B switches (tools/sparse_ab.py): slices per query, and the dense collect mode
-    if (const char* e = getenv("B200RAG_SPARSE_SLICES")) { if (atoi(e) > 0) n_slices = atoi(e); }
-    // bit 0: dense collect mode, bit 1: bulk append
-    const char* ed = getenv("B200RAG_SPARSE_DENSE");
-    const int flags = ed ? atoi(ed) : 3;
-    if (n_slices > n_blocks) n_slices = n_blocks;
-    B200_REQUIRE(n_slices <= 65535, "sparse_topk: too many slices");
     dim3 grid((unsigned)n_queries, (unsigned)n_slices);
-    sparse_query_kernel<<<grid, SP_THREADS, smem, st>>>(blk_term_ptr, post_doc, post_w, n_docs, n_terms, block_docs,
-                                                       (int)n_blocks, (int)n_slices, q_ptr, q_terms, q_vals, k, cap, id_offset,
-                                                       part_scores, part_ids, doc_mask, flags, g_sparse_stats); count_launch();
+    sparse_query_kernel<<<grid, SP_THREADS, smem, st>>>(p); count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
-    return launch_merge(part_scores, part_ids, n_queries, nullptr, (int)(n_slices * k), k, nullptr, out_scores, out_ids,
-                        out_counts, st);
+    if (n_slices == 1) return B200RAG_OK;
+    return launch_merge(p.part_scores, p.part_ids, n_queries, nullptr, n_slices * k, k, nullptr, out_scores, out_ids, out_counts, st);
 }
 
 }  // extern "C"

@@ -8,16 +8,22 @@
 A "step" is one batch of 1024 queries through the exact cosine top-100 search over a 10M x 768 fp16 corpus
 (BASELINE config 3; it fits one B200).  With N GPUs the SAME 10M rows are sharded row-wise (strong scaling): each
 rank scans its shard, one NCCL all-gather carries the k candidates per query, the merge kernel reduces them.
+Every number goes through the reference-facing plugin object -- B200IndexManager (N = 1) / its row-sharded subclass
+(N > 1), the drop-in for MilvusIndexManager (reference src/advanced_rag/indexing.py:445-551):
 
-  value     whole-job queries/s with the query batch already resident in HBM (fp32), search = prepare + scan + finish
-            (+ all-gather + merge for N>1), timed with CUDA events, max over ranks.
-  e2e       same metric through the public Python API with HOST buffers: pinned fp32 queries -> H2D -> search ->
-            D2H of ids + scores, every step, consumed by a double-buffered host loop (results of step i are on the host
-            before step i+2 is issued).
-  roofline  the dominant kernel (dense_scan3_kernel, the full scan): algorithmic FLOPs per launch / its CUDA-event duration, measured
-            live inside the timed region through the b200rag_profile_next_scan hook.
+  value     whole-job queries/s with the query batch already resident in HBM (fp32): manager.search_batch_ids = prepare +
+            scan + finish (+ all-gather + merge for N>1), results stay on the device; CUDA events, max over ranks.
+  e2e       the same metric through manager.search_batch_arrays with HOST buffers: pinned fp32 queries -> H2D -> search ->
+            D2H of ids + scores + counts into numpy arrays the caller holds when the call returns, every step, one
+            synchronous call per step (no overlap between steps).
+  roofline  the dominant kernel (dense_scan3_kernel, the full scan): algorithmic FLOPs per launch / its CUDA-event duration,
+            measured live inside the timed region through the b200rag_profile_next_scan hook.
   cpu_baseline / --impl reference: the same exact search on the box's host cores (numpy BLAS sgemm + partial sort,
-            "Milvus mocked" -- see oracle/oracle.py) on a bounded row sample, extrapolated linearly in rows.
+            "Milvus mocked" -- see oracle/oracle.py) with every host thread, on a bounded row sample per step; `steps` and
+            `ms_per_step` are what was really run and measured, `value` extrapolates linearly in rows to the 10M-row workload.
+  extras    batch-1 latency, result-dict materialisation cost, in-run exactness checks (merged result for N>1), and the
+            other BASELINE configurations (bench_extras.py): c1 with the reference chain on the host cores, c2, c4 stage
+            table, c5 shard, near-duplicate corpus.
 """
 from __future__ import annotations
 
@@ -25,7 +31,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -53,6 +58,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--extras", default="c1,c2,c4,c5,dups", help="comma list of secondary configurations to run (N = 1)")
     return ap.parse_args()
 
 
@@ -126,11 +132,31 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- reference / CPU arm
-def cpu_dense_qps(rows_total: int, dim: int, batch: int, k: int, sample_rows: int, steps: int, warmup: int, seed: int):
+def use_all_host_threads() -> int:
+    """BLAS / OpenMP on every host core, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers).  Must run
+    before numpy is imported for the environment part; threadpoolctl raises the limit of pools that are already loaded."""
+    cores = os.cpu_count() or 1
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(cores)
+    return cores
+
+
+def blas_threads() -> int:
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+        info = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") in ("blas", "openmp")]
+        return max(info) if info else 1
+    except Exception:                               # noqa: BLE001
+        return int(os.environ.get("OMP_NUM_THREADS", "1"))
+
+
+def cpu_dense_sample(rows_total: int, dim: int, batch: int, k: int, sample_rows: int, steps: int, warmup: int, seed: int):
     """The exact cosine top-k on the host cores: numpy BLAS sgemm + argpartition over a row sample (fp32, what a CPU
-    deployment of the mocked-Milvus path runs), extrapolated linearly to rows_total."""
+    deployment of the mocked-Milvus path runs).  Returns (seconds per sample step, sample rows, threads used)."""
     import numpy as np
     from oracle import oracle
+    threads = blas_threads()
     rng = np.random.default_rng(seed)
     sample_rows = min(sample_rows, rows_total)
     x = rng.standard_normal((sample_rows, dim), dtype=np.float32)
@@ -143,37 +169,54 @@ def cpu_dense_qps(rows_total: int, dim: int, batch: int, k: int, sample_rows: in
         oracle.dense_topk_blas(x, q, k)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    t = sum(times) / len(times)
-    qps = batch / (t * rows_total / sample_rows)
-    return qps, t, sample_rows
+    return sum(times) / len(times), sample_rows, threads
+
+
+def cpu_baseline_block(args, steps: int, warmup: int):
+    t, srows, threads = cpu_dense_sample(args.rows, args.dim, args.batch, args.k, args.cpu_sample_rows, steps, warmup, args.seed)
+    qps = args.batch / (t * args.rows / srows)
+    return {"value": qps, "unit": "queries/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
+            "sample": f"numpy BLAS sgemm + argpartition on {threads} threads: {steps} timed steps of {args.batch} queries x "
+                      f"{srows} of the {args.rows} rows ({t * 1e3:.0f} ms measured per step), QPS extrapolated linearly in rows",
+            "sample_ms_per_step": t * 1e3, "sample_rows": srows}, t, srows
 
 
 def run_reference(args):
+    """--impl reference: the CPU implementation of the path on this box's host cores.  Rank 0 only; the line reports what was
+    actually run (`steps` timed steps of `ms_per_step` each, over a row sample) and extrapolates only `value`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 5))
-    qps, t, srows = cpu_dense_qps(args.rows, args.dim, args.batch, args.k, args.cpu_sample_rows, steps, min(args.warmup, 1), args.seed)
-    sample = (f"numpy BLAS sgemm + argpartition, {args.batch} queries x {srows} of {args.rows} rows per step "
-              f"({t:.2f} s/step), QPS extrapolated linearly in rows")
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 2))
+    cb, t, srows = cpu_baseline_block(args, steps, warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3 * args.rows / srows, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "queries/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.rows}x{args.dim} exact cosine top-{args.k}, query batch {args.batch}, host CPU"},
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": f"{args.rows}x{args.dim} exact cosine top-{args.k}, query batch {args.batch}, host CPU; each timed step "
+                               f"scans a {srows}-row sample ({srows / args.rows:.3f} of the workload) and `value` = batch / "
+                               f"(ms_per_step * rows / sample_rows)",
+                   "sample_rows": srows, "rows": args.rows},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------- B200 arm
-def build_shard(engine, dist_mod, args, device, rank, world):
+def build_manager(args, device, rank, world):
+    """The 10M x 768 corpus behind the plugin object: payload-less bulk rows (ids read f"c{row:09d}")."""
     import torch
-    start, end = dist_mod.shard_range(args.rows, rank, world)
-    idx = engine.DenseIndex(args.dim, "f16", "COSINE", device, id_offset=start, capacity=end - start)
+    from b200rag import distributed as bdist
+    from b200rag.index_manager import B200IndexManager
+    kw = dict(semantic_dim=args.dim, sparse_dim=8, domain_dim=8, device=device, dtype="f16", enable_sparse=False)
+    if world > 1:
+        mgr = bdist.ShardedIndexManager(args.rows, **kw)
+        start, end = mgr.start, mgr.end
+    else:
+        mgr = B200IndexManager(**kw)
+        start, end = 0, args.rows
     g = torch.Generator(device=device)
     row = start
     while row < end:
@@ -183,17 +226,19 @@ def build_shard(engine, dist_mod, args, device, rank, world):
         g.manual_seed(args.seed * 1_000_003 + blk)
         x = torch.randn((b1 - b0, args.dim), generator=g, device=device, dtype=torch.float32)
         lo, hi = max(row, b0) - b0, min(end, b1) - b0
-        idx.add(x[lo:hi])
+        mgr.add_vectors(x[lo:hi])
         row = b0 + hi
-    return idx
+    return mgr
 
 
 def main():
     args = parse_args()
     if args.impl == "reference":
+        use_all_host_threads()
         run_reference(args)
         return
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     from b200rag import _lib, distributed as bdist, engine
@@ -209,22 +254,14 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load()
     B, K, D = args.batch, args.k, args.dim
+    COL = "semantic_index"
 
-    idx = build_shard(engine, bdist, args, device, rank, world)
-    n_local = idx.n
+    mgr = build_manager(args, device, rank, world)
+    n_local = mgr._sem.n
     g = torch.Generator(device=device).manual_seed(args.seed + 1000)
     POOL = 8
     q_dev = [torch.randn((B, D), generator=g, device=device, dtype=torch.float32) for _ in range(POOL)]
     q_host = [q.cpu().pin_memory() for q in q_dev]
-
-    # N > 1: pack -> ONE NCCL all-gather -> merge kernel, on the compute stream.  (Running the exchange of batch b on a side
-    # stream next to the scan of batch b+1 was measured and is slower: the persistent scan wants every SM pair at launch and
-    # the NCCL / merge CTAs delay some of its clusters -- scan 1.45 -> 1.98 ms at 8 GPUs.)
-    def search(q):
-        s, i, f = idx.search(q, K, engine.DENSE_AUTO)
-        if world > 1:
-            s, i = bdist.gather_and_merge(s, i, K, engine.merge_topk, None, engine.merge_gathered)
-        return s, i, f
 
     def barrier():
         if world > 1:
@@ -241,11 +278,11 @@ def main():
     sampler = ClockSampler(local_rank)
     flags_total = torch.zeros((), dtype=torch.int64, device=device)
     for it in range(args.warmup):
-        s, i, f = search(q_dev[it % POOL])
-        flags_total += f.sum()        # also warms torch's own reduce/add kernels (first use costs ~100 ms of module load)
+        s, i, c = mgr.search_batch_ids(q_dev[it % POOL], COL, K)
+        flags_total += mgr._sem.last_flags.sum()   # also warms torch's own reduce/add kernels (first use costs ~100 ms of module load)
     barrier()
 
-    # ---------------- timed region 1: device-resident inputs -------------------------------------
+    # ---------------- timed region 1: device-resident inputs, results stay on the device ---------
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -258,8 +295,8 @@ def main():
     ev0.record()
     for it in range(args.steps):
         lib.b200rag_profile_next_scan(scan_ev[it][0].cuda_event, scan_ev[it][1].cuda_event)
-        s, i, f = search(q_dev[(args.warmup + it) % POOL])
-        flags_total += f.sum()
+        s, i, c = mgr.search_batch_ids(q_dev[(args.warmup + it) % POOL], COL, K)
+        flags_total += mgr._sem.last_flags.sum()
     ev1.record()
     barrier()
     launches = int(lib.b200rag_kernel_launch_count()) - launches0
@@ -270,39 +307,27 @@ def main():
     ms_per_step = ms_total / args.steps
     value = B * args.steps / (ms_total * 1e-3)
 
-    # ---------------- timed region 2: end to end from host buffers -------------------------------
-    # Every step: pinned fp32 queries -> H2D -> search -> D2H of ids + scores into pinned host buffers.  The consumer is
-    # double buffered, as a serving loop would be: before issuing step i+1 the host WAITS until the results of step i-1
-    # are in host memory (so it holds every step's results at most one step late), and the region ends when the last
-    # step's results have landed.  Nothing is skipped; copies and compute of neighbouring steps may overlap.
-    out_ids_h = [torch.empty((B, K), dtype=torch.int64).pin_memory() for _ in range(2)]
-    out_sc_h = [torch.empty((B, K), dtype=torch.float64).pin_memory() for _ in range(2)]
-    done = [torch.cuda.Event(), torch.cuda.Event()]
+    # ---------------- timed region 2: end to end through the columnar plugin call ----------------
+    # Every step: pinned fp32 host queries -> manager.search_batch_arrays -> numpy rows / scores / counts on the host.  The
+    # call is synchronous (the caller holds the step's results when it returns), so H2D, search and D2H of one step do not
+    # overlap with the next; nothing is skipped or cached.
     for it in range(min(args.warmup, 2)):
-        search(q_host[it % POOL].to(device, non_blocking=True))
+        mgr.search_batch_arrays(q_host[it % POOL], COL, K)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     checksum = 0
+    t_wall0 = time.perf_counter()
+    e0.record()
     for it in range(args.steps):
-        qd = q_host[(args.warmup + it) % POOL].to(device, non_blocking=True)
-        s, i, _ = search(qd)
-        if it >= 2:
-            done[it % 2].synchronize()                    # results of step it-2 left this buffer pair long ago; it-1 may still fly
-        out_ids_h[it % 2].copy_(i, non_blocking=True)
-        out_sc_h[it % 2].copy_(s, non_blocking=True)
-        done[it % 2].record()
-        if it >= 1:
-            done[(it - 1) % 2].synchronize()              # the caller now holds step it-1's results on the host
-            checksum += int(out_ids_h[(it - 1) % 2][0, 0])
-    done[(args.steps - 1) % 2].synchronize()
-    checksum += int(out_ids_h[(args.steps - 1) % 2][0, 0])
+        arr = mgr.search_batch_arrays(q_host[(args.warmup + it) % POOL], COL, K)
+        checksum += int(arr.rows[0, 0]) + int(arr.counts[-1])
     e1.record()
     barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
     e2e_value = B * args.steps / (e2e_ms * 1e-3)
 
-    # ---------------- extras: batch-1 latency ----------------------------------------------------
+    # ---------------- extras ------------------------------------------------------------------
     extras = {}
     if not args.no_extras:
         lat = []
@@ -310,8 +335,7 @@ def main():
         for j in range(60):
             barrier()
             t0 = time.perf_counter()
-            s, i, _ = search(q1[j].to(device, non_blocking=True))
-            i_h = i.cpu()
+            arr1 = mgr.search_batch_arrays(q1[j], COL, K)
             t1 = time.perf_counter()
             if j >= 10:
                 lat.append((t1 - t0) * 1e3)
@@ -320,18 +344,54 @@ def main():
             dist.all_reduce(lat_t, op=dist.ReduceOp.MAX)
         extras["batch1_p50_ms"] = float(lat_t.item())
         extras["batch1_hbm_floor_ms"] = n_local * D * 2 / (load_peaks()["hbm_gbs"] * 1e9) * 1e3
-        # in-run exactness check (outside every timed region): the tensor-core path against the CUDA-core exact scan
-        # (canonical fp64 arithmetic, itself bit-exact against the CPU oracle in tests/) on a query subset of this very index
+        # result-dict materialisation (reference indexing.py:534-551 shape) on top of the columnar call, top_k = 20 and K
+        for kk in (20, K):
+            ts = []
+            for j in range(4):
+                barrier()
+                t0 = time.perf_counter()
+                hits = mgr.search_batch(q_host[j % POOL], COL, kk)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            extras[f"dict_results_top{kk}"] = {"ms_per_batch": statistics.median(ts[1:]), "qps": B / statistics.median(ts[1:]) * 1e3,
+                                               "dicts_per_batch": sum(len(h) for h in hits)}
+        # in-run exactness check (outside every timed region): what the plugin call returns (tensor-core path, merged over
+        # the ranks for N > 1) against the CUDA-core exact scan (canonical fp64 arithmetic, itself bit-exact against the CPU
+        # oracle in tests/) pushed through the same gather + merge, on a query subset of this very index
         sub = torch.tensor([0, 1, 127, 128, 500, B - 1], device=device).clamp(max=B - 1).unique()
-        qs = q_dev[0][sub]
-        sa, ia, fa = idx.search(qs, K, engine.DENSE_AUTO)
-        sx, ix, _ = idx.search(qs, K, engine.DENSE_EXACT)
+        qs = q_dev[0][sub].contiguous()
+        sa, ia, _ = mgr.search_batch_ids(qs, COL, K)
+        fa = mgr._sem.last_flags
+        sx, ix, _ = mgr._sem.search(qs, K, engine.DENSE_EXACT)
+        if world > 1:
+            sx, ix = bdist.gather_and_merge(sx, ix, K, engine.merge_topk, None, engine.merge_gathered)
         ok = bool(torch.equal(ia, ix) and torch.equal(sa, sx))
         ok_t = torch.tensor([1 if ok else 0], device=device)
         if world > 1:
             dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
-        extras["exact_check"] = {"queries": int(sub.numel()), "ids_and_fp64_scores_equal_to_exact_scan": bool(ok_t.item()),
+        extras["exact_check"] = {"queries": int(sub.numel()), "what": "plugin result (merged over ranks) == exact fp64 scan -> same gather + merge",
+                                 "ids_and_fp64_scores_equal_to_exact_scan": bool(ok_t.item()),
                                  "recall_at_k": float((ia == ix).float().mean().item()), "flagged": int(fa.sum().item())}
+
+    # ---------------- secondary configurations (N = 1; they need the memory the headline index holds) ---
+    if not args.no_extras and world == 1:
+        import bench_extras as bx
+        del mgr
+        torch.cuda.empty_cache()
+        want = set(args.extras.split(","))
+        for key, name, fn in (("c1", "c1", lambda: bx.c1(device)),
+                              ("c2", "c2", lambda: bx.dense_config(device, 1_000_000, 768, 1024, 100, "IP")),
+                              ("c4", "c4", lambda: bx.c4(device)),
+                              ("c5", "c5_shard", lambda: bx.dense_config(device, 12_500_000, 384, 4096, 10, "COSINE", reps=5)),
+                              ("dups", "near_duplicates", lambda: bx.near_duplicates(device))):
+            if key not in want:
+                continue
+            try:
+                t0 = time.time()
+                extras[name] = fn()
+                extras[name]["wall_s"] = round(time.time() - t0, 1)
+            except Exception as e:                  # noqa: BLE001 - a secondary configuration must not take the headline down
+                extras[name] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
 
     if rank == 0:
         peaks = load_peaks()
@@ -349,17 +409,19 @@ def main():
                     traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        scan_kernel = "dense_scan_kernel" if os.environ.get("B200RAG_SCAN_VERSION", "") == "1" else "dense_scan3_kernel"
+        scan_kernel = "dense_scan_kernel" if lib.b200rag_get_option(b"scan_version") == 1 else "dense_scan3_kernel"
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"{args.rows}x{D} fp16 exact cosine top-{K}, query batch {B}, row-sharded over {world} GPU(s)",
+                       "api": "B200IndexManager.search_batch_ids (value) / .search_batch_arrays (e2e)" if world == 1 else
+                              "ShardedIndexManager.search_batch_ids (value) / .search_batch_arrays (e2e)",
                        "l2": f"inputs larger than L2 ({n_local * D * 2 / 1e9:.1f} GB per GPU streamed every step)",
                        "mode": "AUTO (tcgen05 scan + exact fp64 re-score, exact fallback for unproven queries)",
                        "flagged_queries_in_timed_region": int(flags_total.item())},
-            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * K * 16,
-                    "ms_per_step": e2e_ms / args.steps},
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * K * 16 + B * 4,
+                    "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall_ms / args.steps, "checksum": checksum},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"kernel": scan_kernel, "bound": "tensor", "achieved": achieved_tf,
@@ -372,12 +434,10 @@ def main():
         }
         if extras:
             line["extras"] = extras
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            qps, t, srows = cpu_dense_qps(args.rows, D, B, K, args.cpu_sample_rows, 5, 1, args.seed)     # ~12 s of host work
-            line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                                    "sample": f"numpy BLAS sgemm + argpartition, {B} queries x {srows} of {args.rows} rows "
-                                              f"({t:.2f} s per pass, 5 timed passes), extrapolated linearly in rows"}
+        if not args.no_cpu_baseline:
+            # ~10-15 s of host work at N = 1; a shorter sample under torchrun (the other ranks wait at the barrier below)
+            cb, _, _ = cpu_baseline_block(args, 5 if world == 1 else 2, 1)
+            line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define B200RAG_ABI_VERSION 1
+#define B200RAG_ABI_VERSION 2
 
 typedef enum { B200RAG_F16 = 0, B200RAG_BF16 = 1 } b200rag_dtype;
 
@@ -114,17 +114,53 @@ int b200rag_dense_topk_masked(const void* corpus16, int64_t n_rows, int32_t dim,
  * after its scan kernel on the call's stream, then clears the hook.  bench.py uses it to time the dominant kernel
  * inside the timed region without a profiler. */
 int b200rag_profile_next_scan(void* start_event, void* stop_event);
-/* Debug/profiling: enable per-CTA cycle counters in the tensor-core scan kernels (16 u64 slots per CTA: MMA total,
- * MMA wait-for-data, MMA wait-for-epilogue, MMA wait-for-queries, producer total, producer wait-for-slot, epilogue
- * total, epilogue wait-for-accumulator, epilogue compaction, epilogue query load, #compactions, #slow-path groups).
- * With out_host != NULL the counters of the last scan are copied to host memory (synchronous). */
-int b200rag_debug_scan_stats(int32_t enable, uint64_t* out_host, int32_t max_ctas);
+/* Debug/profiling: per-CTA cycle counters, written into a DEVICE buffer the caller owns (the library keeps no global
+ * state: the registration is per calling thread and holds until it is cleared with a NULL buffer).
+ *   kind 0 = tensor-core dense scan: 16 u64 slots per CTA, 256 CTAs (MMA total, MMA wait-for-data, MMA wait-for-epilogue,
+ *            MMA wait-for-queries, producer total, producer wait-for-slot, epilogue total, epilogue wait-for-accumulator,
+ *            epilogue compaction, epilogue query load, #compactions, #slow-path groups); needs n_slots >= 4096.
+ *   kind 1 = sparse scan: 12 u64 slots per CTA, first 1024 CTAs (see sparse_bm25.cu); needs n_slots >= 12288.
+ * A scan launched from this thread while a large-enough buffer is registered zeroes it and fills it. */
+int b200rag_debug_set_stats_buffer(int32_t kind, uint64_t* device_buf, size_t n_slots);
 
-/* Debug/profiling: per-CTA cycle counters of the sparse scan (12 u64 slots per CTA, first 1024 CTAs: init, compaction
- * after a bulk append, postings fetched + first term applied, remaining terms applied, accumulators scanned, bulk
- * append, finalize + output, #collects with candidates, candidate rounds, #compactions, #candidates appended in bulk,
- * unused).  Same protocol as b200rag_debug_scan_stats. */
-int b200rag_debug_sparse_stats(int32_t enable, uint64_t* out_host, int32_t max_ctas);
+/* A/B options for measurements (tools/scan_ab.py, tools/sparse_ab.py).  Process-wide integer knobs, set explicitly and read
+ * with atomic loads -- nothing is read from the environment.  value < 0 restores the built-in default.
+ *   "scan_version" 1|3, "qg_span", "epi" 0|1, "no_sample" 0|1, "stage_rows" 8|16|32, "sample_mult", "mmr_path" (0 auto, 1 general
+ *   kernel), "sparse_slices", "sparse_flags", "no_tier0" 0|1, "finish_version".
+ * b200rag_get_option returns the stored value (-1 = default in force, -2 = unknown name). */
+int b200rag_set_option(const char* name, int64_t value);
+int64_t b200rag_get_option(const char* name);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Metadata predicate -> row bit mask.  Replaces the server-side evaluation of `expr=filters` in Collection.search
+ * (reference indexing.py:505-523); expressions are the conjunctions HybridRetriever._build_filter_expression emits
+ * (reference retrieval.py:565-632) over the scalar fields of the collection schema (indexing.py:191-225).
+ *   terms    HOST array of n_terms (<= 16) parsed terms; `column` / `lut` are DEVICE pointers with one entry per row /
+ *            per dictionary code.  Missing values never match: NaN (f64), INT64_MIN (i64), code < 0 (dictionary).
+ *   and_mask optional u32 [ceil(n_rows/32)] ANDed into the result (e.g. the live-row mask after deletes); may be NULL
+ *   out_mask u32 [ceil(n_rows/32)], bit (row & 31) of word (row >> 5) = row satisfies every term
+ *   out_count optional DEVICE i64: number of set bits */
+typedef enum { B200RAG_OP_EQ = 0, B200RAG_OP_NE = 1, B200RAG_OP_GE = 2, B200RAG_OP_LE = 3, B200RAG_OP_GT = 4, B200RAG_OP_LT = 5 } b200rag_filter_op;
+typedef enum {
+    B200RAG_COL_F64 = 0,         /* double column compared with fvalue */
+    B200RAG_COL_I64 = 1,         /* int64 column compared with ivalue */
+    B200RAG_COL_I64_AS_F64 = 2,  /* int64 column compared with fvalue (non-integral literal) */
+    B200RAG_COL_CODE = 3,        /* int32 dictionary codes: row matches iff lut[code] != 0 (the host evaluated op on the dictionary);
+                                    lut == NULL: op must be == or != and is applied to (code, ivalue) */
+    B200RAG_COL_NEVER = 4        /* literal type does not fit the column: no row matches */
+} b200rag_filter_kind;
+typedef struct {
+    const void* column;
+    const uint8_t* lut;
+    double fvalue;
+    int64_t ivalue;
+    int32_t kind;
+    int32_t op;
+    int32_t lut_size;
+    int32_t reserved;
+} b200rag_filter_term;
+int b200rag_filter_mask(const b200rag_filter_term* terms, int32_t n_terms, int64_t n_rows, const uint32_t* and_mask,
+                        uint32_t* out_mask, int64_t* out_count, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Sparse inner-product top-k over doc-range-blocked postings (K3).  Replaces Collection.search on
@@ -162,9 +198,10 @@ int b200rag_merge_topk(const double* cand_scores, const int64_t* cand_ids, int32
                        int32_t k, double* out_scores, int64_t* out_ids,
                        void* workspace, size_t workspace_bytes, void* stream);
 
-/* Same reduce, reading the NCCL all-gather buffer in place: gathered i64 [n_ranks, n_queries, 2k] = per rank and query
- * k fp64 score bit patterns followed by k ids (id < 0 = empty slot).  Saves the unpack / transpose passes between the
- * collective and the merge (they cost more than the merge itself at 8 GPUs). */
+/* Same reduce, reading the NCCL all-gather buffer in place: gathered i64 [n_ranks, 2, n_queries, k] = per rank a plane of
+ * k fp64 score bit patterns per query followed by a plane of k ids per query (id < 0 = empty slot) -- i.e. the out_scores and
+ * out_ids arrays of b200rag_dense_topk, which a rank points straight at the two halves of its send buffer.  No pack, unpack
+ * or transpose pass between the search, the collective and the merge. */
 int b200rag_merge_gathered(const int64_t* gathered, int32_t n_ranks, int32_t n_queries, int32_t k,
                            double* out_scores, int64_t* out_ids, void* stream);
 

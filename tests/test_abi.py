@@ -28,7 +28,39 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(lib, s), f"{s} declared in include/b200rag.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == syms
-    assert lib.b200rag_abi_version() == 1
+    assert lib.b200rag_abi_version() == 2
+
+
+def test_options_are_explicit_and_reentrant_from_two_threads():
+    """reentrant, no global mutable state read from the environment.  A/B knobs are set through
+    b200rag_set_option (atomics), the last-error string and the debug buffers are per thread; argument validation can run
+    from two threads at once without interfering."""
+    import threading
+    from b200rag import _lib
+    lib = _lib.load()
+    assert lib.b200rag_get_option(b"sparse_slices") == -1 and lib.b200rag_get_option(b"no_such_option") == -2
+    _lib.set_option("sparse_slices", 4)
+    assert lib.b200rag_get_option(b"sparse_slices") == 4
+    _lib.set_option("sparse_slices", -1)
+    assert lib.b200rag_get_option(b"sparse_slices") == -1
+    assert lib.b200rag_set_option(b"bogus", 1) == _lib.E_INVALID
+    errors = {}
+
+    def worker(tag, bad_dim):
+        for _ in range(200):
+            rc = lib.b200rag_prepare_rows(None, None, 4, bad_dim, 0, 0, None)
+            msg = lib.b200rag_last_error().decode()
+            if rc != _lib.E_INVALID or f"dim={bad_dim}" not in msg:
+                errors[tag] = (rc, msg)
+                return
+            assert lib.b200rag_debug_set_stats_buffer(1, None, 0) == 0
+
+    ts = [threading.Thread(target=worker, args=("a", -3)), threading.Thread(target=worker, args=("b", 9000))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
 
 
 def test_fails_loudly_without_gpu_or_with_bad_arguments():

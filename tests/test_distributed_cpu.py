@@ -43,6 +43,24 @@ def _worker(rank: int, world: int, port: int, n: int, d: int, b: int, k: int, ou
         ms, mi = bdist.gather_and_merge(torch.from_numpy(s), torch.from_numpy(i), k, merge)
         np.save(os.path.join(out_dir, f"s{rank}.npy"), ms.numpy())
         np.save(os.path.join(out_dir, f"i{rank}.npy"), mi.numpy())
+        # ---- sparse: document-range shards (cut at postings-block boundaries) with GLOBAL idf / avgdl, same exchange
+        from b200rag import bm25, synth
+        vocab, nq, ks, align = 300, 7, 15, 64
+        dp, ti, tf = synth.zipf_corpus(n, vocab, 3, mean_len=12)
+        qp, qt, qv = synth.zipf_queries(nq, vocab, 4, n_terms=5, skip_top=5)
+        a, e = bdist.shard_range(n, rank, world, align=align)
+        assert a % align == 0 and (e % align == 0 or e == n)
+        lp, lt, lf = dp[a: e + 1] - dp[a], ti[dp[a]: dp[e]], tf[dp[a]: dp[e]]
+        stats = bdist.bm25_global_stats(lp, lt, lf, vocab)
+        assert stats[0] == n and int(stats[2]) == int(tf.sum())
+        w = bm25.bm25_weights(lp, lt, lf, vocab, stats=stats)
+        tp, pd, pw = synth.doc_major_to_term_major(lp, lt, w, vocab)
+        ss, si, sc = oracle.sparse_topk(tp, pd, pw, e - a, qp, qt, qv, ks, id_offset=a)
+        si = np.where(np.arange(ks)[None, :] < sc[:, None], si, -1)
+        ms, mi = bdist.gather_and_merge(torch.from_numpy(ss.astype(np.float64)), torch.from_numpy(si), ks, merge)
+        np.save(os.path.join(out_dir, f"ss{rank}.npy"), ms.numpy())
+        np.save(os.path.join(out_dir, f"si{rank}.npy"), mi.numpy())
+        np.save(os.path.join(out_dir, f"w{rank}.npy"), w)
     finally:
         dist.destroy_process_group()
 
@@ -58,6 +76,17 @@ def test_shard_range_covers_rows_exactly_once():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_aligned_shard_ranges_cut_at_block_boundaries():
+    from b200rag.distributed import shard_range
+    for n in (1, 16383, 16384, 100_000, 1_000_000, 100_000_000):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w, align=16384) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[r][1] == spans[r + 1][0] for r in range(w - 1))
+            assert all(s % 16384 == 0 or s == n for s, _ in spans)
+            assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 2 * 16384
+
+
 def test_pack_unpack_round_trip():
     from b200rag.distributed import pack_candidates, unpack_gathered
     rng = np.random.default_rng(1)
@@ -65,6 +94,7 @@ def test_pack_unpack_round_trip():
     sc = torch.from_numpy(rng.standard_normal((g, b, k)))
     ids = torch.from_numpy(rng.integers(0, 1000, (g, b, k)))
     msg = torch.stack([pack_candidates(sc[r], ids[r]) for r in range(g)])
+    assert msg.shape == (g, 2, b, k)                          # per rank: a plane of score bits, a plane of ids
     s2, i2 = unpack_gathered(msg, k)
     assert s2.shape == (b, g * k)
     for r in range(g):
@@ -86,3 +116,17 @@ def test_two_rank_gather_and_merge_equals_single_shard(tmp_path, oracle_lib, wor
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"i{r}.npy"), ref_i), f"rank {r} ids differ from the single-shard search"
         assert np.array_equal(np.load(tmp_path / f"s{r}.npy"), ref_s), f"rank {r} scores differ"
+    # sparse: sharded postings with all-reduced df / avgdl == the single-shard index, weights and results bit for bit
+    from b200rag import bm25, synth
+    vocab, nq, ks = 300, 7, 15
+    dp, ti, tf = synth.zipf_corpus(n, vocab, 3, mean_len=12)
+    qp, qt, qv = synth.zipf_queries(nq, vocab, 4, n_terms=5, skip_top=5)
+    w = bm25.bm25_weights(dp, ti, tf, vocab)
+    assert np.array_equal(np.concatenate([np.load(tmp_path / f"w{r}.npy") for r in range(world)]).view(np.uint32), w.view(np.uint32))
+    tp, pd, pw = synth.doc_major_to_term_major(dp, ti, w, vocab)
+    rs, ri, rc = o.sparse_topk(tp, pd, pw, n, qp, qt, qv, ks)
+    ri = np.where(np.arange(ks)[None, :] < rc[:, None], ri, -1)
+    for r in range(world):
+        got_i, got_s = np.load(tmp_path / f"si{r}.npy"), np.load(tmp_path / f"ss{r}.npy")
+        assert np.array_equal(got_i, ri), f"rank {r} sparse ids differ from the single-shard search"
+        assert np.array_equal(got_s[ri >= 0].astype(np.float32).view(np.uint32), rs[ri >= 0].view(np.uint32))

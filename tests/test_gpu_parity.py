@@ -155,12 +155,13 @@ def test_sparse_long_walk_both_collect_modes(eng, oracle_lib, signed):
         assert list(s[q, : c[q]]) == [rs[q, j] for j in keep], q
 
 
-def test_sparse_full_size_collect_paths_agree(eng, monkeypatch):
+def test_sparse_full_size_collect_paths_agree(eng):
     """BASELINE config 4's sparse side at full size (1M documents, 100K-term Zipf vocabulary, 256 queries of 8 terms, top-500;
-    too large for the CPU oracle inside a test): the kernel's collect paths -- touched-bitmap walk with one candidate per
-    thread and round (B200RAG_SPARSE_DENSE=0, the form the oracle-checked small tests pin), dense threshold scan, bulk
-    append, and both -- must return bit-identical lists; the lists are sorted by (score desc, id asc); and the scores
-    agree with an fp64 recomputation from the CSR."""
+    too large for the CPU oracle inside a test): the kernel's collect paths (exchange collect vs touched-bitmap walk only)
+    and slicings (1, 2, 5 slices per query) must return bit-identical lists; the lists are sorted by (score desc, id asc);
+    and the scores agree with an fp64 recomputation from the CSR.  (The oracle itself checks the same walk at 16384-document
+    blocks x 9 blocks in test_sparse_16384_blocks_long_walk_matches_oracle.)"""
+    from b200rag import _lib
     from b200rag import bm25, synth
     n_docs, vocab, n_q, k = 1_000_000, 100_000, 256, 500
     doc_ptr, term_ids, tf = synth.zipf_corpus_device(n_docs, vocab, 0, DEV)
@@ -169,12 +170,16 @@ def test_sparse_full_size_collect_paths_agree(eng, monkeypatch):
     qp, qt, qv = synth.zipf_queries(n_q, vocab, 100, n_terms=8, skip_top=100)
     qv = (qv * np.random.default_rng(1).uniform(0.5, 2.0, qv.size)).astype(np.float32)
     got = {}
-    for flags in ("0", "1", "2", "3"):
-        monkeypatch.setenv("B200RAG_SPARSE_DENSE", flags)
-        s, i, c = idx.search(qp, qt, qv, k)
-        torch.cuda.synchronize()
-        got[flags] = (s.cpu().numpy(), i.cpu().numpy(), c.cpu().numpy())
-    monkeypatch.delenv("B200RAG_SPARSE_DENSE")
+    try:
+        for flags in ("0", "1", "2", "3"):
+            _lib.set_option("sparse_flags", 1 if flags == "1" else 0)
+            _lib.set_option("sparse_slices", {"0": -1, "1": -1, "2": 1, "3": 5}[flags])
+            s, i, c = idx.search(qp, qt, qv, k)
+            torch.cuda.synchronize()
+            got[flags] = (s.cpu().numpy(), i.cpu().numpy(), c.cpu().numpy())
+    finally:
+        _lib.set_option("sparse_flags", -1)
+        _lib.set_option("sparse_slices", -1)
     s0, i0, c0 = got["0"]
     for flags in ("1", "2", "3"):
         s, i, c = got[flags]
@@ -193,6 +198,39 @@ def test_sparse_full_size_collect_paths_agree(eng, monkeypatch):
         ref_s, _ = torch.topk(full, k)
         assert np.allclose(full[torch.from_numpy(i0[q]).to(DEV)].cpu().numpy(), s0[q], rtol=1e-5)
         assert np.allclose(ref_s.cpu().numpy(), s0[q], rtol=1e-5)
+
+
+@pytest.mark.parametrize("slices,k", [(1, 40), (-1, 40), (3, 500)])
+def test_sparse_16384_blocks_long_walk_matches_oracle(eng, oracle_lib, slices, k):
+    """The production block size: 16384-document blocks x 10 blocks, walked by one CTA per query (slices = 1), by the
+    library's own slicing and by three slices that share thresholds; top-40 (config 1) and top-500 (config 4) -- bit exact
+    against the oracle, with and without a document filter."""
+    from b200rag import _lib, synth
+    o = oracle_lib
+    n_docs, vocab, n_q = 150_000, 20_000, 96
+    dp, ti, w, qp, qt, qv = _sparse_case(n_docs, vocab, n_q, seed=31, mean_len=100, skip_top=50)
+    qv = (qv * np.random.default_rng(2).uniform(0.5, 2.0, qv.size)).astype(np.float32)
+    tp, pd, pw = synth.doc_major_to_term_major(dp, ti, w, vocab)
+    ref_s, ref_i, ref_c = o.sparse_topk(tp, pd, pw, n_docs, qp, qt, qv, k)
+    idx = eng.SparseIndex(dp, ti, w, vocab, DEV, block_docs=16384)
+    assert idx.n_blocks == 10
+    _lib.set_option("sparse_slices", slices)
+    try:
+        s, i, c = idx.search(qp, qt, qv, k)
+        allowed = np.random.default_rng(3).random(n_docs) < 0.5
+        sm, im, cm = idx.search(qp, qt, qv, k, doc_mask=eng.pack_row_mask(torch.from_numpy(allowed).to(DEV)))
+    finally:
+        _lib.set_option("sparse_slices", -1)
+    assert np.array_equal(c.cpu().numpy(), ref_c)
+    assert np.array_equal(i.cpu().numpy(), ref_i)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), ref_s.view(np.uint32))
+    rs, ri, rc = o.sparse_topk(tp, pd, pw, n_docs, qp[:9], qt, qv, n_docs)
+    sm, im, cm = sm.cpu().numpy(), im.cpu().numpy(), cm.cpu().numpy()
+    for q in range(8):
+        keep = [j for j in range(rc[q]) if allowed[ri[q, j]]][:k]
+        assert cm[q] == len(keep), q
+        assert list(im[q, : cm[q]]) == [int(ri[q, j]) for j in keep], q
+        assert list(sm[q, : cm[q]]) == [rs[q, j] for j in keep], q
 
 
 @pytest.mark.parametrize("block", [1024, 16384])
@@ -347,14 +385,14 @@ def test_mmr_batch_matches_oracle_random(eng):
 
 
 @pytest.mark.parametrize("force_warp_kernel", [False, True])
-def test_mmr_config4_scale_matches_oracle(eng, monkeypatch, force_warp_kernel):
+def test_mmr_config4_scale_matches_oracle(eng, force_warp_kernel):
     """BASELINE config-4 shape for the diversification: ~1000 candidates with ~90 unique tokens each out of a 100K-term
     Zipf vocabulary (token ids beyond 65535 exercise the 16-bit token cache), lambda 0.7, k = 100.  Both MMR kernels
     (thread-per-candidate fast path, warp-per-candidate general path) against the oracle restatement of the reference."""
     from b200rag import synth
+    from b200rag import _lib
     from oracle import fusion
-    if force_warp_kernel:
-        monkeypatch.setenv("B200RAG_MMR_WARP", "1")
+    _lib.set_option("mmr_path", 1 if force_warp_kernel else -1)
     vocab, n_docs, b, n_max, k = 100_000, 4000, 3, 1000, 100
     dp, ti, _ = synth.zipf_corpus(n_docs, vocab, 3)
     rng = np.random.default_rng(17)
@@ -363,8 +401,11 @@ def test_mmr_config4_scale_matches_oracle(eng, monkeypatch, force_warp_kernel):
     rel = np.sort(rng.random((b, n_max)) * 0.016, axis=1)[:, ::-1].copy()
     rel[1, 5] = rel[1, 4]                                   # an exact relevance tie: the earlier candidate must win
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
-    picks, pn = eng.mmr_select(t(cand), t(rel), t(n), t(dp), t(ti.astype(np.int32)), vocab,
-                               t(np.asarray([0.7, 0.5, 0.8])), t(np.asarray([k, k, 37], np.int32)), k)
+    try:
+        picks, pn = eng.mmr_select(t(cand), t(rel), t(n), t(dp), t(ti.astype(np.int32)), vocab,
+                                   t(np.asarray([0.7, 0.5, 0.8])), t(np.asarray([k, k, 37], np.int32)), k)
+    finally:
+        _lib.set_option("mmr_path", -1)
     assert int(ti.max()) > 65535
     for q in range(b):
         sets = [frozenset(ti[dp[d]: dp[d + 1]].tolist()) for d in cand[q, : n[q]]]

@@ -79,15 +79,22 @@ def test_filter_expressions_match_reference(golden):
     assert n_err >= 4
 
 
+def _store(n=50):
+    from b200rag.index_manager import PayloadStore
+    store = PayloadStore()
+    meta = [{"doc_id": 'doc"123' if i % 2 else "a\\b", "chunk_index": i % 4, "entropy": i / 50.0,
+             "redundancy": 0.2 if i % 5 == 0 else 0.3, "domain_density": 0.5 if i < 10 else 0.25,
+             "timestamp": f"2024-0{1 + i % 9}-01", "token_count": 100 + 10 * i} for i in range(n)]
+    store.commit([f"c{i}" for i in range(n)], ["x"] * n, store.convert(n, meta))
+    return store, meta
+
+
 def test_filter_expression_round_trips_through_the_evaluator(golden):
     """The strings _build_filter_expression emits are what B200IndexManager.search receives as `filters`: the manager's
-    parser must accept every one of them and select the right rows."""
-    from b200rag.index_manager import PayloadStore, _eval_filter, _parse_filter
-    store = PayloadStore()
-    for i in range(50):
-        store.append(f"c{i}", "x", {"doc_id": 'doc"123' if i % 2 else "a\\b", "chunk_index": i % 4, "entropy": i / 50.0,
-                                    "redundancy": 0.2 if i % 5 == 0 else 0.3, "domain_density": 0.5 if i < 10 else 0.25,
-                                    "timestamp": f"2024-0{1 + i % 9}-01", "token_count": 100 + 10 * i})
+    parser must accept every one of them and select the right rows (host restatement of the predicate semantics; the GPU
+    kernel is checked against it in tests/test_gpu_reference_behaviours.py)."""
+    from b200rag.index_manager import _parse_filter, eval_filter_host as _eval_filter
+    store, _ = _store()
     r = _retriever()
     for case in golden["filters"]:
         if "error" in case or not case["expr"]:
@@ -101,10 +108,61 @@ def test_filter_expression_round_trips_through_the_evaluator(golden):
     assert m.tolist() == [f"2024-0{1 + i % 9}-01" >= "2024-05-01" and 100 + 10 * i <= 300 for i in range(50)]
     m = _eval_filter(store, r._build_filter_expression({"doc_id": "a\\b", "domain_density": 0.5}))
     assert m.tolist() == [i % 2 == 0 and i < 10 for i in range(50)]
+    # a literal of the wrong type matches nothing; != never matches a missing value
+    assert not _eval_filter(store, 'entropy == "0.5"').any() and not _eval_filter(store, "doc_id == 3").any()
+    assert _eval_filter(store, "chunk_index >= 1.5").tolist() == [i % 4 >= 2 for i in range(50)]
     with pytest.raises(ValueError):
         _eval_filter(store, "evil == 1")
     with pytest.raises(ValueError):
         _eval_filter(store, "entropy >= 0.2 or entropy < 0.1")
+
+
+def test_payload_store_is_columnar_and_hits_are_fresh_dicts():
+    """Reference hit shape (indexing.py:534-551) from typed columns: values come back as the schema types them
+    (indexing.py:191-225), missing values as None, and every call builds fresh dicts (retrieval.py:361-363 mutates them)."""
+    from b200rag.index_manager import HitLists, PayloadStore, SearchArrays
+    store, meta = _store(20)
+    extra = store.convert(2, [None, {"doc_id": 7, "entropy": None, "chunk_index": 3}])
+    store.commit(["n0", "n1"], ["", "y z"], extra)
+    assert len(store) == 22 and store.num["entropy"].view.dtype == np.float64 and store.codes["doc_id"].view.dtype == np.int32
+    rows = np.asarray([3, 21, 20, 0], dtype=np.int64)
+    hits = store.hits(rows, np.asarray([0.5, 0.25, 0.125, 0.0]))
+    assert [h["id"] for h in hits] == ["c3", "n1", "n0", "c0"] and [h["score"] for h in hits] == [0.5, 0.25, 0.125, 0.0]
+    assert hits[0]["metadata"] == {k: meta[3][k] for k in ("doc_id", "chunk_index", "entropy", "redundancy", "domain_density", "timestamp")}
+    assert hits[1]["metadata"] == {"doc_id": "7", "chunk_index": 3, "entropy": None, "redundancy": None, "domain_density": None,
+                                   "timestamp": None}
+    assert all(v is None for v in hits[2]["metadata"].values()) and hits[2]["content"] == ""
+    assert isinstance(hits[0]["metadata"]["chunk_index"], int) and isinstance(hits[0]["metadata"]["entropy"], float)
+    again = store.hits(rows, np.zeros(4))
+    assert again[0] is not hits[0] and again[0]["metadata"] is not hits[0]["metadata"]
+    assert store.hit(3, 0.5) == hits[0]
+    # lazy List[List[dict]] view over a columnar result; counts and -1 padding are honoured
+    arr = SearchArrays(np.asarray([[3, 21, -1], [0, -1, -1], [-1, -1, -1]]), np.asarray([[.5, .25, 0], [1., 0, 0], [0, 0, 0.]]),
+                       np.asarray([2, 1, 0], dtype=np.int32), store)
+    lazy = arr.hits()
+    assert isinstance(lazy, HitLists) and len(lazy) == 3
+    assert [h["id"] for h in lazy[0]] == ["c3", "n1"] and lazy[2] == [] and lazy[-2][0]["id"] == "c0"
+    assert lazy[0][0] is not lazy[0][0]
+    assert [[h["id"] for h in q] for q in lazy.materialize()] == [["c3", "n1"], ["c0"], []] == arr.chunk_ids()
+    assert [[h["id"] for h in q] for q in lazy] == arr.chunk_ids()
+    # a value the schema type cannot hold is refused before anything is stored
+    with pytest.raises(ValueError):
+        store.convert(1, [{"entropy": "high"}])
+    with pytest.raises(ValueError):
+        store.convert(2, [{}])
+    assert len(store) == 22 and len(store.dict_values["doc_id"]) == 3
+    store.keep(np.asarray([0, 21]))
+    assert store.ids == ["c0", "n1"] and store.codes["doc_id"].view.tolist() == [store.dict_code["doc_id"]["a\\b"], 2]
+
+
+def test_csr_take_selects_rows():
+    from b200rag.index_manager import _csr_take
+    ptr = np.asarray([0, 2, 2, 5, 6], np.int64)
+    a, b = np.arange(6, dtype=np.int32), np.arange(6, dtype=np.float32) * 0.5
+    p2, (a2, b2) = _csr_take(ptr, [a, b], np.asarray([2, 0, 1]))
+    assert p2.tolist() == [0, 3, 5, 5] and a2.tolist() == [2, 3, 4, 0, 1] and b2.tolist() == [1.0, 1.5, 2.0, 0.0, 0.5]
+    p3, (a3,) = _csr_take(ptr, [a], np.zeros(0, np.int64))
+    assert p3.tolist() == [0] and a3.size == 0
 
 
 def test_learned_rerank_matches_reference(golden):

@@ -1,9 +1,10 @@
 """Same-box A/B of the sparse scan (BASELINE config 4's BM25 side: 1M documents, 100K-term Zipf vocabulary, 256 queries of
 8 terms, top-500) under the kernel's switches:
 
-    B200RAG_SPARSE_DENSE=bits   1 = dense collect mode, 2 = bulk append (default 3)
-    B200RAG_SPARSE_SLICES=n      slices per query (default: 2 * SMs / queries)
-    --block-docs a,b,...         documents per postings block
+    option "sparse_flags"   bit 0 = touched-bitmap collect only (no exchange collect); default 0
+    option "sparse_slices"  slices per query (0 = the library's choice)
+    --block-docs a,b,...    documents per postings block
+    --variants flags:slices,...
 
 Every variant must return the same ids / scores as the first one (bit exact); times are CUDA-event medians.
 No oracle use: this is a profiling helper, parity lives in tests/.
@@ -15,8 +16,6 @@ import json
 import os
 import statistics
 import sys
-
-import ctypes
 
 import numpy as np
 import torch
@@ -32,8 +31,8 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--k", type=int, default=500)
 ap.add_argument("--reps", type=int, default=15)
 ap.add_argument("--block-docs", default="16384")
-ap.add_argument("--variants", default="0:0,1:0,3:0")
-ap.add_argument("--stats", action="store_true", help="per-phase cycle counters of one launch (b200rag_debug_sparse_stats)")
+ap.add_argument("--variants", default="0:0,0:1,0:2,0:8,1:0")
+ap.add_argument("--stats", action="store_true", help="per-phase cycle counters of one launch (b200rag_debug_set_stats_buffer)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 
@@ -62,8 +61,8 @@ for bd in [int(x) for x in args.block_docs.split(",")]:
     nbytes = statistics.mean(idx.query_bytes(q[0], q[1]) for q in qs)
     for var in args.variants.split(","):
         dense, slices = var.split(":")
-        os.environ["B200RAG_SPARSE_DENSE"] = dense
-        os.environ["B200RAG_SPARSE_SLICES"] = slices
+        _lib.set_option("sparse_flags", int(dense))
+        _lib.set_option("sparse_slices", int(slices) if int(slices) > 0 else -1)
         it = [0]
 
         def fn():
@@ -80,22 +79,22 @@ for bd in [int(x) for x in args.block_docs.split(",")]:
         else:
             same = all(torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a, b.view(torch.int32) if b.dtype == torch.float32 else b)
                        for a, b in zip(got, ref))
-        print(json.dumps({"block_docs": bd, "dense": int(dense), "slices": int(slices), "ms": round(med, 4), "best_ms": round(best, 4),
+        print(json.dumps({"block_docs": bd, "flags": int(dense), "slices": int(slices), "ms": round(med, 4), "best_ms": round(best, 4),
                           "gbs": round(nbytes / med / 1e6, 1), "same_as_first": bool(same)}), flush=True)
         if args.stats:
             lib = _lib.load()
-            lib.b200rag_debug_sparse_stats(1, None, 0)
+            buf = torch.zeros((1024, 12), dtype=torch.int64, device=dev)
+            lib.b200rag_debug_set_stats_buffer(1, buf.data_ptr(), buf.numel())
             idx.search(*qs[0], args.k)
-            buf = np.zeros((1024, 12), dtype=np.uint64)
-            lib.b200rag_debug_sparse_stats(0, buf.ctypes.data_as(ctypes.c_void_p), 1024)
-            used = buf[buf.sum(1) > 0].astype(np.float64)
-            phases = [(0, "init"), (2, "fetch + term 1"), (3, "terms 2.."), (4, "scan accumulators"), (5, "bulk append"),
-                      (1, "compaction"), (8, "candidate rounds"), (6, "finalize")]
-            tot = used[:, [i for i, _ in phases]].sum(1)
+            torch.cuda.synchronize()
+            lib.b200rag_debug_set_stats_buffer(1, None, 0)
+            used = buf.cpu().numpy().astype(np.float64)
+            used = used[used.sum(1) > 0]
+            tot = used[:, :4].sum(1)
             print(f"    {len(used)} CTAs; cycles per CTA: mean {tot.mean():.0f}  min {tot.min():.0f}  max {tot.max():.0f}; per CTA: "
-                  f"{used[:, 7].mean():.1f} collects with candidates, {used[:, 9].mean():.1f} bulk compactions, "
-                  f"{used[:, 10].mean():.0f} candidates appended in bulk")
-            for i, n_ in phases:
+                  f"{used[:, 4].mean():.1f} blocks ({used[:, 7].mean():.1f} on the bitmap path), {used[:, 8].mean():.0f} postings, "
+                  f"{used[:, 5].mean():.0f} survivors staged, {used[:, 6].mean():.2f} collect re-runs")
+            for i, n_ in ((0, "init + finalize"), (1, "accumulate"), (2, "collect"), (3, "drain to top-k")):
                 v = used[:, i].mean()
                 print(f"    {n_:18s} {v:10.0f} cycles  {100 * v / tot.mean():5.1f}%")
     del idx
