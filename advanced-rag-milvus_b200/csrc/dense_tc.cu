@@ -23,6 +23,7 @@
 //     the fp32 accumulation error of the tensor-core path (checked empirically in tests/test_gpu_dense_tc.py).
 #include "tc_common.cuh"
 #include "select.cuh"
+#include "finish.cuh"
 
 namespace b200rag {
 
@@ -206,32 +207,6 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
 // ----------------------------------------------------------------------------------------------- finish kernel
 constexpr int FN_THREADS = 256;
-
-struct FinishParams {
-    const uint16_t* corpus;
-    const uint16_t* queries;
-    int64_t n_rows;
-    int dim;
-    int n_q;
-    int k;
-    int kprime;
-    int cap;
-    int nqb;
-    int n_chunks;
-    int topk_cap;        // BlockTopK capacity
-    int stage_rows;      // candidate rows staged per re-score batch (<= FN_THREADS / 8; fewer for very wide vectors)
-    int64_t id_offset;
-    double row_norm_bound;
-    const unsigned long long* cand;
-    const int* cand_cnt;
-    const unsigned int* gthr;
-    double* out_scores;
-    int64_t* out_ids;
-    int32_t* out_flags;
-    int32_t* flag_list;   // compacted list of flagged queries
-    int32_t* n_flagged;
-    float* err_max;       // optional [n_q]: max |tensor score - exact score| over the re-scored candidates
-};
 
 template <int DTYPE>
 __global__ void __launch_bounds__(FN_THREADS) dense_finish_kernel(const FinishParams p) {
@@ -683,10 +658,15 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
             s0.qg_span = 1;
             int rc = launch(s0);
             if (rc) return rc;
-            size_t tsm = BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.s_topk_cap) + 64;
-            sample_threshold_kernel<<<pl.nqb * TC_BM, FN_THREADS, tsm, st>>>(s0.cand, s0.cand_cnt, s0.cap, pl.nqb, pl.s_chunks,
-                                                                            pl.s_rank, pl.s_topk_cap, sp.gthr); count_launch();
-            B200_CUDA_CHECK(cudaGetLastError());
+            if (option(OPT_FINISH_VERSION, 2) == 1) {
+                size_t tsm = BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.s_topk_cap) + 64;
+                sample_threshold_kernel<<<pl.nqb * TC_BM, FN_THREADS, tsm, st>>>(s0.cand, s0.cand_cnt, s0.cap, pl.nqb, pl.s_chunks,
+                                                                                pl.s_rank, pl.s_topk_cap, sp.gthr); count_launch();
+                B200_CUDA_CHECK(cudaGetLastError());
+            } else {
+                rc = launch_sample_threshold2(s0.cand, s0.cap, pl.nqb, pl.s_chunks, pl.s_rank, sp.gthr, st);
+                if (rc) return rc;
+            }
         }
         sp.n_tiles = pl.n_tiles;
         sp.tile_stride = 1;
@@ -730,7 +710,11 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
     fp.flag_list = flag_list;
     fp.n_flagged = n_flagged;
     fp.err_max = out_err;
-    if (dtype == B200RAG_F16) {
+    if (option(OPT_FINISH_VERSION, 2) != 1 && finish2_smem_bytes(dim, pl.kprime) <= 200 * 1024) {
+        // second generation (dense_finish.cu): warp-level selection, one thread per candidate row
+        int rc = launch_finish2(fp, dtype, st);
+        if (rc) return rc;
+    } else if (dtype == B200RAG_F16) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(dense_finish_kernel<B200RAG_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.finish_smem));
         dense_finish_kernel<B200RAG_F16><<<n_q, FN_THREADS, pl.finish_smem, st>>>(fp); count_launch();
     } else {

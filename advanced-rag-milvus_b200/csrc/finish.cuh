@@ -1,0 +1,41 @@
+// finish.cuh -- parameters of the finish stage (K2) shared by its two kernel generations (dense_tc.cu, dense_finish.cu).
+#pragma once
+#include "tc_common.cuh"
+
+namespace b200rag {
+
+struct FinishParams {
+    const uint16_t* corpus;
+    const uint16_t* queries;
+    int64_t n_rows;
+    int dim;
+    int n_q;
+    int k;
+    int kprime;
+    int cap;
+    int nqb;
+    int n_chunks;
+    int topk_cap;        // BlockTopK capacity
+    int stage_rows;      // candidate rows staged per re-score batch (<= FN_THREADS / 8; fewer for very wide vectors)
+    int64_t id_offset;
+    double row_norm_bound;
+    const unsigned long long* cand;
+    const int* cand_cnt;
+    const unsigned int* gthr;
+    double* out_scores;
+    int64_t* out_ids;
+    int32_t* out_flags;
+    int32_t* flag_list;   // compacted list of flagged queries
+    int32_t* n_flagged;
+    float* err_max;       // optional [n_q]: max |tensor score - exact score| over the re-scored candidates
+};
+
+
+// Second generation (dense_finish.cu): one 128-thread CTA per query, warp-level selection, one thread per candidate row.
+size_t finish2_smem_bytes(int dim, int kprime);
+int launch_finish2(const FinishParams& fp, int dtype, cudaStream_t st);
+// Warp-per-query replacement of sample_threshold_kernel.
+int launch_sample_threshold2(const unsigned long long* cand, int cap, int nqb, int n_chunks, int rank, unsigned int* gthr,
+                             cudaStream_t st);
+
+}  // namespace b200rag
