@@ -34,13 +34,16 @@ int launch_merge(const double* cand_scores, const int64_t* cand_ids, int n_launc
 
 constexpr int SP_THREADS = 256;
 constexpr int SP_WARPS = SP_THREADS / 32;
-constexpr int SP_TG = 8;            // query terms handled together (one register pair per term and thread)
+constexpr int SP_TG = 8;            // query terms handled together
 constexpr int SP_STAGE = 1024;      // survivors staged per collect pass
+constexpr int SP_PCAP = 2560;       // postings of one block staged in shared memory (per buffer; the rest is read in place)
+constexpr int SP_RING = 3;          // range / layout slots: block b uses slot b % 3, slot 3 serves the term groups beyond the first
 constexpr int SP_NSTAT = 12;        // debug counters per CTA (b200rag_debug_set_stats_buffer kind 1)
 constexpr int SP_STAT_CTAS = 1024;
 constexpr int SP_MAX_SLICES = 32;
 
-enum { SPS_TOTAL = 0, SPS_ACC, SPS_COLLECT, SPS_DRAIN, SPS_BLOCKS, SPS_STAGED, SPS_RESCANS, SPS_BITMAP_BLOCKS, SPS_POSTINGS };
+enum { SPS_TOTAL = 0, SPS_ACC, SPS_COLLECT, SPS_DRAIN, SPS_BLOCKS, SPS_STAGED, SPS_RESCANS, SPS_BITMAP_BLOCKS, SPS_POSTINGS,
+       SPS_WAIT, SPS_UNSTAGED };
 
 struct SparseParams {
     const int64_t* blk_term_ptr;
@@ -60,29 +63,43 @@ struct SparseParams {
     int32_t* out_counts;
     unsigned int* gthr;         // [n_queries] mono32 keys of the best k-th score any slice has established (n_slices > 1)
     const uint32_t* doc_mask;
-    int flags;                  // bit 0: never use the exchange collect (A/B)
+    int flags;                  // bit 0: never use the exchange collect; bit 1: no shared-memory staging of the postings (A/B)
     unsigned long long* stats;
 };
 
-__global__ void __launch_bounds__(SP_THREADS, 3) sparse_query_kernel(const SparseParams p) {
+__device__ __forceinline__ void sp_cp_async4(void* smem_dst, const void* gsrc, unsigned src_bytes) {
+    // 4-byte asynchronous global -> shared copy; src_bytes < 4 zero-fills the rest (nothing beyond src_bytes is read)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
+                 "r"(src_bytes)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(SP_THREADS, 2) sparse_query_kernel(const SparseParams p) {
     extern __shared__ __align__(16) char smem[];
-    __shared__ long long s_beg[SP_TG];         // posting ranges of the current term group inside the current block
-    __shared__ int s_len[SP_TG];
-    __shared__ int s_off[SP_TG + 1];           // exclusive prefix of s_len: the flat index space of the collect pass
-    __shared__ float s_qv[SP_TG];
+    // per ring slot: posting ranges of a term group inside one block and where their staged copies live
+    __shared__ long long s_beg[SP_RING + 1][SP_TG];
+    __shared__ int s_len[SP_RING + 1][SP_TG];
+    __shared__ int s_slen[SP_RING + 1][SP_TG];      // leading postings of the list that are staged
+    __shared__ int s_woff[SP_RING + 1][SP_TG];      // staged weights start here (staging buffer index)
+    __shared__ int s_doff[SP_RING + 1][SP_TG];      // staged rows start here (u16 index; even base + the list's odd/even shift)
+    __shared__ int s_off[SP_RING + 1][SP_TG + 1];   // exclusive prefix of s_len: the flat index space of the collect pass
+    __shared__ float s_qv[SP_RING + 1][SP_TG];
     __shared__ int s_nstage;
     __shared__ unsigned int s_gthr;
     __shared__ unsigned long long s_stat[SP_NSTAT];
     __shared__ long long s_last;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = blockIdx.x, slice = blockIdx.y;
     const int block_docs = p.block_docs, n_words = block_docs >> 5;
     float* acc = reinterpret_cast<float*>(smem);                                     // [block_docs]
     uint32_t* touched = reinterpret_cast<uint32_t*>(acc + block_docs);                // [n_words]
     uint32_t* stage_doc = touched + n_words;                                          // [SP_STAGE] row inside the block
     float* stage_sc = reinterpret_cast<float*>(stage_doc + SP_STAGE);                 // [SP_STAGE]
-    char* tkmem = reinterpret_cast<char*>(stage_sc + SP_STAGE);
+    float* pw = stage_sc + SP_STAGE;                                                  // [2][SP_PCAP] staged weights
+    uint16_t* pd = reinterpret_cast<uint16_t*>(pw + 2 * SP_PCAP);                     // [2][SP_PCAP + 32] staged rows
+    constexpr int PD_STRIDE = SP_PCAP + 32;
+    char* tkmem = reinterpret_cast<char*>(pd + 2 * PD_STRIDE);
     tkmem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tkmem) + 15) & ~uintptr_t(15));
     using TopK = BlockTopK<SP_THREADS, uint32_t>;
     TopK tk;
@@ -112,8 +129,11 @@ __global__ void __launch_bounds__(SP_THREADS, 3) sparse_query_kernel(const Spars
     const int nq = (int)(p.q_ptr[q + 1] - qs);
     const int n_groups = (nq + SP_TG - 1) / SP_TG;
     const bool multi = n_groups > 1;
+    const bool staging = !(p.flags & 2);
     const int b0 = (int)((int64_t)slice * p.n_blocks / p.n_slices), b1 = (int)((int64_t)(slice + 1) * p.n_blocks / p.n_slices);
     const size_t row_stride = (size_t)p.n_terms + 1;
+    // postings in the whole index = the end pointer of the last block (bounds the 4-byte row copies at the very end)
+    const long long nnz = p.blk_term_ptr[(size_t)(p.n_blocks - 1) * row_stride + p.n_terms];
 
     // ranges of term group g inside block blk: thread j < SP_TG owns term g * SP_TG + j
     int my_t = -1;
@@ -136,52 +156,88 @@ __global__ void __launch_bounds__(SP_THREADS, 3) sparse_query_kernel(const Spars
             rl = (int)(src[1] - rb);
         }
     };
-    auto publish_range = [&](long long rb, int rl) {          // threads < SP_TG, then a barrier, then thread 0 builds s_off
-        if (tid < SP_TG) { s_beg[tid] = rb; s_len[tid] = rl; s_qv[tid] = my_qv; }
-    };
-    auto build_offsets = [&]() {                              // after the barrier that follows publish_range
-        if (tid == 0) {
-            int o = 0;
+    // Warp 0 publishes the ranges its lanes 0..7 hold into ring slot `slot`, together with the staging layout: the flat
+    // prefix (collect pass), how much of every list fits the staging buffer and where.  Followed by a barrier.
+    auto publish = [&](int slot, long long rb, int rl, bool stage_it) {
+        if (warp != 0) return;
+        int len = tid < SP_TG ? rl : 0;
+        int incl = len, wincl;
 #pragma unroll
-            for (int j = 0; j < SP_TG; ++j) { s_off[j] = o; o += s_len[j]; }
-            s_off[SP_TG] = o;
-            if (stats) s_stat[SPS_POSTINGS] += (unsigned long long)o;
+        for (int o = 1; o < SP_TG; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int excl = incl - len;
+        const int woff = min(excl, SP_PCAP);
+        const int slen = stage_it ? max(0, min(len, SP_PCAP - excl)) : 0;
+        // rows are staged as aligned 4-byte words: a list that starts at an odd posting index keeps its shift
+        const int sh = (int)(rb & 1);
+        int dw = slen ? 2 * ((sh + slen + 1) >> 1) : 0;        // u16 slots this list occupies (even)
+        wincl = dw;
+#pragma unroll
+        for (int o = 1; o < SP_TG; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wincl, o);
+            if (lane >= o) wincl += v;
+        }
+        if (tid < SP_TG) {
+            s_beg[slot][tid] = rb;
+            s_len[slot][tid] = len;
+            s_slen[slot][tid] = slen;
+            s_woff[slot][tid] = woff;
+            s_doff[slot][tid] = wincl - dw + sh;
+            s_off[slot][tid] = excl;
+            s_qv[slot][tid] = my_qv;
+            if (tid == SP_TG - 1) s_off[slot][SP_TG] = incl;
+        }
+    };
+    // All threads: start the asynchronous copies of a published block's leading postings into staging buffer `buf`.
+    auto issue_stage = [&](int slot, int buf) {
+        float* wdst = pw + buf * SP_PCAP;
+        uint32_t* ddst = reinterpret_cast<uint32_t*>(pd + buf * PD_STRIDE);
+        const uint32_t* dsrc32 = reinterpret_cast<const uint32_t*>(p.post_doc);
+#pragma unroll
+        for (int j = 0; j < SP_TG; ++j) {
+            const int slen = s_slen[slot][j];
+            if (slen == 0) continue;
+            const long long beg = s_beg[slot][j];
+            const int woff = s_woff[slot][j];
+            for (int i = tid; i < slen; i += SP_THREADS) sp_cp_async4(wdst + woff + i, p.post_w + beg + i, 4u);
+            const int sh = (int)(beg & 1);
+            const long long g0 = beg - sh;                                 // even posting index
+            const int nw = (sh + slen + 1) >> 1;
+            const int dbase = (s_doff[slot][j] - sh) >> 1;                 // word index inside the staging buffer
+            for (int wi = tid; wi < nw; wi += SP_THREADS)
+                sp_cp_async4(ddst + dbase + wi, dsrc32 + (g0 >> 1) + wi, g0 + 2 * wi + 1 < nnz ? 4u : 2u);
         }
     };
 
-    // ---- ordered accumulate of the published term group; `prev_pw` = warps that took part in the previous non-empty step
-    auto accumulate_group = [&](bool bitmap, int& prev_pw) {
-        int dreg[SP_TG];
-        float wreg[SP_TG];
+    // ---- ordered accumulate of the term group in `slot`; `prev_pw` = warps that took part in the previous non-empty step
+    auto accumulate_group = [&](int slot, int buf, bool bitmap, int& prev_pw) {
+        const float* wsrc = pw + buf * SP_PCAP;
+        const uint16_t* dsrc = pd + buf * PD_STRIDE;
 #pragma unroll
         for (int j = 0; j < SP_TG; ++j) {
-            dreg[j] = -1;
-            wreg[j] = 0.f;
-            if (tid < s_len[j]) {
-                const long long i = s_beg[j] + tid;
-                dreg[j] = p.post_doc[i];
-                wreg[j] = p.post_w[i];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < SP_TG; ++j) {
-            const int len = s_len[j];
+            const int len = s_len[slot][j];
             if (len == 0) continue;                                                  // CTA-uniform
-            const int pw = len >= SP_THREADS ? SP_WARPS : (len + 31) >> 5;
+            const int pwarps = len >= SP_THREADS ? SP_WARPS : (len + 31) >> 5;
             if (prev_pw) {
-                if (prev_pw > 1 || pw > 1) __syncthreads();
+                if (prev_pw > 1 || pwarps > 1) __syncthreads();
                 else __syncwarp();
             }
-            prev_pw = pw;
-            if (warp < pw) {
-                const float qv = s_qv[j];
-                if (dreg[j] >= 0) {
-                    const int d = dreg[j];
-                    acc[d] = fmaf(qv, wreg[j], acc[d]);
+            prev_pw = pwarps;
+            if (warp < pwarps) {
+                const float qv = s_qv[slot][j];
+                const int slen = s_slen[slot][j];
+                const float* ws = wsrc + s_woff[slot][j];
+                const uint16_t* ds = dsrc + s_doff[slot][j];
+                int i = tid;
+                for (; i < slen; i += SP_THREADS) {                                  // staged part: shared memory only
+                    const int d = ds[i];
+                    acc[d] = fmaf(qv, ws[i], acc[d]);
                     if (bitmap) atomicOr(&touched[d >> 5], 1u << (d & 31));
                 }
-                const long long beg = s_beg[j];
-                for (int i = tid + SP_THREADS; i < len; i += 2 * SP_THREADS) {      // long lists: two postings in flight
+                const long long beg = s_beg[slot][j];
+                for (; i < len; i += 2 * SP_THREADS) {                               // the rest of a long list: two in flight
                     const int i1 = i + SP_THREADS;
                     const int d0 = p.post_doc[beg + i];
                     const float w0 = p.post_w[beg + i];
@@ -208,13 +264,15 @@ __global__ void __launch_bounds__(SP_THREADS, 3) sparse_query_kernel(const Spars
         return true;
     };
 
-    // ---- exchange collect over the published term group: flat index space, every posting visited once
-    auto collect_group_exch = [&](float thr_f, int64_t doc0) {
-        const int total = s_off[SP_TG];
+    // ---- exchange collect over the term group in `slot`: flat index space, every posting visited once
+    auto collect_group_exch = [&](int slot, int buf, float thr_f, int64_t doc0) {
+        const uint16_t* dsrc = pd + buf * PD_STRIDE;
+        const int total = s_off[slot][SP_TG];
         int j = 0;
         for (int pos = tid; pos < total; pos += SP_THREADS) {
-            while (pos >= s_off[j + 1]) ++j;
-            const int d = p.post_doc[s_beg[j] + (pos - s_off[j])];
+            while (pos >= s_off[slot][j + 1]) ++j;
+            const int i = pos - s_off[slot][j];
+            const int d = i < s_slen[slot][j] ? (int)dsrc[s_doff[slot][j] + i] : (int)p.post_doc[s_beg[slot][j] + i];
             const float sc = atomicExch(&acc[d], 0.0f);
             if (sc >= thr_f) {
                 bool ok = true;
@@ -254,16 +312,26 @@ __global__ void __launch_bounds__(SP_THREADS, 3) sparse_query_kernel(const Spars
         }
     };
 
+    // ---- prologue: ranges of the first block published and staged, ranges of the second one in flight
     load_term(0);
     long long nb = 0;
     int nl = 0;
-    if (b0 < b1) fetch_range(b0, nb, nl);
-    __syncthreads();
+    const bool walk = nq > 0 && b0 < b1;
+    if (walk) fetch_range(b0, nb, nl);
+    __syncthreads();                                           // (init of acc / touched / top-k done)
+    if (walk) {
+        publish(b0 % SP_RING, nb, nl, staging);
+        __syncthreads();
+        issue_stage(b0 % SP_RING, b0 & 1);
+        if (b0 + 1 < b1) fetch_range(b0 + 1, nb, nl);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     SP_MARK(SPS_TOTAL);
     for (int blk = b0; blk < b1 && nq > 0; ++blk) {
         const int64_t doc0 = (int64_t)blk * block_docs;
-        // ---- block top: publish the ranges fetched during the previous block, exchange thresholds with the other slices
-        publish_range(nb, nl);
+        const int slot = blk % SP_RING, buf = blk & 1;
+        // ---- block top: publish + stage the NEXT block, exchange thresholds with the other slices, wait for THIS block's copies
+        if (blk + 1 < b1) publish((blk + 1) % SP_RING, nb, nl, staging);
         if (tid == 0 && p.gthr) {
             if (tk.st->has_thr) atomicMax(p.gthr + q, (unsigned int)tk.st->thr_hi);
             unsigned int g;
@@ -271,46 +339,52 @@ __global__ void __launch_bounds__(SP_THREADS, 3) sparse_query_kernel(const Spars
             s_gthr = g;
         }
         __syncthreads();
-        build_offsets();
-        if (blk + 1 < b1) fetch_range(blk + 1, nb, nl);       // (group 0 of the next block: in flight during this one)
+        if (blk + 1 < b1) issue_stage((blk + 1) % SP_RING, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");   // (one group per block, possibly empty)
+        if (blk + 2 < b1) fetch_range(blk + 2, nb, nl);        // (in flight during this whole block)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the newest group has landed: this block's
+        __syncthreads();
+        SP_MARK(SPS_WAIT);
         float thr_f = tk.threshold_hi32_as_float();
         if (s_gthr) thr_f = fmaxf(thr_f, unmono32(s_gthr));
         const bool bitmap = !(thr_f > 0.0f) || (p.flags & 1);  // CTA-uniform
         // ---- accumulate, all term groups in ascending term order
         int prev_pw = 0;
-        accumulate_group(bitmap, prev_pw);
-        for (int g = 1; g < n_groups; ++g) {                   // queries with more than SP_TG terms: unpipelined
-            __syncthreads();                                   // everyone is done with the published ranges
+        accumulate_group(slot, buf, bitmap, prev_pw);
+        for (int g = 1; g < n_groups; ++g) {                   // queries with more than SP_TG terms: unstaged, unpipelined
+            __syncthreads();
             load_term(g);
             long long rb;
             int rl;
             fetch_range(blk, rb, rl);
-            publish_range(rb, rl);
+            publish(SP_RING, rb, rl, false);
             __syncthreads();
             prev_pw = 0;                                       // (the barrier above already ordered the previous group)
-            accumulate_group(bitmap, prev_pw);
+            accumulate_group(SP_RING, buf, bitmap, prev_pw);
         }
         __syncthreads();
         SP_MARK(SPS_ACC);
-        if (stats && tid == 0) { s_stat[SPS_BLOCKS] += 1; s_stat[SPS_BITMAP_BLOCKS] += bitmap ? 1 : 0; }
+        if (stats && tid == 0) {
+            s_stat[SPS_BLOCKS] += 1;
+            s_stat[SPS_BITMAP_BLOCKS] += bitmap ? 1 : 0;
+            s_stat[SPS_POSTINGS] += (unsigned long long)s_off[slot][SP_TG];
+            for (int j = 0; j < SP_TG; ++j) s_stat[SPS_UNSTAGED] += (unsigned long long)(s_len[slot][j] - s_slen[slot][j]);
+        }
         // ---- collect (repeated while the staging list overflows)
         for (;;) {
             if (bitmap) {
                 collect_bitmap(thr_f, doc0);
-            } else if (!multi) {
-                collect_group_exch(thr_f, doc0);               // (s_off was built at the block top)
             } else {
-                for (int g = 0; g < n_groups; ++g) {
+                collect_group_exch(slot, buf, thr_f, doc0);
+                for (int g = 1; g < n_groups; ++g) {
                     __syncthreads();
                     load_term(g);
                     long long rb;
                     int rl;
                     fetch_range(blk, rb, rl);
-                    publish_range(rb, rl);
+                    publish(SP_RING, rb, rl, false);
                     __syncthreads();
-                    build_offsets();
-                    __syncthreads();
-                    collect_group_exch(thr_f, doc0);
+                    collect_group_exch(SP_RING, buf, thr_f, doc0);
                 }
             }
             __syncthreads();
@@ -341,12 +415,12 @@ __global__ void __launch_bounds__(SP_THREADS, 3) sparse_query_kernel(const Spars
             SP_MARK(SPS_DRAIN);
             if (staged_raw <= SP_STAGE) break;
         }
-        if (multi) {                                           // back to group 0 for the next block's prefetch
+        if (multi) {                                           // back to group 0 (the prefetched ranges in nb / nl belong to it)
             __syncthreads();
             load_term(0);
-            if (blk + 1 < b1) fetch_range(blk + 1, nb, nl);
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     tk.finalize();
     const int n = tk.count();
@@ -375,11 +449,19 @@ __global__ void __launch_bounds__(SP_THREADS, 3) sparse_query_kernel(const Spars
 #undef SP_MARK
 }
 
+static size_t sparse_smem_for(int block_docs, int cap) {
+    return (size_t)block_docs * 4 + (size_t)(block_docs / 32) * 4 + (size_t)SP_STAGE * 8 + (size_t)2 * SP_PCAP * 4 +
+           (size_t)2 * (SP_PCAP + 32) * 2 + 16 + BlockTopK<SP_THREADS, uint32_t>::smem_bytes(cap) + 64;
+}
+
 static size_t sparse_smem(int block_docs, int k, int* cap_out) {
-    const int cap = BlockTopK<SP_THREADS, uint32_t>::capacity_for(k, SP_THREADS);
+    // streaming top-k buffer: at least k + 512 entries (one compaction per 256 survivors); grown to k + 1024 (one per 768)
+    // while two CTAs still fit an SM (each compaction is a multi-pass radix select over the whole buffer)
+    int cap = BlockTopK<SP_THREADS, uint32_t>::capacity_for(k, SP_THREADS);
+    const int big = k + 1024 > cap ? k + 1024 : cap;
+    if (sparse_smem_for(block_docs, big) + 1024 <= 113 * 1024) cap = big;
     if (cap_out) *cap_out = cap;
-    return (size_t)block_docs * 4 + (size_t)(block_docs / 32) * 4 + (size_t)SP_STAGE * 8 + 16 +
-           BlockTopK<SP_THREADS, uint32_t>::smem_bytes(cap) + 64;
+    return sparse_smem_for(block_docs, cap);
 }
 
 static int sparse_slices(int64_t n_blocks, int n_queries) {
@@ -430,6 +512,7 @@ int b200rag_sparse_topk_masked(const int64_t* blk_term_ptr, const uint16_t* post
                                void* workspace, size_t workspace_bytes, void* stream) {
     B200_REQUIRE(blk_term_ptr && q_ptr && out_scores && out_ids && out_counts && workspace, "sparse_topk: null pointer");
     B200_REQUIRE(n_docs >= 0 && n_terms > 0 && n_queries >= 0 && k > 0, "sparse_topk: bad sizes");
+    B200_REQUIRE(((uintptr_t)post_doc & 3) == 0 && ((uintptr_t)post_w & 3) == 0, "sparse_topk: postings arrays must be 4-byte aligned");
     B200_REQUIRE(block_docs > 0 && block_docs <= 32768 && block_docs % 32 == 0,
                  "sparse_topk: block_docs must be a multiple of 32 in (0, 32768], got %d", block_docs);
     if (n_queries == 0) return B200RAG_OK;
