@@ -1,29 +1,31 @@
-// sparse_bm25.cu -- sparse inner-product (BM25-weighted) top-k over doc-range-blocked postings  (K3, second generation).
+// sparse_bm25.cu -- sparse inner-product (BM25-weighted) top-k over doc-range-blocked postings  (K3, round-2 generation).
 //
-// One 256-thread CTA owns one (query, slice of document blocks) and walks its blocks one after the other; two or three
-// CTAs share an SM.  The block's per-document accumulators live in shared memory (fp32, 64 KB at 16384-document blocks),
-// zeroed once per CTA -- collecting a block puts every touched accumulator back to zero.  Per block:
+// One 256-thread CTA owns one (query, slice of document blocks) and walks its blocks one after the other; two or three CTAs
+// share an SM.  The block's per-document accumulators live in shared memory (fp32), zeroed once per CTA -- collecting a block
+// puts every touched accumulator back to zero.  What bounds this kernel is not bytes (6 per posting) but the dependent chain
+// inside a block: ranges -> postings -> accumulator read-modify-write per term, in term order.  Round 1 ran that chain once per
+// CTA with a block barrier between terms and found the candidates by reading all 16384 accumulators back (7.9 warp instructions
+// per posting, profiles/r1_sparse_ncu.md).  This generation:
 //
-//   accumulate (ordered)  the first 256 postings of each of up to 8 query terms are requested TOGETHER (one u16 row + one f32
-//       weight per thread and term, all in flight at once), then applied in ascending term id so that every document sees
-//       acc = fmaf(qv, w, acc)  in the canonical order (bit-identical to oracle/exact_scan.c:orc_sparse_topk).  Only as many
-//       WARPS as a list has 32-posting pieces take part in its step (a 20-posting list costs one warp a dozen instructions,
-//       not the whole CTA), and the barrier between two steps shrinks to __syncwarp when both fit one warp.  Postings of one
-//       term hit distinct documents: no atomics on the accumulators.
-//   collect (unordered)   once the running k-th best score `thr` is positive -- after the first block or two -- the SAME
-//       postings are walked again as one flat index space spread evenly over the threads: s = atomicExch(&acc[row], 0);
-//       the first visitor of a document gets its final score, later visitors (other terms of the same document) get 0, and
-//       only s >= thr goes on.  The walk is proportional to the postings, it resets the accumulators as it goes, and there
-//       is no scan over the 16384 accumulators and no touched-bitmap (round 1 read 64 KB of shared memory per block to find
-//       ~2000 touched documents: 7.9 warp instructions per posting, see profiles/r1_sparse_ncu.md).  While thr <= 0 (first
-//       block, queries with non-positive scores) a touched-bitmap marks the candidates instead -- a document with score
-//       exactly 0 that shares a term with the query is still a hit.
-//   survivors go through a 1024-entry staging list into the CTA's streaming top-k (select.cuh), which lives for the whole
-//       walk.  If the list overflows (first blocks only) the overflowing documents keep their accumulator, the list is
-//       drained -- which raises thr -- and the collect pass runs again.
-// Slices of one query share their thresholds through a global atomicMax, so a slice that starts late does not repeat the
-// warm-up.  Algorithmic HBM traffic = 6 bytes per posting of the query's terms (the collect pass re-reads the 2-byte rows
-// from L1/L2).  grid = (queries, slices); merge_topk_kernel reduces the slices.
+//   staging     the postings of the NEXT block (rows u16 + weights f32 of up to 8 query terms) are copied into shared memory with
+//               cp.async while the current block is processed (ranges are fetched two blocks ahead): no global-memory latency
+//               on the chain, and the collect pass re-reads the rows from shared memory.
+//   warp-private sub-ranges   every warp owns 1/8 of the block's documents.  One flat pass over the staged (doc-sorted) lists
+//               records where each list crosses the sub-range boundaries; then each warp applies ITS part of the 8 lists in
+//               ascending term id -- acc = fmaf(qv, w, acc), the canonical order, bit-identical to oracle/exact_scan.c -- with
+//               __syncwarp only: eight independent chains per CTA instead of one, no block barrier between terms.
+//   collect     proportional to the postings, not to the documents: once the running k-th best score `thr` is positive (after the
+//               first block or two) each warp walks its postings again, takes the final score out of the accumulator and
+//               zeroes it (later postings of the same document then read 0); only scores >= thr go on.  No scan over the
+//               accumulators, no touched-bitmap.  While thr <= 0 (first block, queries with non-positive scores) a bitmap marks
+//               the candidates instead -- a document with score exactly 0 that shares a term with the query is still a hit.
+//   survivors   go through a staging list into the CTA's streaming top-k (select.cuh); the list is drained (which raises thr)
+//               when it is half full, not after every block.  If it overflows, the overflowing documents keep their
+//               accumulator, the list is drained and the collect pass of that block runs again.
+// Blocks that do not fit this scheme (more staged postings than the buffer holds, queries with more than 8 terms, block sizes
+// that are not a power of two >= 256) take the block-level path: same arithmetic, a block barrier between terms, postings read
+// in place.  Slices of one query share their thresholds through a global atomicMax.  Algorithmic HBM traffic = 6 bytes per
+// posting of the query's terms.  grid = (queries, slices); merge_topk_kernel reduces the slices.
 #include "common.cuh"
 #include "select.cuh"
 
@@ -84,6 +86,8 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sparse_query_kernel(const Spars
     __shared__ int s_doff[SP_RING + 1][SP_TG];      // staged rows start here (u16 index; even base + the list's odd/even shift)
     __shared__ int s_off[SP_RING + 1][SP_TG + 1];   // exclusive prefix of s_len: the flat index space of the collect pass
     __shared__ float s_qv[SP_RING + 1][SP_TG];
+    __shared__ int s_fits[SP_RING + 1];             // every posting of the slot's lists is staged
+    __shared__ int s_bnd[SP_TG][SP_WARPS + 1];      // current block: where list j crosses the warps' document sub-ranges
     __shared__ int s_nstage;
     __shared__ unsigned int s_gthr;
     __shared__ unsigned long long s_stat[SP_NSTAT];
@@ -187,7 +191,10 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sparse_query_kernel(const Spars
             s_doff[slot][tid] = wincl - dw + sh;
             s_off[slot][tid] = excl;
             s_qv[slot][tid] = my_qv;
-            if (tid == SP_TG - 1) s_off[slot][SP_TG] = incl;
+            if (tid == SP_TG - 1) {
+                s_off[slot][SP_TG] = incl;
+                s_fits[slot] = stage_it && incl <= SP_PCAP;
+            }
         }
     };
     // All threads: start the asynchronous copies of a published block's leading postings into staging buffer `buf`.
@@ -256,10 +263,10 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sparse_query_kernel(const Spars
     };
 
     // a survivor goes to the staging list; false = the list is full (the caller keeps the document for the next pass)
-    auto stage = [&](int d, float sc) -> bool {
+    auto stage = [&](uint32_t doc, float sc) -> bool {       // doc = row inside this shard (block start + row in block)
         const int slot = atomicAdd(&s_nstage, 1);
         if (slot >= SP_STAGE) return false;
-        stage_doc[slot] = (uint32_t)d;
+        stage_doc[slot] = doc;
         stage_sc[slot] = sc;
         return true;
     };
@@ -280,14 +287,14 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sparse_query_kernel(const Spars
                     const int64_t g = doc0 + d;
                     ok = (__ldg(p.doc_mask + (g >> 5)) >> (g & 31)) & 1u;
                 }
-                if (ok && !stage(d, sc)) acc[d] = sc;         // list full: the document waits for the next pass
+                if (ok && !stage((uint32_t)(doc0 + d), sc)) acc[d] = sc;     // list full: the document waits for the next pass
             }
         }
     };
     // ---- bitmap collect: every thread owns whole 32-document words
-    auto collect_bitmap = [&](float thr_f, int64_t doc0) {
+    auto collect_bitmap = [&](float thr_f, int64_t doc0, int w_begin, int w_end, int w_first, int w_step) {
         const int64_t n_mask_words = (p.n_docs + 31) >> 5;
-        for (int w = tid; w < n_words; w += SP_THREADS) {
+        for (int w = w_begin + w_first; w < w_end; w += w_step) {
             uint32_t m = touched[w];
             if (!m) continue;
             uint32_t allowed = 0xffffffffu;
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sparse_query_kernel(const Spars
                 const int d = w * 32 + b;
                 const float sc = acc[d];
                 if (!(sc < thr_f) && ((allowed >> b) & 1u)) {
-                    if (stage(d, sc)) acc[d] = 0.0f;
+                    if (stage((uint32_t)(doc0 + d), sc)) acc[d] = 0.0f;
                     else keep |= 1u << b;
                 } else {
                     acc[d] = 0.0f;
@@ -327,6 +334,11 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sparse_query_kernel(const Spars
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     SP_MARK(SPS_TOTAL);
+    // warp-private sub-ranges need a power-of-two block of at least 32 documents per warp
+    const bool fast_geom = (block_docs & (block_docs - 1)) == 0 && block_docs >= 32 * SP_WARPS;
+    const int sub_shift = 31 - __clz(block_docs) - 3;             // log2(block_docs / SP_WARPS)
+    const int sub_words = n_words / SP_WARPS;
+    float thr_f = -CUDART_INF_F;
     for (int blk = b0; blk < b1 && nq > 0; ++blk) {
         const int64_t doc0 = (int64_t)blk * block_docs;
         const int slot = blk % SP_RING, buf = blk & 1;
@@ -345,35 +357,101 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sparse_query_kernel(const Spars
         asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the newest group has landed: this block's
         __syncthreads();
         SP_MARK(SPS_WAIT);
-        float thr_f = tk.threshold_hi32_as_float();
         if (s_gthr) thr_f = fmaxf(thr_f, unmono32(s_gthr));
         const bool bitmap = !(thr_f > 0.0f) || (p.flags & 1);  // CTA-uniform
-        // ---- accumulate, all term groups in ascending term order
-        int prev_pw = 0;
-        accumulate_group(slot, buf, bitmap, prev_pw);
-        for (int g = 1; g < n_groups; ++g) {                   // queries with more than SP_TG terms: unstaged, unpipelined
+        const bool fast = fast_geom && !multi && s_fits[slot] && !(p.flags & 4);
+        const float* wsrc = pw + buf * SP_PCAP;
+        const uint16_t* dsrc = pd + buf * PD_STRIDE;
+        if (fast) {
+            // ---- where does each (doc-sorted) staged list cross the warps' sub-range boundaries?  One flat pass.
+            {
+                const int total = s_off[slot][SP_TG];
+                int j = 0;
+                for (int pos = tid; pos < total; pos += SP_THREADS) {
+                    while (pos >= s_off[slot][j + 1]) ++j;
+                    const int i = pos - s_off[slot][j];
+                    const uint16_t* ds = dsrc + s_doff[slot][j];
+                    const int wcur = ds[i] >> sub_shift;
+                    const int wprev = i ? (ds[i - 1] >> sub_shift) : -1;
+                    for (int w = wprev + 1; w <= wcur; ++w) s_bnd[j][w] = i;
+                    if (i == s_len[slot][j] - 1)
+                        for (int w = wcur + 1; w <= SP_WARPS; ++w) s_bnd[j][w] = i + 1;
+                }
+                if (tid < SP_TG && s_len[slot][tid] == 0)
+                    for (int w = 0; w <= SP_WARPS; ++w) s_bnd[tid][w] = 0;
+            }
             __syncthreads();
-            load_term(g);
-            long long rb;
-            int rl;
-            fetch_range(blk, rb, rl);
-            publish(SP_RING, rb, rl, false);
+            // ---- accumulate: this warp's documents, all lists in ascending term order, warp-level ordering only
+#pragma unroll
+            for (int j = 0; j < SP_TG; ++j) {
+                const int lo = s_bnd[j][warp], hi = s_bnd[j][warp + 1];
+                if (lo < hi) {                                 // warp-uniform
+                    const float qv = s_qv[slot][j];
+                    const float* ws = wsrc + s_woff[slot][j];
+                    const uint16_t* ds = dsrc + s_doff[slot][j];
+                    for (int i = lo + lane; i < hi; i += 32) {
+                        const int d = ds[i];
+                        acc[d] = fmaf(qv, ws[i], acc[d]);
+                        if (bitmap) atomicOr(&touched[d >> 5], 1u << (d & 31));
+                    }
+                    __syncwarp();
+                }
+            }
+            SP_MARK(SPS_ACC);
+        } else {
+            // ---- block-level path: all term groups in ascending term order, a block barrier between lists
+            int prev_pw = 0;
+            accumulate_group(slot, buf, bitmap, prev_pw);
+            for (int g = 1; g < n_groups; ++g) {               // queries with more than SP_TG terms: unstaged, unpipelined
+                __syncthreads();
+                load_term(g);
+                long long rb;
+                int rl;
+                fetch_range(blk, rb, rl);
+                publish(SP_RING, rb, rl, false);
+                __syncthreads();
+                prev_pw = 0;                                   // (the barrier above already ordered the previous group)
+                accumulate_group(SP_RING, buf, bitmap, prev_pw);
+            }
             __syncthreads();
-            prev_pw = 0;                                       // (the barrier above already ordered the previous group)
-            accumulate_group(SP_RING, buf, bitmap, prev_pw);
+            SP_MARK(SPS_ACC);
         }
-        __syncthreads();
-        SP_MARK(SPS_ACC);
         if (stats && tid == 0) {
             s_stat[SPS_BLOCKS] += 1;
             s_stat[SPS_BITMAP_BLOCKS] += bitmap ? 1 : 0;
             s_stat[SPS_POSTINGS] += (unsigned long long)s_off[slot][SP_TG];
-            for (int j = 0; j < SP_TG; ++j) s_stat[SPS_UNSTAGED] += (unsigned long long)(s_len[slot][j] - s_slen[slot][j]);
+            s_stat[SPS_UNSTAGED] += fast ? 0 : 1;
         }
         // ---- collect (repeated while the staging list overflows)
         for (;;) {
-            if (bitmap) {
-                collect_bitmap(thr_f, doc0);
+            if (fast) {
+                if (bitmap) {
+                    collect_bitmap(thr_f, doc0, warp * sub_words, (warp + 1) * sub_words, lane, 32);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < SP_TG; ++j) {
+                        const int lo = s_bnd[j][warp], hi = s_bnd[j][warp + 1];
+                        if (lo < hi) {
+                            const uint16_t* ds = dsrc + s_doff[slot][j];
+                            for (int i = lo + lane; i < hi; i += 32) {
+                                const int d = ds[i];
+                                const float sc = acc[d];       // the document's final score; 0 if an earlier list took it
+                                acc[d] = 0.0f;
+                                if (sc >= thr_f) {
+                                    bool ok = true;
+                                    if (p.doc_mask) {
+                                        const int64_t g = doc0 + d;
+                                        ok = (__ldg(p.doc_mask + (g >> 5)) >> (g & 31)) & 1u;
+                                    }
+                                    if (ok && !stage((uint32_t)(doc0 + d), sc)) acc[d] = sc;   // list full: next pass
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            } else if (bitmap) {
+                collect_bitmap(thr_f, doc0, 0, n_words, tid, SP_THREADS);
             } else {
                 collect_group_exch(slot, buf, thr_f, doc0);
                 for (int g = 1; g < n_groups; ++g) {
@@ -390,6 +468,9 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sparse_query_kernel(const Spars
             __syncthreads();
             const int staged_raw = s_nstage;
             SP_MARK(SPS_COLLECT);
+            // the list is drained when it is half full (or overflowed, or the walk ends): each drain costs two barriers per
+            // 256 survivors plus, now and then, a compaction of the top-k buffer
+            if (staged_raw <= SP_STAGE / 2 && blk + 1 < b1) break;
             if (staged_raw == 0) break;
             const int staged = staged_raw < SP_STAGE ? staged_raw : SP_STAGE;
             for (int base = 0; base < staged; base += SP_THREADS) {
@@ -400,7 +481,7 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sparse_query_kernel(const Spars
                 bool have = false;
                 if (i < staged) {
                     h = (uint64_t)mono32(stage_sc[i]);
-                    l = ~(uint32_t)(doc0 + stage_doc[i]);
+                    l = ~stage_doc[i];
                     have = tk.passes(tv, h, l);
                 }
                 tk.append(tv, have, h, l);

@@ -1,7 +1,7 @@
 """Same-box A/B of the sparse scan (BASELINE config 4's BM25 side: 1M documents, 100K-term Zipf vocabulary, 256 queries of
 8 terms, top-500) under the kernel's switches:
 
-    option "sparse_flags"   bit 0 = touched-bitmap collect only (no exchange collect); default 0
+    option "sparse_flags"   bit 0 = touched-bitmap collect only, bit 1 = no shared-memory staging, bit 2 = no warp-private path
     option "sparse_slices"  slices per query (0 = the library's choice)
     --block-docs a,b,...    documents per postings block
     --variants flags:slices,...
@@ -94,7 +94,9 @@ for bd in [int(x) for x in args.block_docs.split(",")]:
             print(f"    {len(used)} CTAs; cycles per CTA: mean {tot.mean():.0f}  min {tot.min():.0f}  max {tot.max():.0f}; per CTA: "
                   f"{used[:, 4].mean():.1f} blocks ({used[:, 7].mean():.1f} on the bitmap path), {used[:, 8].mean():.0f} postings, "
                   f"{used[:, 5].mean():.0f} survivors staged, {used[:, 6].mean():.2f} collect re-runs")
-            for i, n_ in ((0, "init + finalize"), (1, "accumulate"), (2, "collect"), (3, "drain to top-k")):
+            tot = used[:, [0, 1, 2, 3, 9]].sum(1)
+            print(f"    blocks on the block-level path per CTA: {used[:, 10].mean():.1f}")
+            for i, n_ in ((0, "init + finalize"), (9, "block top (wait)"), (1, "accumulate"), (2, "collect"), (3, "drain to top-k")):
                 v = used[:, i].mean()
                 print(f"    {n_:18s} {v:10.0f} cycles  {100 * v / tot.mean():5.1f}%")
     del idx
