@@ -26,8 +26,7 @@
 // that are not a power of two >= 256) take the block-level path: same arithmetic, a block barrier between terms, postings read
 // in place.  Slices of one query share their thresholds through a global atomicMax.  Algorithmic HBM traffic = 6 bytes per
 // posting of the query's terms.  grid = (queries, slices); merge_topk_kernel reduces the slices.
-#include "common.cuh"
-#include "select.cuh"
+#include "sparse.cuh"
 
 namespace b200rag {
 
@@ -46,28 +45,6 @@ constexpr int SP_MAX_SLICES = 32;
 
 enum { SPS_TOTAL = 0, SPS_ACC, SPS_COLLECT, SPS_DRAIN, SPS_BLOCKS, SPS_STAGED, SPS_RESCANS, SPS_BITMAP_BLOCKS, SPS_POSTINGS,
        SPS_WAIT, SPS_UNSTAGED };
-
-struct SparseParams {
-    const int64_t* blk_term_ptr;
-    const uint16_t* post_doc;
-    const float* post_w;
-    int64_t n_docs;
-    int n_terms, block_docs, n_blocks, n_slices;
-    const int64_t* q_ptr;
-    const int32_t* q_terms;
-    const float* q_vals;
-    int k, cap;
-    int64_t id_offset;
-    double* part_scores;        // [n_queries][n_slices][k]   (n_slices > 1)
-    int64_t* part_ids;
-    float* out_scores;          // [n_queries][k]             (n_slices == 1: written directly)
-    int64_t* out_ids;
-    int32_t* out_counts;
-    unsigned int* gthr;         // [n_queries] mono32 keys of the best k-th score any slice has established (n_slices > 1)
-    const uint32_t* doc_mask;
-    int flags;                  // bit 0: never use the exchange collect; bit 1: no shared-memory staging of the postings (A/B)
-    unsigned long long* stats;
-};
 
 __device__ __forceinline__ void sp_cp_async4(void* smem_dst, const void* gsrc, unsigned src_bytes) {
     // 4-byte asynchronous global -> shared copy; src_bytes < 4 zero-fills the rest (nothing beyond src_bytes is read)
@@ -95,6 +72,10 @@ __global__ void __launch_bounds__(SP_THREADS, 2) sparse_query_kernel(const Spars
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = blockIdx.x, slice = blockIdx.y;
+    {   // queries of up to p.mask_max_terms terms are served by sparse_mask_kernel (sparse_mask.cu); this CTA has nothing to do
+        const int nq0 = (int)(p.q_ptr[q + 1] - p.q_ptr[q]);
+        if (nq0 <= p.mask_max_terms) return;
+    }
     const int block_docs = p.block_docs, n_words = block_docs >> 5;
     float* acc = reinterpret_cast<float*>(smem);                                     // [block_docs]
     uint32_t* touched = reinterpret_cast<uint32_t*>(acc + block_docs);                // [n_words]
@@ -600,11 +581,6 @@ int b200rag_sparse_topk_masked(const int64_t* blk_term_ptr, const uint16_t* post
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SparseParams p;
     size_t smem = sparse_smem(block_docs, k, &p.cap);
-    if (smem > 225 * 1024) {
-        set_error("sparse_topk: block_docs=%d with k=%d needs %zu bytes of shared memory (max 230400); use a smaller block",
-                  block_docs, k, smem);
-        return B200RAG_E_UNSUPPORTED;
-    }
     int64_t n_blocks = (n_docs + block_docs - 1) / block_docs;
     if (n_blocks < 1) n_blocks = 1;
     B200_REQUIRE(n_queries <= 2147483647 && n_blocks <= 2147483647, "sparse_topk: too many blocks");
@@ -639,6 +615,22 @@ int b200rag_sparse_topk_masked(const int64_t* blk_term_ptr, const uint16_t* post
     p.flags = option(OPT_SPARSE_FLAGS, 0);
     p.stats = stats_buffer(STATS_SPARSE, (size_t)SP_STAT_CTAS * SP_NSTAT);
     if (p.stats) B200_CUDA_CHECK(cudaMemsetAsync(p.stats, 0, (size_t)SP_STAT_CTAS * SP_NSTAT * 8, st));
+    // Queries of up to 15 terms: the mask kernel (sparse_mask.cu), the product path.  Longer queries: the accumulator kernel of
+    // this file.  How long the queries are is only known on the device, so both are launched and every CTA of the kernel that
+    // does not serve its query leaves at once.
+    if (smem > 225 * 1024) {
+        set_error("sparse_topk: block_docs=%d with k=%d needs %zu bytes of shared memory (max 230400); use a smaller block",
+                  block_docs, k, smem);
+        return B200RAG_E_UNSUPPORTED;
+    }
+    const size_t mask_smem = sparse_mask_smem(block_docs, k, nullptr);
+    const bool use_mask = !(p.flags & 8) && mask_smem <= 225 * 1024 && ((uintptr_t)post_doc & 15) == 0 && ((uintptr_t)post_w & 15) == 0 &&
+                          block_docs % 8 == 0;
+    p.mask_max_terms = use_mask ? SPM_MAX_TERMS : -1;
+    if (use_mask) {
+        int rc = launch_sparse_mask(p, n_queries, st);
+        if (rc) return rc;
+    }
     B200_CUDA_CHECK(cudaFuncSetAttribute(sparse_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)n_queries, (unsigned)n_slices);
     sparse_query_kernel<<<grid, SP_THREADS, smem, st>>>(p); count_launch();

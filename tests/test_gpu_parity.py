@@ -157,8 +157,8 @@ def test_sparse_long_walk_both_collect_modes(eng, oracle_lib, signed):
 
 def test_sparse_full_size_collect_paths_agree(eng):
     """BASELINE config 4's sparse side at full size (1M documents, 100K-term Zipf vocabulary, 256 queries of 8 terms, top-500;
-    too large for the CPU oracle inside a test): the kernel's collect paths (exchange collect vs touched-bitmap walk only)
-    and slicings (1, 2, 5 slices per query) must return bit-identical lists; the lists are sorted by (score desc, id asc);
+    too large for the CPU oracle inside a test): the two sparse kernels (term-mask kernel, accumulator kernel), staged and
+    unstaged postings, and different slicings (1, 2, 5 slices per query) must return bit-identical lists; the lists are sorted by (score desc, id asc);
     and the scores agree with an fp64 recomputation from the CSR.  (The oracle itself checks the same walk at 16384-document
     blocks x 9 blocks in test_sparse_16384_blocks_long_walk_matches_oracle.)"""
     from b200rag import _lib
@@ -172,7 +172,7 @@ def test_sparse_full_size_collect_paths_agree(eng):
     got = {}
     try:
         for flags in ("0", "1", "2", "3"):
-            _lib.set_option("sparse_flags", 1 if flags == "1" else 0)
+            _lib.set_option("sparse_flags", {"0": 0, "1": 8, "2": 2, "3": 0}[flags])      # 8: accumulator kernel, 2: no staging
             _lib.set_option("sparse_slices", {"0": -1, "1": -1, "2": 1, "3": 5}[flags])
             s, i, c = idx.search(qp, qt, qv, k)
             torch.cuda.synchronize()

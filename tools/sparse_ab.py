@@ -1,7 +1,7 @@
 """Same-box A/B of the sparse scan (BASELINE config 4's BM25 side: 1M documents, 100K-term Zipf vocabulary, 256 queries of
 8 terms, top-500) under the kernel's switches:
 
-    option "sparse_flags"   bit 0 = touched-bitmap collect only, bit 1 = no shared-memory staging, bit 2 = no warp-private path
+    option "sparse_flags"   bit 1 (2) = no shared-memory staging, bit 3 (8) = accumulator kernel for every query
     option "sparse_slices"  slices per query (0 = the library's choice)
     --block-docs a,b,...    documents per postings block
     --variants flags:slices,...
@@ -90,13 +90,11 @@ for bd in [int(x) for x in args.block_docs.split(",")]:
             lib.b200rag_debug_set_stats_buffer(1, None, 0)
             used = buf.cpu().numpy().astype(np.float64)
             used = used[used.sum(1) > 0]
-            tot = used[:, :4].sum(1)
-            print(f"    {len(used)} CTAs; cycles per CTA: mean {tot.mean():.0f}  min {tot.min():.0f}  max {tot.max():.0f}; per CTA: "
-                  f"{used[:, 4].mean():.1f} blocks ({used[:, 7].mean():.1f} on the bitmap path), {used[:, 8].mean():.0f} postings, "
-                  f"{used[:, 5].mean():.0f} survivors staged, {used[:, 6].mean():.2f} collect re-runs")
             tot = used[:, [0, 1, 2, 3, 9]].sum(1)
-            print(f"    blocks on the block-level path per CTA: {used[:, 10].mean():.1f}")
-            for i, n_ in ((0, "init + finalize"), (9, "block top (wait)"), (1, "accumulate"), (2, "collect"), (3, "drain to top-k")):
+            print(f"    {len(used)} CTAs; cycles per CTA: mean {tot.mean():.0f}  min {tot.min():.0f}  max {tot.max():.0f}; per CTA: "
+                  f"{used[:, 4].mean():.1f} blocks ({used[:, 10].mean():.1f} not staged), {used[:, 8].mean():.0f} postings, "
+                  f"{used[:, 7].mean():.0f} extra terms chained, {used[:, 5].mean():.0f} survivors staged, {used[:, 6].mean():.2f} score re-runs")
+            for i, n_ in ((0, "init + finalize"), (9, "block top (wait)"), (1, "mark"), (2, "score"), (3, "drain to top-k")):
                 v = used[:, i].mean()
                 print(f"    {n_:18s} {v:10.0f} cycles  {100 * v / tot.mean():5.1f}%")
     del idx
