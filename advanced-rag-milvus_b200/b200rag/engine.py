@@ -253,6 +253,50 @@ def mmr_select(cand_doc: torch.Tensor, cand_rel: torch.Tensor, cand_n: torch.Ten
     return picks, n
 
 
+def rerank_learned(scores: torch.Tensor, method_mask: torch.Tensor, n: torch.Tensor, k_out: int, base_weight: float = 1.0,
+                   method_bonus: float = 0.1, recency_weight: float = 0.0, recency: Optional[torch.Tensor] = None
+                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """LearnedRanker re-rank of a fused batch (reference ranker.py:109-125 + retrieval.py:518-563): scores f64 [B,T], method
+    masks i32 [B,T], valid counts i32 [B] -> (positions i32 [B,k_out] into the input, -1 padded; re-ranked scores f64; counts)."""
+    for t, nm in ((scores, "scores"), (method_mask, "method_mask"), (n, "n")):
+        _require_cuda(t, nm)
+    if (scores.dtype, method_mask.dtype, n.dtype) != (torch.float64, torch.int32, torch.int32) or scores.shape != method_mask.shape:
+        raise ValueError("rerank_learned expects f64 scores, i32 masks of the same [B, T] shape and i32 counts")
+    if recency is not None and (recency.dtype != torch.float64 or recency.shape != scores.shape or not recency.is_cuda):
+        raise ValueError("recency must be a CUDA f64 tensor shaped like scores")
+    b, t_max = scores.shape
+    dev = scores.device
+    pos = torch.empty((b, k_out), dtype=torch.int32, device=dev)
+    out = torch.empty((b, k_out), dtype=torch.float64, device=dev)
+    cnt = torch.empty((b,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().b200rag_rerank_learned(scores.data_ptr(), method_mask.data_ptr(),
+                                                 recency.contiguous().data_ptr() if recency is not None else None, n.data_ptr(), b,
+                                                 t_max, float(base_weight), float(method_bonus), float(recency_weight), int(k_out),
+                                                 pos.data_ptr(), out.data_ptr(), cnt.data_ptr(), _stream_ptr(dev)))
+    return pos, out, cnt
+
+
+def pairwise_jaccard(docs: torch.Tensor, n: torch.Tensor, doc_tok_ptr: torch.Tensor, doc_tok_ids: torch.Tensor
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Mean pairwise token-set Jaccard per result list (reference evaluation.py:327-344): docs i32 [B, n_max] rows in the token
+    CSR, n i32 [B] -> (mean f64 [B], pairs averaged i32 [B]).  diversity = 1 - mean (evaluation.py:315-325)."""
+    for t, nm in ((docs, "docs"), (n, "n"), (doc_tok_ptr, "doc_tok_ptr"), (doc_tok_ids, "doc_tok_ids")):
+        _require_cuda(t, nm)
+    if (docs.dtype, n.dtype, doc_tok_ptr.dtype, doc_tok_ids.dtype) != (torch.int32, torch.int32, torch.int64, torch.int32):
+        raise ValueError("pairwise_jaccard: wrong tensor dtypes")
+    b, n_max = docs.shape
+    dev = docs.device
+    mean = torch.empty((b,), dtype=torch.float64, device=dev)
+    pairs = torch.empty((b,), dtype=torch.int32, device=dev)
+    L = _lib.load()
+    ws = _WS.get(dev, L.b200rag_pairwise_jaccard_workspace_bytes(b, n_max))
+    with torch.cuda.device(dev):
+        check(L.b200rag_pairwise_jaccard(docs.data_ptr(), n.data_ptr(), b, n_max, doc_tok_ptr.data_ptr(), doc_tok_ids.data_ptr(),
+                                         mean.data_ptr(), pairs.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)))
+    return mean, pairs
+
+
 class DenseIndex:
     """A contiguous row shard of 16-bit vectors in HBM with exact inner-product / cosine search.
 

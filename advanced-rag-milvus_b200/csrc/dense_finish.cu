@@ -33,8 +33,12 @@ template <int DTYPE>
 __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishParams p) {
     extern __shared__ __align__(16) char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q = blockIdx.x;
-    const int qb = q / TC_BM, ql = q % TC_BM;
+    // slot = position of the query in THIS launch's query block matrix (candidate buffers, thresholds); q = the query the
+    // results belong to.  They differ in the tier-0 re-scan, which packs the flagged queries of the first pass.
+    const int slot_q = blockIdx.x;
+    if (p.gate && slot_q >= __ldg(p.gate)) return;
+    const int q = p.q_list ? __ldg(p.q_list + slot_q) : slot_q;
+    const int qb = slot_q / TC_BM, ql = slot_q % TC_BM;
     const int sel_cap = finish2_sel_cap(p.kprime);
     float* qf = reinterpret_cast<float*>(smem);                                           // [dim] the query, exact in fp32
     unsigned long long* buf = reinterpret_cast<unsigned long long*>(qf + p.dim);          // [sel_cap] (score bits << 32) | row
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
             s_n = cnt;
             // m: every row outside the candidate set has tensor-core score <= m (-inf if nothing was ever dropped): the scan
             // drops a row only below a threshold it pushed to gthr, the merge above only at or below its last threshold
-            const unsigned int gk = p.gthr[q];
+            const unsigned int gk = p.gthr[slot_q];
             s_m = fmaxf(compacted ? thr : -CUDART_INF_F, gk ? unmono32(gk) : -CUDART_INF_F);
             s_err = 0.f;
             s_ek_sh = -CUDART_INF;
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
         // proven complete iff nothing was dropped (m = -inf) or the k-th exact score clears m + eps
         const bool proven = (m == -CUDART_INF_F) || (n >= p.k && s_ek_sh > (double)m + eps);
         const int flag = proven ? 0 : 1;
-        if (p.out_flags) p.out_flags[q] = flag;
+        if (p.out_flags) p.out_flags[q] = flag | (p.q_list ? 2 : 0);      // bit 1: the query went through the tier-0 re-scan
         if (flag) p.flag_list[atomicAdd(p.n_flagged, 1)] = q;
         if (p.err_max) p.err_max[q] = s_err;
     }

@@ -407,6 +407,31 @@ sample_threshold_kernel(const unsigned long long* __restrict__ cand, const int* 
     if (tid == 0) gthr[q] = tk.count() >= rank ? (unsigned int)tk.out_hi()[rank - 1] : 0u;
 }
 
+// ----------------------------------------------------------------------------------------------- tier-0 gather
+// Packs the queries the first pass flagged into a fresh query block matrix (zero rows behind them), publishes how many there
+// are (the device-side gate of the re-scan and its finish), and moves the flagged queries beyond the tier's capacity to the
+// exact scan's list.  One warp per slot.
+__global__ void __launch_bounds__(128)
+tier0_gather_kernel(const uint16_t* __restrict__ queries, const int32_t* __restrict__ flag_list, const int32_t* __restrict__ n_flagged,
+                    int dim, int n_slots, int max_served, uint16_t* __restrict__ q_out, int32_t* __restrict__ gate,
+                    int32_t* __restrict__ flag_list2) {
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int nf = __ldg(n_flagged);
+    const int served = nf < max_served ? nf : max_served;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { gate[0] = served; gate[1] = nf - served; }
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < nf - served; i += blockDim.x) flag_list2[i] = flag_list[served + i];
+    if (slot >= n_slots) return;
+    uint4* dst = reinterpret_cast<uint4*>(q_out + (size_t)slot * dim);
+    if (slot < served) {
+        const uint4* src = reinterpret_cast<const uint4*>(queries + (size_t)__ldg(flag_list + slot) * dim);
+        for (int c = lane; c < dim / 8; c += 32) dst[c] = __ldg(src + c);
+    } else if (nf > 0) {                                 // (nothing flagged: the re-scan is gated off and never reads the block)
+        for (int c = lane; c < dim / 8; c += 32) dst[c] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 // ----------------------------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -456,7 +481,13 @@ struct TensorPlan {
     int stage_rows;
     size_t scan_smem, finish_smem;
     size_t off_cand, off_cnt, off_gthr, off_flaglist, off_nflag, off_stats, off_qpad, off_exact, total;
+    // tier 0: flagged queries re-scanned on the tensor path with the widest candidate set the kernels support
+    int t0, t0_nq, t0_nqb, t0_kprime, t0_cap, t0_span, t0_chunks, t0_items, t0_clusters;
+    size_t t0_smem, off_t0_cand, off_t0_cnt, off_t0_gthr, off_t0_q, off_t0_gate, off_flaglist2;
 };
+
+constexpr int TC_T0_MAX_QUERIES = 1024;   // flagged queries one tier-0 pass serves (the rest go straight to the exact scan)
+constexpr int TC_T0_KPRIME = 640;         // = TC_MAX_C / 2: tie groups of up to ~500 rows around rank k are resolved
 
 static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
 
@@ -554,6 +585,34 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     pl.off_flaglist = take((size_t)n_q * 4);
     pl.off_qpad = take((size_t)pl.nqb * TC_BM * dim * 2);      // query block padded with zero rows (no TMA out-of-bounds rows)
     pl.off_nflag = take(256);
+    // tier 0 (CTA-pair scan generation only; pointless when the first pass already runs at the widest k')
+    pl.t0 = option(OPT_NO_TIER0, 0) == 0 && pl.kprime < TC_T0_KPRIME && n_rows > 0;
+    if (pl.t0) {
+        pl.t0_nq = n_q < TC_T0_MAX_QUERIES ? n_q : TC_T0_MAX_QUERIES;
+        pl.t0_nqb = 2 * ((pl.t0_nq + 2 * TC_BM - 1) / (2 * TC_BM));
+        pl.t0_kprime = TC_T0_KPRIME;
+        pl.t0_cap = tc_bufcap(pl.t0_kprime);
+        const int qg = pl.t0_nqb / 2;
+        pl.t0_span = qg < TC_QG_SPAN_MAX ? qg : TC_QG_SPAN_MAX;
+        while (pl.t0_span > 1 && scan3_smem_bytes(pl.t0_cap, pl.t0_span) > TC_SMEM_LIMIT) --pl.t0_span;
+        pl.t0_smem = scan3_smem_bytes(pl.t0_cap, pl.t0_span);
+        pl.t0_clusters = scan3_max_clusters(pl.t0_cap, pl.t0_span, pl.sm_count);
+        const int spans = (qg + pl.t0_span - 1) / pl.t0_span;
+        const int want_t0 = pl.t0_clusters / gcd_int(spans, pl.t0_clusters);
+        const int tiles3 = (int)((n_rows + 255) / 256);
+        pl.t0_chunks = want_t0 < tiles3 ? want_t0 : tiles3;
+        if (pl.t0_chunks < 1) pl.t0_chunks = 1;
+        pl.t0_items = spans * pl.t0_chunks;
+        if (pl.t0_smem > TC_SMEM_LIMIT || finish2_smem_bytes(dim, pl.t0_kprime) > 200 * 1024) pl.t0 = 0;
+    }
+    if (pl.t0) {
+        pl.off_t0_cand = take((size_t)pl.t0_chunks * pl.t0_nqb * TC_BM * pl.t0_cap * 8);
+        pl.off_t0_cnt = take((size_t)pl.t0_chunks * pl.t0_nqb * TC_BM * 4);
+        pl.off_t0_gthr = take((size_t)pl.t0_nqb * TC_BM * 4);
+        pl.off_t0_q = take((size_t)pl.t0_nqb * TC_BM * dim * 2);
+        pl.off_t0_gate = take(256);                          // [0] live tier-0 slots, [1] queries left for the exact scan
+        pl.off_flaglist2 = take((size_t)n_q * 4);
+    }
     pl.off_stats = take((size_t)256 * ST_N * 8);
     {   // exact fallback, tier A (<= TC_FALLBACK_BATCH queries) and tier B (the rest): they run one after the other in the same region
         const int na = n_q < TC_FALLBACK_BATCH ? n_q : TC_FALLBACK_BATCH;
@@ -623,6 +682,7 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
         }
         sp.queries = static_cast<const uint16_t*>(q_scan);
         sp.row_mask = row_mask;
+        sp.gate = nullptr;
         // per-role cycle counters go to the caller's buffer of this thread (b200rag_debug_set_stats_buffer), if any
         sp.stats = stats_buffer(STATS_SCAN, (size_t)256 * ST_N);
         if (sp.stats) B200_CUDA_CHECK(cudaMemsetAsync(sp.stats, 0, (size_t)256 * ST_N * 8, st));
@@ -723,19 +783,77 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
     }
     B200_CUDA_CHECK(cudaGetLastError());
 
+    const int32_t* fb_list = flag_list;          // what the exact scan has to redo: all flagged queries, unless tier 0 runs first
+    const int32_t* fb_count = n_flagged;
+    if (with_fallback && pl.t0) {
+        // Tier 0: the flagged queries once more on the tensor path, with k' = 640 candidates instead of k + 28.  A query is
+        // flagged when rows tie (to within the fp32 error band) across the edge of its candidate set -- duplicated chunks,
+        // boilerplate -- and a tie group of up to ~500 rows fits the wider set, so the proof then succeeds and the ~100x
+        // slower CUDA-core scan is not needed.  Gated on the device by the flagged-query count: no host round trip, and a
+        // batch without flagged queries pays three empty launches.
+        uint16_t* q_t0 = reinterpret_cast<uint16_t*>(ws + pl.off_t0_q);
+        int32_t* gate = reinterpret_cast<int32_t*>(ws + pl.off_t0_gate);
+        int32_t* flag_list2 = reinterpret_cast<int32_t*>(ws + pl.off_flaglist2);
+        const int n_slots = pl.t0_nqb * TC_BM;
+        B200_CUDA_CHECK(cudaMemsetAsync(ws + pl.off_t0_gthr, 0, (size_t)n_slots * 4, st));
+        tier0_gather_kernel<<<(n_slots + 3) / 4, 128, 0, st>>>(static_cast<const uint16_t*>(queries16), flag_list, n_flagged, dim, n_slots,
+                                                               pl.t0_nq, q_t0, gate, flag_list2); count_launch();
+        B200_CUDA_CHECK(cudaGetLastError());
+        ScanParams st0;
+        st0.n_rows = n_rows;
+        st0.n_q = n_slots;
+        st0.dim = dim;
+        st0.n_kblocks = (dim + TC_BK - 1) / TC_BK;
+        st0.n_tiles = (int)((n_rows + 255) / 256);
+        st0.tile_stride = 1;
+        st0.nqb = pl.t0_nqb;
+        st0.n_chunks = pl.t0_chunks;
+        st0.n_items = pl.t0_items;
+        st0.qg_span = pl.t0_span;
+        st0.kprime = pl.t0_kprime;
+        st0.cap = pl.t0_cap;
+        st0.sample = 0;
+        st0.idesc = umma_idesc_mn(dtype, 2 * TC_BM, 256);
+        st0.cand = reinterpret_cast<unsigned long long*>(ws + pl.off_t0_cand);
+        st0.cand_cnt = reinterpret_cast<int*>(ws + pl.off_t0_cnt);
+        st0.gthr = reinterpret_cast<unsigned int*>(ws + pl.off_t0_gthr);
+        st0.queries = q_t0;
+        st0.row_mask = row_mask;
+        st0.stats = nullptr;
+        st0.gate = gate;
+        int rc = launch_scan3(corpus16, dtype, st0, pl.t0_clusters, pl.t0_cap, pl.t0_span, st);
+        if (rc) return rc;
+        FinishParams f0 = fp;
+        f0.n_q = n_slots;
+        f0.kprime = pl.t0_kprime;
+        f0.cap = pl.t0_cap;
+        f0.nqb = pl.t0_nqb;
+        f0.n_chunks = pl.t0_chunks;
+        f0.cand = st0.cand;
+        f0.cand_cnt = st0.cand_cnt;
+        f0.gthr = st0.gthr;
+        f0.flag_list = flag_list2;
+        f0.n_flagged = gate + 1;
+        f0.q_list = flag_list;
+        f0.gate = gate;
+        rc = launch_finish2(f0, dtype, st);
+        if (rc) return rc;
+        fb_list = flag_list2;
+        fb_count = gate + 1;
+    }
     if (with_fallback) {
-        // AUTO: results must be exact for every query, so the flagged ones are re-run on the exact path -- without a host
-        // round trip: the exact scan is launched unconditionally over the flag list and gated ON THE DEVICE by the
+        // AUTO: results must be exact for every query, so the queries that are still flagged are re-run on the exact path --
+        // without a host round trip: the exact scan is launched unconditionally over the flag list and gated ON THE DEVICE by the
         // flagged-query counter (CTAs of unused slots leave at once).  Tier A covers the first TC_FALLBACK_BATCH flagged
         // queries with a many-chunk plan (the usual case: zero, one or a few of them); tier B covers every further slot
         // with the few-chunk plan of a large batch and only does work on pathological inputs (massive ties).
         const int na = n_q < TC_FALLBACK_BATCH ? n_q : TC_FALLBACK_BATCH;
-        int rc = run_exact(corpus16, n_rows, dim, dtype, queries16, na, flag_list, k, id_offset, out_scores, out_ids,
-                           ws + pl.off_exact, pl.total - pl.off_exact, st, n_flagged, 0, row_mask);
+        int rc = run_exact(corpus16, n_rows, dim, dtype, queries16, na, fb_list, k, id_offset, out_scores, out_ids,
+                           ws + pl.off_exact, pl.total - pl.off_exact, st, fb_count, 0, row_mask);
         if (rc) return rc;
         if (n_q > na) {
-            rc = run_exact(corpus16, n_rows, dim, dtype, queries16, n_q - na, flag_list + na, k, id_offset, out_scores, out_ids,
-                           ws + pl.off_exact, pl.total - pl.off_exact, st, n_flagged, na, row_mask);
+            rc = run_exact(corpus16, n_rows, dim, dtype, queries16, n_q - na, fb_list + na, k, id_offset, out_scores, out_ids,
+                           ws + pl.off_exact, pl.total - pl.off_exact, st, fb_count, na, row_mask);
             if (rc) return rc;
         }
     }

@@ -59,8 +59,11 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1;
     const int n_clusters = gridDim.x >> 1;
-    const int qgroups = p.nqb >> 1;                     // nqb is padded to an even number of query blocks
-    const int n_spans = (qgroups + p.qg_span - 1) / p.qg_span;
+    const int qgroups_all = p.nqb >> 1;                 // nqb is padded to an even number of query blocks
+    const int n_spans = (qgroups_all + p.qg_span - 1) / p.qg_span;
+    // device-side gate (tier-0 re-scan of flagged queries): only the first *gate queries exist; pairs of query blocks beyond
+    // them are skipped by every role alike, so a launch with nothing to do costs a few microseconds
+    const int qgroups = p.gate ? min(qgroups_all, (__ldg(p.gate) + 2 * TC_BM - 1) / (2 * TC_BM)) : qgroups_all;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
@@ -89,9 +92,10 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             ST_T0(st_begin);
             for (int item = cluster_id; item < p.n_items; item += n_clusters) {
                 const int chunk = item / n_spans, qg0 = (item % n_spans) * p.qg_span;
-                const int qg1 = min(qg0 + p.qg_span, qgroups);
+                const int qg1 = max(qg0, min(qg0 + p.qg_span, qgroups));
                 const int t0 = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
                 const int t1 = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
+                if (qg1 == qg0) continue;
                 for (int tile = t0; tile < t1; ++tile) {
                     const int xrow = tile * p.tile_stride * T3_BN + rank * T3_HALF;
                     for (int qg = qg0; qg < qg1; ++qg) {
@@ -124,7 +128,7 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             ST_T0(st_begin);
             for (int item = cluster_id; item < p.n_items; item += n_clusters) {
                 const int chunk = item / n_spans, qg0 = (item % n_spans) * p.qg_span;
-                const int n_acc = (min(qg0 + p.qg_span, qgroups) - qg0) *
+                const int n_acc = max(0, min(qg0 + p.qg_span, qgroups) - qg0) *
                                   ((int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks) - (int)((int64_t)chunk * p.n_tiles / p.n_chunks));
                 for (int acc = 0; acc < n_acc; ++acc) {       // one accumulator per (tile, pair of query blocks)
                     ST_T0(te);
@@ -173,9 +177,10 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         ST_T0(st_begin);
         for (int item = cluster_id; item < p.n_items; item += n_clusters) {
             const int chunk = item / n_spans, qg0 = (item % n_spans) * p.qg_span;
-            const int qg1 = min(qg0 + p.qg_span, qgroups);
+            const int qg1 = max(qg0, min(qg0 + p.qg_span, qgroups));
             const int t0 = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
             const int t1 = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
+            if (qg1 == qg0) continue;
             if (p.sample) {
                 // ---- SAMPLE pass (qg_span == 1): best group maxima in registers
                 const int qb = qg0 * 2 + rank;

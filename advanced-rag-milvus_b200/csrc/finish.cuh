@@ -28,6 +28,9 @@ struct FinishParams {
     int32_t* flag_list;   // compacted list of flagged queries
     int32_t* n_flagged;
     float* err_max;       // optional [n_q]: max |tensor score - exact score| over the re-scored candidates
+    // tier-0 re-scan (dense_finish.cu only): launch slot -> original query, and the number of live slots (device scalar)
+    const int32_t* q_list = nullptr;
+    const int32_t* gate = nullptr;
 };
 
 

@@ -35,6 +35,7 @@ constexpr int SPM_RING = 3;
 constexpr int SPM_NSTAT = 12;
 constexpr int SPM_STAT_CTAS = 1024;
 constexpr uint32_t SPM_DONE = 0x8000u;
+constexpr int SPM_MULTI = 1024;      // queued multi-term documents per score pass (more are chained inline)
 
 enum { SMS_TOTAL = 0, SMS_MARK, SMS_SCORE, SMS_DRAIN, SMS_BLOCKS, SMS_STAGED, SMS_RESCANS, SMS_MULTI, SMS_POSTINGS, SMS_WAIT, SMS_UNSTAGED };
 
@@ -58,7 +59,8 @@ __global__ void __launch_bounds__(SPM_THREADS, 2) sparse_mask_kernel(const Spars
     extern __shared__ __align__(16) char smem[];
     __shared__ SpmSlot s_slot[SPM_RING];
     __shared__ float s_qv[SPM_TG];
-    __shared__ int s_nstage;
+    __shared__ int s_nstage, s_nmulti;
+    __shared__ uint32_t multi[SPM_MULTI];            // owners of multi-term documents of the current block: (list << 16) | posting
     __shared__ unsigned int s_gthr;
     __shared__ unsigned long long s_stat[SPM_NSTAT];
     __shared__ long long s_last;
@@ -243,6 +245,27 @@ __global__ void __launch_bounds__(SPM_THREADS, 2) sparse_mask_kernel(const Spars
         auto w_at = [&](int j, int i) -> float {
             return staged ? swb[s.wbase[j] + i] : __ldg(p.post_w + s.beg[j] + i);
         };
+        // the canonical chain of a document whose lowest term is list j (posting i): its own weight, then every further term
+        // of its mask in ascending order, each found by binary search in that term's row-sorted list
+        auto chain_score = [&](int j, int i, int d, uint32_t m) -> float {
+            float sc = fmaf(s_qv[j], w_at(j, i), 0.0f);
+            uint32_t rest = (m & ~SPM_DONE) >> (j + 1);
+            int j2 = j + 1;
+            while (rest) {
+                const int sk = __ffs((int)rest) - 1;
+                j2 += sk;
+                rest >>= sk + 1;
+                int lo = 0, hi = s.len[j2];
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (row_at(j2, mid) < d) lo = mid + 1;
+                    else hi = mid;
+                }
+                sc = fmaf(s_qv[j2], w_at(j2, lo), sc);
+                ++j2;
+            }
+            return sc;
+        };
         // ---- mark: which of the query's terms does every document of the block hold?
         {
             int j = 0;
@@ -259,40 +282,50 @@ __global__ void __launch_bounds__(SPM_THREADS, 2) sparse_mask_kernel(const Spars
             s_stat[SMS_POSTINGS] += (unsigned long long)total;
             s_stat[SMS_UNSTAGED] += staged ? 0 : 1;
         }
-        // ---- score (repeated while the survivor list overflows)
+        // ---- score (repeated while the survivor list overflows).  Documents with ONE query term -- the great majority -- are
+        //      scored on the spot; owners of documents with several terms are queued and handled afterwards with every lane of
+        //      a warp busy on a queued document (a binary search per further term: done inline it would stall the 31 other lanes
+        //      of nearly every warp iteration).
         for (;;) {
-            int j = 0, n_multi = 0;
-            for (int pos = tid; pos < total; pos += SPM_THREADS) {
-                while (pos >= s.off[j + 1]) ++j;
-                const int i = pos - s.off[j];
-                const int d = row_at(j, i);
-                const uint32_t m = mask16[d];
-                if (m & (SPM_DONE | ((1u << j) - 1u))) continue;         // a lower term owns the document, or it is finished
-                float sc = fmaf(s_qv[j], w_at(j, i), 0.0f);
-                uint32_t rest = m >> (j + 1);                            // the document's further terms, ascending
-                int j2 = j + 1;
-                while (rest) {
-                    const int sk = __ffs((int)rest) - 1;
-                    j2 += sk;
-                    rest >>= sk + 1;
-                    int lo = 0, hi = s.len[j2];                          // the list is sorted by row: lower bound of d
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (row_at(j2, mid) < d) lo = mid + 1;
-                        else hi = mid;
-                    }
-                    sc = fmaf(s_qv[j2], w_at(j2, lo), sc);
-                    ++j2;
-                    ++n_multi;
-                }
+            if (tid == 0) s_nmulti = 0;
+            __syncthreads();
+            auto finish_doc = [&](int d, uint32_t m, float sc) {
                 bool keep = !(sc < thr_f);
                 if (keep && p.doc_mask) {
                     const int64_t g = doc0 + d;
                     keep = (__ldg(p.doc_mask + (g >> 5)) >> (g & 31)) & 1u;
                 }
-                if (!keep || stage((uint32_t)(doc0 + d), sc)) mask16[d] = (uint16_t)(m | SPM_DONE);     // only the owner writes
+                if (!keep || stage((uint32_t)(doc0 + d), sc)) mask16[d] = (uint16_t)(m | SPM_DONE);   // only the owner writes
+            };
+            {
+                int j = 0;
+                for (int pos = tid; pos < total; pos += SPM_THREADS) {
+                    while (pos >= s.off[j + 1]) ++j;
+                    const int i = pos - s.off[j];
+                    const int d = row_at(j, i);
+                    const uint32_t m = mask16[d];
+                    if (m & (SPM_DONE | ((1u << j) - 1u))) continue;     // a lower term owns the document, or it is finished
+                    if (m >> (j + 1)) {                                  // further terms: queue (j, i) for the second phase
+                        const int at = atomicAdd(&s_nmulti, 1);
+                        if (at < SPM_MULTI) multi[at] = ((uint32_t)j << 16) | (uint32_t)i;
+                        else finish_doc(d, m, chain_score(j, i, d, m));  // (queue full: inline after all)
+                    } else {
+                        finish_doc(d, m, fmaf(s_qv[j], w_at(j, i), 0.0f));
+                    }
+                }
             }
-            if (stats && n_multi) atomicAdd(&s_stat[SMS_MULTI], (unsigned long long)n_multi);
+            __syncthreads();
+            {
+                const int n_multi = min(s_nmulti, SPM_MULTI);
+                for (int idx = tid; idx < n_multi; idx += SPM_THREADS) {
+                    const uint32_t e = multi[idx];
+                    const int j = (int)(e >> 16), i = (int)(e & 0xffffu);
+                    const int d = row_at(j, i);
+                    const uint32_t m = mask16[d];
+                    finish_doc(d, m, chain_score(j, i, d, m));
+                }
+                if (stats && tid == 0) s_stat[SMS_MULTI] += (unsigned long long)s_nmulti;
+            }
             __syncthreads();
             const int staged_raw = s_nstage;
             SPM_MARK(SMS_SCORE);

@@ -524,6 +524,7 @@ struct ScanParams {
     const uint16_t* queries;    // query block matrix (padded to whole blocks)
     const uint32_t* row_mask;   // optional filter: bit (row & 31) of word (row >> 5) set = row allowed; NULL = no filter
     unsigned long long* stats;  // optional [gridDim.x][16] cycle counters (debug/profiling), may be NULL
+    const int* gate;            // optional device scalar: only queries [0, *gate) exist (dense_tc3.cu; NULL = all n_q)
 };
 
 }  // namespace b200rag

@@ -81,7 +81,8 @@ int b200rag_prepare_rows(const float* in_f32, void* out16, int64_t n_rows, int32
  *   corpus16  [n_rows, dim]   stored rows of this shard (dim % 8 == 0, 16-byte aligned base)
  *   queries16 [n_queries, dim]
  *   out_scores f64 [n_queries, k]  canonical scores;  out_ids i64 [n_queries, k] = local row + id_offset
- *   out_flags  i32 [n_queries] or NULL: bit0 = the tensor-core candidate set could not be PROVEN complete for
+ *   out_flags  i32 [n_queries] or NULL: bit1 = the query went through the widened tier-0 re-scan (k' = 640 candidates, for
+ *              tie groups across the edge of the first pass' candidate set); bit0 = the tensor-core candidate set could not be PROVEN complete for
  *              this query (near-ties beyond the slack); in AUTO mode such queries were re-run on the exact path,
  *              so results are always exact and the flag is informational.  AUTO never synchronises with the host: the
  *              fallback is launched unconditionally and gated on the device by the number of flagged queries.  Shapes
@@ -239,6 +240,26 @@ int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const in
                        const double* lambda, const int32_t* k_sel, int32_t k_max,
                        int32_t* out_pick, int32_t* out_n,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Learned re-rank of a fused batch.  Replaces HybridRetriever.rerank with the LearnedRanker (reference retrieval.py:518-563,
+ * ranker.py:109-125):  s = base_weight*score + method_bonus*popcount(method_mask) + recency_weight*recency  (fp64, the
+ * reference's operation order), stable descending sort, first k_out.
+ *   scores f64 [n_queries, t_max] fused scores, method_mask i32 same shape (bit l: list l returned the hit, as b200rag_rrf_fuse
+ *   writes it), recency f64 same shape or NULL (= 0), n_in i32 [n_queries] valid entries per query
+ *   out_pos i32 [n_queries, k_out] positions into the input (-1 padded), out_scores f64 same shape, out_n i32 [n_queries] */
+int b200rag_rerank_learned(const double* scores, const int32_t* method_mask, const double* recency, const int32_t* n_in,
+                           int32_t n_queries, int32_t t_max, double base_weight, double method_bonus, double recency_weight,
+                           int32_t k_out, int32_t* out_pos, double* out_scores, int32_t* out_n, void* stream);
+
+/* Mean pairwise token-set Jaccard of every query's result list.  Replaces RAGEvaluator._calculate_pairwise_similarity
+ * (reference evaluation.py:327-344; diversity = 1 - it, :315-325): pairs i < j whose two token sets are non-empty, numpy's mean.
+ *   docs i32 [n_queries, n_max] rows of the results in the token CSR (see b200rag_mmr_select), n_in i32 [n_queries]
+ *   out_mean f64 [n_queries] (0 when no pair qualifies), out_pairs i32 [n_queries] number of pairs averaged */
+size_t b200rag_pairwise_jaccard_workspace_bytes(int32_t n_queries, int32_t n_max);
+int b200rag_pairwise_jaccard(const int32_t* docs, const int32_t* n_in, int32_t n_queries, int32_t n_max,
+                             const int64_t* doc_tok_ptr, const int32_t* doc_tok_ids, double* out_mean, int32_t* out_pairs,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -88,3 +88,19 @@ def learned_rank(scores: Sequence[float], n_methods: Sequence[int], recency: Seq
           for s, m, r in zip(scores, n_methods, recency)]
     order = sorted(range(len(rs)), key=rs.__getitem__, reverse=True)[:top_k]
     return order, [rs[i] for i in order]
+
+
+def pairwise_similarity(token_sets: Sequence[frozenset]) -> Tuple[float, int]:
+    """RAGEvaluator._calculate_pairwise_similarity (reference evaluation.py:327-344): mean token-set Jaccard over the pairs
+    i < j whose two sets are non-empty, 0.0 when fewer than two results or no pair qualifies.  The mean is numpy's
+    (np.mean of a Python list), as in the reference.  Returns (mean, number of pairs averaged)."""
+    import numpy as np
+    if len(token_sets) < 2:
+        return 0.0, 0
+    sims = []
+    for i in range(len(token_sets)):
+        for j in range(i + 1, len(token_sets)):
+            a, b = token_sets[i], token_sets[j]
+            if a and b:
+                sims.append(len(a & b) / len(a | b))
+    return (float(np.mean(sims)) if sims else 0.0), len(sims)

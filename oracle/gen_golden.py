@@ -162,6 +162,19 @@ def main() -> None:
             "in_n_methods": [x[2] for x in fused_in], "top_k": top_k,
             "out_ids": [d["id"] for d in rer], "out_scores_hex": [float(d["score"]).hex() for d in rer]})
 
+    # ---------------- evaluation: mean pairwise token-set Jaccard (reference evaluation.py:327-344) ----------
+    from advanced_rag.evaluation import RAGEvaluator
+    ev = RAGEvaluator()
+    cases["pairwise_similarity"] = []
+    for n_res, vocab, max_len in [(5, 12, 8), (20, 40, 25), (2, 5, 4), (1, 5, 4), (30, 300, 60), (100, 60, 30), (17, 9, 6)]:
+        res = [_doc(i, rng, vocab, rng.randint(0, max_len)) for i in range(n_res)]
+        if n_res >= 5:
+            res[2]["content"] = ""                       # an empty token set: its pairs are skipped (:338)
+            res[4]["content"] = res[3]["content"].upper()  # .lower() makes them identical
+        val = ev._calculate_pairwise_similarity(res)
+        cases["pairwise_similarity"].append({"contents": [d["content"] for d in res], "mean_hex": float(val).hex(),
+                                             "diversity_hex": float(ev._calculate_diversity(res)).hex()})
+
     # ---------------- filter expressions (row S3) ------------------------------------------------
     r = HybridRetriever(index_manager=None)
     for f in [

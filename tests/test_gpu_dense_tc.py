@@ -80,7 +80,43 @@ def test_massive_ties_are_flagged_and_auto_mode_falls_back(eng, oracle_lib):
     assert f.cpu().numpy().all(), "400-way ties cannot be proven complete with k'=128 candidates"
     s, i, f = idx.search(torch.from_numpy(q), 100, mode=eng.DENSE_AUTO)
     assert np.array_equal(i.cpu().numpy(), ref_i) and np.array_equal(s.cpu().numpy(), ref_s)
-    assert f.cpu().numpy().all()                                # flags stay informational
+    f = f.cpu().numpy()
+    # AUTO: the flagged queries went through the tier-0 re-scan (bit 1), whose k' = 640 candidates hold the whole 400-way tie
+    # group, so the proof succeeded there (bit 0 cleared) and the CUDA-core scan was not needed
+    assert ((f & 2) == 2).all() and ((f & 1) == 0).all()
+
+
+@pytest.mark.parametrize("copies,tier0", [(8, True), (64, True), (64, False), (700, True)])
+def test_near_duplicate_corpus_is_exact_with_and_without_tier0(eng, oracle_lib, copies, tier0):
+    """corpora with duplicated chunks.  Every row occurs `copies` times; tie groups straddle rank k.  The
+    result must equal the oracle whichever path resolves a query: first pass (8 copies fit k' = k + 28), tier-0 re-scan
+    (64 copies), or the exact CUDA-core scan (tier 0 switched off, or a 700-way tie that exceeds even k' = 640)."""
+    from b200rag import _lib
+    o = oracle_lib
+    rng = np.random.default_rng(copies)
+    n_base, d, b, k = 40_000 // copies, 128, 160, 100
+    base = rng.standard_normal((n_base, d)).astype(np.float32)
+    x = np.tile(base, (copies, 1))                              # copy c of row r has id c * n_base + r
+    q = rng.standard_normal((b, d)).astype(np.float32)
+    xb, qb = o.normalize_rows(x, o.F16), o.normalize_rows(q, o.F16)
+    ref_s, ref_i = o.dense_topk(xb, qb, k, o.F16)
+    idx = eng.DenseIndex(d, "f16", "COSINE", DEV)
+    idx.add(torch.from_numpy(x))
+    _lib.set_option("no_tier0", 0 if tier0 else 1)
+    try:
+        s, i, f = idx.search(torch.from_numpy(q), k, mode=eng.DENSE_AUTO)
+    finally:
+        _lib.set_option("no_tier0", -1)
+    assert np.array_equal(i.cpu().numpy(), ref_i) and np.array_equal(s.cpu().numpy(), ref_s)
+    f = f.cpu().numpy()
+    if copies == 8:
+        assert (f == 0).all()
+    elif copies == 64 and tier0:
+        assert ((f & 2) == 2).any() and ((f & 1) == 0).all()     # resolved by the re-scan
+    elif copies == 64:
+        assert ((f & 1) == 1).any() and ((f & 2) == 0).all()     # straight to the exact scan
+    else:
+        assert ((f & 3) == 3).any()                              # re-scanned AND still unproven: exact scan
 
 
 def test_auto_equals_exact_mode_at_one_million_rows(eng):

@@ -434,3 +434,69 @@ def test_sparse_filtered_matches_oracle(eng, oracle_lib):
         assert c[q] == len(keep)
         assert list(i[q, : c[q]]) == [int(ri[q, j]) for j in keep]
         assert list(s[q, : c[q]]) == [rs[q, j] for j in keep]
+
+
+# ------------------------------------------------------------------------------------------------ rerank + diversity (8f-4)
+def test_learned_rerank_kernel_matches_reference_golden_and_oracle(eng):
+    """b200rag_rerank_learned == the reference's rerank with the LearnedRanker (golden from retrieval.py:518-563 +
+    ranker.py:109-125) and == the oracle restatement on random batches with ties, recency and ragged lengths."""
+    from oracle import fusion
+    g = load_golden()
+    for case in g["rerank"]:
+        sc = np.asarray([float.fromhex(h) for h in case["in_scores_hex"]])
+        mk = np.asarray([(1 << m) - 1 for m in case["in_n_methods"]], np.int32)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+        pos, out, cnt = eng.rerank_learned(t(sc[None, :]), t(mk[None, :]), t(np.asarray([sc.size], np.int32)), case["top_k"])
+        m = int(cnt[0])
+        assert [case["in_ids"][i] for i in pos[0, :m].cpu().tolist()] == case["out_ids"]
+        assert [float(v).hex() for v in out[0, :m].cpu().tolist()] == case["out_scores_hex"]
+    rng = np.random.default_rng(3)
+    b, t_max, k_out = 40, 100, 7
+    sc = np.round(rng.random((b, t_max)) * 0.02, 3)                 # rounded: plenty of exact ties
+    mk = rng.integers(1, 8, (b, t_max)).astype(np.int32)
+    rec = rng.random((b, t_max))
+    n = rng.integers(0, t_max + 1, b).astype(np.int32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    for bw, mb, rw, use_rec in ((1.0, 0.1, 0.0, False), (2.0, 0.5, 0.25, True)):
+        pos, out, cnt = eng.rerank_learned(t(sc), t(mk), t(n), k_out, bw, mb, rw, t(rec) if use_rec else None)
+        for q in range(b):
+            nm = [bin(int(v)).count("1") for v in mk[q, : n[q]]]
+            order, rs = fusion.learned_rank(list(sc[q, : n[q]]), nm, list(rec[q, : n[q]]) if use_rec else [0.0] * int(n[q]), k_out, bw, mb, rw)
+            m = int(cnt[q])
+            assert m == len(order) and pos[q, :m].cpu().tolist() == order and out[q, :m].cpu().tolist() == rs, q
+            assert (pos[q, m:] == -1).all()
+
+
+def test_pairwise_jaccard_kernel_matches_reference_golden_and_oracle(eng):
+    """b200rag_pairwise_jaccard == RAGEvaluator._calculate_pairwise_similarity (golden from evaluation.py:327-344, numpy mean
+    included) and == the oracle restatement on random result lists."""
+    from oracle import fusion
+    g = load_golden()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+    def run(lists):                                # lists: per query a list of contents
+        vocab, ptr, ids = {}, [0], []
+        docs = np.zeros((len(lists), max(1, max(len(l) for l in lists))), np.int32)
+        row = 0
+        for q, l in enumerate(lists):
+            for j, c in enumerate(l):
+                s = sorted({vocab.setdefault(tok, len(vocab)) for tok in fusion.tokens(c)})
+                ids.extend(s)
+                ptr.append(len(ids))
+                docs[q, j] = row
+                row += 1
+        if row == 0:
+            ptr.append(0)
+        mean, pairs = eng.pairwise_jaccard(t(docs), t(np.asarray([len(l) for l in lists], np.int32)), t(np.asarray(ptr, np.int64)),
+                                           t(np.asarray(ids if ids else [0], np.int32)))
+        return mean.cpu().tolist(), pairs.cpu().tolist()
+
+    lists = [c["contents"] for c in g["pairwise_similarity"]]
+    mean, pairs = run(lists)
+    assert [float(v).hex() for v in mean] == [c["mean_hex"] for c in g["pairwise_similarity"]]
+    rng = np.random.default_rng(8)
+    lists = [[" ".join(f"w{rng.integers(30)}" for _ in range(rng.integers(0, 20))) for _ in range(rng.integers(0, 40))] for _ in range(25)]
+    mean, pairs = run(lists)
+    for q, l in enumerate(lists):
+        want, np_ = fusion.pairwise_similarity([fusion.tokens(c) for c in l])
+        assert mean[q] == want and pairs[q] == np_, q

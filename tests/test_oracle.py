@@ -38,6 +38,19 @@ def test_learned_rank_restatement_matches_reference_golden():
         assert [r.hex() for r in rs] == c["out_scores_hex"]
 
 
+def test_pairwise_similarity_restatement_matches_reference_golden():
+    """reference evaluation.py:327-344 (RAGEvaluator._calculate_pairwise_similarity / _calculate_diversity), golden produced by
+    executing the reference (oracle/gen_golden.py)."""
+    from oracle import fusion
+    g = load_golden()
+    assert len(g["pairwise_similarity"]) >= 6
+    for case in g["pairwise_similarity"]:
+        mean, pairs = fusion.pairwise_similarity([fusion.tokens(c) for c in case["contents"]])
+        assert float(mean).hex() == case["mean_hex"], len(case["contents"])
+        if len(case["contents"]) >= 2:
+            assert float(1.0 - mean).hex() == case["diversity_hex"]
+
+
 def test_reference_known_answers():
     """Known answers quoted in SURVEY.md section 8c (probe of the reference's _fuse_results)."""
     ids, sc, _ = fusion.rrf_fuse([["A", "B"], ["A", "C"]], [0.7, 0.3])
