@@ -64,6 +64,7 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     // device-side gate (tier-0 re-scan of flagged queries): only the first *gate queries exist; pairs of query blocks beyond
     // them are skipped by every role alike, so a launch with nothing to do costs a few microseconds
     const int qgroups = p.gate ? min(qgroups_all, (__ldg(p.gate) + 2 * TC_BM - 1) / (2 * TC_BM)) : qgroups_all;
+    const int n_q_live = p.gate ? min(p.n_q, __ldg(p.gate)) : p.n_q;      // (padding rows of the last live pair never pass)
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
@@ -210,7 +211,7 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 const int q = (qg * 2 + rank) * TC_BM + qlane;
                 // start from the best threshold any CTA has established for this query so far (valid lower bound of the
                 // global k'-th best score; -inf while nobody has k' candidates yet); padding lanes never pass
-                st_thr[(qg - qg0) * TC_BM + qlane] = q < p.n_q ? gthr_load(p.gthr + q) : CUDART_INF_F;
+                st_thr[(qg - qg0) * TC_BM + qlane] = q < n_q_live ? gthr_load(p.gthr + q) : CUDART_INF_F;
                 st_cnt[(qg - qg0) * TC_BM + qlane] = 0;
             }
             for (int tile = t0; tile < t1; ++tile) {
@@ -223,7 +224,7 @@ dense_scan3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     unsigned int* my_gthr = p.gthr + q;       // gthr has nqb*128 entries, padded blocks included
                     float thr = st_thr[si];
                     int cnt = st_cnt[si];
-                    if (((tile - t0) & 7) == 7 && q < p.n_q) thr = fmaxf(thr, gthr_load(my_gthr));
+                    if (((tile - t0) & 7) == 7 && q < n_q_live) thr = fmaxf(thr, gthr_load(my_gthr));
                     ST_T0(tt);
                     mbar_wait(&tfull_bar[astage], aphase);
                     ST_ADD(st_wtfull, tt);
@@ -277,11 +278,16 @@ int scan3_max_clusters_query(int cap, int span, int sm_count);
 int scan3_max_clusters(int cap, int span, int sm_count) {
     // the occupancy query costs tens of microseconds per call: one cached answer, guarded (the C ABI is reentrant)
     static std::mutex mu;
-    static int cached_cap = -1, cached_span = -1, cached_sm = -1, cached_val = 0;
+    struct Entry { int cap, span, sm, val; };
+    static Entry cache[8] = {};                         // (the first pass and the tier-0 re-scan alternate between two shapes)
+    static int n_cached = 0, next = 0;
     std::lock_guard<std::mutex> lock(mu);
-    if (cap == cached_cap && span == cached_span && sm_count == cached_sm) return cached_val;
+    for (int i = 0; i < n_cached; ++i)
+        if (cache[i].cap == cap && cache[i].span == span && cache[i].sm == sm_count) return cache[i].val;
     const int val = scan3_max_clusters_query(cap, span, sm_count);
-    cached_cap = cap; cached_span = span; cached_sm = sm_count; cached_val = val;
+    cache[next] = Entry{cap, span, sm_count, val};
+    next = (next + 1) % 8;
+    if (n_cached < 8) ++n_cached;
     return val;
 }
 

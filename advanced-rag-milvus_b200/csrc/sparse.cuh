@@ -34,5 +34,6 @@ struct SparseParams {
 
 size_t sparse_mask_smem(int block_docs, int k, int* cap_out);
 int launch_sparse_mask(const SparseParams& p, int n_queries, cudaStream_t st);
+int launch_sparse_r1(const SparseParams& p, int n_queries, cudaStream_t st);      // sparse_r1.cu: the round-1 kernel (A/B baseline)
 
 }  // namespace b200rag

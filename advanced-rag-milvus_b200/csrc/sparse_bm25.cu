@@ -26,6 +26,8 @@
 // that are not a power of two >= 256) take the block-level path: same arithmetic, a block barrier between terms, postings read
 // in place.  Slices of one query share their thresholds through a global atomicMax.  Algorithmic HBM traffic = 6 bytes per
 // posting of the query's terms.  grid = (queries, slices); merge_topk_kernel reduces the slices.
+#include <algorithm>
+
 #include "sparse.cuh"
 
 namespace b200rag {
@@ -584,7 +586,13 @@ int b200rag_sparse_topk_masked(const int64_t* blk_term_ptr, const uint16_t* post
     int64_t n_blocks = (n_docs + block_docs - 1) / block_docs;
     if (n_blocks < 1) n_blocks = 1;
     B200_REQUIRE(n_queries <= 2147483647 && n_blocks <= 2147483647, "sparse_topk: too many blocks");
-    const int n_slices = sparse_slices(n_blocks, n_queries);
+    const int ab_flags = option(OPT_SPARSE_FLAGS, 0);
+    int n_slices = sparse_slices(n_blocks, n_queries);
+    if ((ab_flags & 16) && option(OPT_SPARSE_SLICES, 0) <= 0) {          // round-1 kernel, round-1 slicing
+        int sm_count = 148, dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        n_slices = (int)std::max<int64_t>(1, std::min<int64_t>(n_blocks, (2 * (int64_t)sm_count) / n_queries));
+    }
     Workspace ws(workspace, workspace_bytes);
     p.part_scores = ws.take<double>((size_t)n_queries * n_slices * k);
     p.part_ids = ws.take<int64_t>((size_t)n_queries * n_slices * k);
@@ -612,12 +620,17 @@ int b200rag_sparse_topk_masked(const int64_t* blk_term_ptr, const uint16_t* post
     p.out_ids = out_ids;
     p.out_counts = out_counts;
     p.doc_mask = doc_mask;
-    p.flags = option(OPT_SPARSE_FLAGS, 0);
+    p.flags = ab_flags;
     p.stats = stats_buffer(STATS_SPARSE, (size_t)SP_STAT_CTAS * SP_NSTAT);
     if (p.stats) B200_CUDA_CHECK(cudaMemsetAsync(p.stats, 0, (size_t)SP_STAT_CTAS * SP_NSTAT * 8, st));
     // Queries of up to 15 terms: the mask kernel (sparse_mask.cu), the product path.  Longer queries: the accumulator kernel of
     // this file.  How long the queries are is only known on the device, so both are launched and every CTA of the kernel that
     // does not serve its query leaves at once.
+    if (p.flags & 16) {                          // A/B: the round-1 kernel (sparse_r1.cu) for every query
+        int rc = launch_sparse_r1(p, n_queries, st);
+        if (rc) return rc;
+        return launch_merge(p.part_scores, p.part_ids, n_queries, nullptr, n_slices * k, k, nullptr, out_scores, out_ids, out_counts, st);
+    }
     if (smem > 225 * 1024) {
         set_error("sparse_topk: block_docs=%d with k=%d needs %zu bytes of shared memory (max 230400); use a smaller block",
                   block_docs, k, smem);

@@ -154,8 +154,17 @@ def test_more_flagged_queries_than_the_first_fallback_tier(eng, oracle_lib):
     ref_s, ref_i = o.dense_topk(xb, qb, 100, o.F16)
     idx = eng.DenseIndex(64, "f16", "COSINE", DEV)
     idx.add(torch.from_numpy(x))
-    s, i, f = idx.search(torch.from_numpy(q), 100, mode=eng.DENSE_AUTO)
+    from b200rag import _lib
+    _lib.set_option("no_tier0", 1)                               # straight to the exact scan: this test is about ITS two tiers
+    try:
+        s, i, f = idx.search(torch.from_numpy(q), 100, mode=eng.DENSE_AUTO)
+    finally:
+        _lib.set_option("no_tier0", -1)
     assert int(f.sum()) == 48
+    assert np.array_equal(i.cpu().numpy(), ref_i) and np.array_equal(s.cpu().numpy(), ref_s)
+    # with the tier-0 re-scan in place the 300-way tie groups fit its k' = 640 candidates: no query reaches the exact scan
+    s, i, f = idx.search(torch.from_numpy(q), 100, mode=eng.DENSE_AUTO)
+    assert (f.cpu().numpy() == 2).all()
     assert np.array_equal(i.cpu().numpy(), ref_i) and np.array_equal(s.cpu().numpy(), ref_s)
 
 
