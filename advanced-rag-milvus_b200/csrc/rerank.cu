@@ -50,37 +50,66 @@ rerank_learned_kernel(const double* __restrict__ scores, const int32_t* __restri
     if (tid == 0) out_n[q] = kk;
 }
 
-// numpy's pairwise summation of a float64 array (numpy/core/src/umath/loops_utils.h.src: DOUBLE_pairwise_sum, block size 128)
-__device__ double np_pairwise_sum(const double* a, int n) {
+// numpy's pairwise summation of a float64 array (numpy/core/src/umath/loops_utils.h.src: DOUBLE_pairwise_sum, block size 128):
+//   n < 8: sequential;  n <= 128: eight interleaved accumulators, combined as a tree, then the tail;  else split at
+//   n/2 rounded down to a multiple of 8 and add the two halves.  The recursion is unrolled into an explicit post-order walk (a
+// recursive __device__ function needs more stack than the default per-thread limit at 4950 pairs).
+__device__ double np_pairwise_leaf(const double* a, int n) {
     if (n < 8) {
         double res = 0.0;
         for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
         return res;
     }
-    if (n <= 128) {
-        double r[8];
+    double r[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = a[j];
-        int i = 8;
-        for (; i < n - (n % 8); i += 8) {
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __dadd_rn(res, a[i]);
-        return res;
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return __dadd_rn(np_pairwise_sum(a, n2), np_pairwise_sum(a + n2, n - n2));
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+__device__ double np_pairwise_sum(const double* a, int n) {
+    struct Frame { int off, len, stage; double left; };
+    Frame st[24];
+    int sp = 0;
+    double ret = 0.0;
+    st[sp++] = Frame{0, n, 0, 0.0};
+    while (sp > 0) {
+        Frame& f = st[sp - 1];
+        if (f.stage == 0) {
+            if (f.len <= 128) {
+                ret = np_pairwise_leaf(a + f.off, f.len);
+                --sp;
+                continue;
+            }
+            int n2 = f.len / 2;
+            n2 -= n2 % 8;
+            f.stage = 1;
+            st[sp++] = Frame{f.off, n2, 0, 0.0};
+        } else if (f.stage == 1) {
+            int n2 = f.len / 2;
+            n2 -= n2 % 8;
+            f.left = ret;
+            f.stage = 2;
+            st[sp++] = Frame{f.off + n2, f.len - n2, 0, 0.0};
+        } else {
+            ret = __dadd_rn(f.left, ret);
+            --sp;
+        }
+    }
+    return ret;
 }
 
 __global__ void __launch_bounds__(RR_THREADS)
 pairwise_jaccard_kernel(const int32_t* __restrict__ docs, const int32_t* __restrict__ n_in, int n_max,
                         const int64_t* __restrict__ doc_tok_ptr, const int32_t* __restrict__ doc_tok_ids,
                         double* __restrict__ pair_ws, double* __restrict__ out_mean, int32_t* __restrict__ out_pairs) {
-    __shared__ int s_valid;
     const int q = blockIdx.x, tid = threadIdx.x;
     const int n = min(n_in[q], n_max);
     const int n_pairs = n * (n - 1) / 2;
@@ -115,7 +144,6 @@ pairwise_jaccard_kernel(const int32_t* __restrict__ docs, const int32_t* __restr
             const double v = sims[pidx];
             if (v >= 0.0) sims[m++] = v;
         }
-        s_valid = m;
         out_pairs[q] = m;
         out_mean[q] = m ? __ddiv_rn(np_pairwise_sum(sims, m), (double)m) : 0.0;
     }

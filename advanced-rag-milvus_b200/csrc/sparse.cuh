@@ -1,5 +1,5 @@
-// sparse.cuh -- parameters shared by the two sparse-scan kernels (sparse_mask.cu: queries of up to 15 terms, the product
-// path; sparse_bm25.cu: any number of terms).
+// sparse.cuh -- parameters of the experimental term-mask sparse kernel (sparse_mask.cu: queries of up to 15 terms, A/B only)
+// and the interface between it and the product kernel's host code (sparse_bm25.cu).
 #pragma once
 #include "common.cuh"
 #include "select.cuh"
@@ -34,6 +34,5 @@ struct SparseParams {
 
 size_t sparse_mask_smem(int block_docs, int k, int* cap_out);
 int launch_sparse_mask(const SparseParams& p, int n_queries, cudaStream_t st);
-int launch_sparse_r1(const SparseParams& p, int n_queries, cudaStream_t st);      // sparse_r1.cu: the round-1 kernel (A/B baseline)
 
 }  // namespace b200rag

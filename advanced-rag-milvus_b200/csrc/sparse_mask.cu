@@ -1,4 +1,7 @@
-// sparse_mask.cu -- sparse inner-product (BM25-weighted) top-k over doc-range-blocked postings, queries of up to 15 terms  (K3).
+// sparse_mask.cu -- sparse inner-product (BM25-weighted) top-k over doc-range-blocked postings, queries of up to 15 terms.
+// EXPERIMENTAL (round 2): selectable with option "sparse_flags" bit 3 (8) for A/B runs; NOT the product path -- on the same box it
+// measured 1.2 - 1.4 ms at config 4 against 0.65 ms for sparse_bm25.cu (321 M warp instructions against 273 M: the per-block
+// bookkeeping of 8192-document blocks outweighs what the missing accumulator traffic saves).  Results are bit-identical.
 //
 // No per-document accumulators.  A document's score is a short chain  s = fmaf(qv_t, w_t, s)  over the query terms it holds, in
 // ascending term id (the canonical order, bit-identical to oracle/exact_scan.c:orc_sparse_topk); most documents a query touches
@@ -368,13 +371,7 @@ __global__ void __launch_bounds__(SPM_THREADS, 2) sparse_mask_kernel(const Spars
     const int n = tk.count();
     const uint64_t* oh = tk.out_hi();
     const uint32_t* ol = tk.out_lo();
-    if (p.n_slices == 1) {
-        for (int i = tid; i < p.k; i += SPM_THREADS) {
-            p.out_scores[(size_t)q * p.k + i] = i < n ? unmono32((uint32_t)oh[i]) : -CUDART_INF_F;
-            p.out_ids[(size_t)q * p.k + i] = i < n ? p.id_offset + (int64_t)(~ol[i]) : -1;
-        }
-        if (tid == 0) p.out_counts[q] = n;
-    } else {
+    {   // per-slice result; merge_topk_kernel reduces the slices (and converts back to fp32)
         double* ps = p.part_scores + ((size_t)q * p.n_slices + slice) * p.k;
         int64_t* pi = p.part_ids + ((size_t)q * p.n_slices + slice) * p.k;
         for (int i = tid; i < p.k; i += SPM_THREADS) {

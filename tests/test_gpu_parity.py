@@ -107,17 +107,22 @@ def _sparse_case(n_docs, vocab, n_q, seed, mean_len=60, n_terms=8, skip_top=20):
     return dp, ti, w, qp, qt, qv
 
 
+@pytest.mark.parametrize("mask_kernel", [False, True])
 @pytest.mark.parametrize("n_docs,vocab,n_q,k,block", [(3000, 500, 16, 25, 1024), (100000, 30000, 32, 40, 32768),
                                                        (70000, 2000, 8, 1000, 32768), (50, 40, 4, 10, 32)])
-def test_sparse_matches_oracle(eng, oracle_lib, n_docs, vocab, n_q, k, block):
-    from b200rag import synth
+def test_sparse_matches_oracle(eng, oracle_lib, n_docs, vocab, n_q, k, block, mask_kernel):
+    from b200rag import _lib, synth
     o = oracle_lib
+    _lib.set_option("sparse_flags", 11 if mask_kernel else -1)       # 11: the experimental term-mask kernel (sparse_mask.cu)
     dp, ti, w, qp, qt, qv = _sparse_case(n_docs, vocab, n_q, seed=n_docs)
     qv = (qv * np.linspace(0.5, 2.0, qv.size)).astype(np.float32)       # general sparse IP, not only 1.0
     tp, pd, pw = synth.doc_major_to_term_major(dp, ti, w, vocab)
     ref_s, ref_i, ref_c = o.sparse_topk(tp, pd, pw, n_docs, qp, qt, qv, k, id_offset=7)
     idx = eng.SparseIndex(dp, ti, w, vocab, DEV, block_docs=block, id_offset=7)
-    s, i, c = idx.search(qp, qt, qv, k)
+    try:
+        s, i, c = idx.search(qp, qt, qv, k)
+    finally:
+        _lib.set_option("sparse_flags", -1)
     assert np.array_equal(c.cpu().numpy(), ref_c)
     assert np.array_equal(i.cpu().numpy(), ref_i)
     assert np.array_equal(s.cpu().numpy().view(np.uint32), ref_s.view(np.uint32))      # bit exact fp32
@@ -157,8 +162,8 @@ def test_sparse_long_walk_both_collect_modes(eng, oracle_lib, signed):
 
 def test_sparse_full_size_collect_paths_agree(eng):
     """BASELINE config 4's sparse side at full size (1M documents, 100K-term Zipf vocabulary, 256 queries of 8 terms, top-500;
-    too large for the CPU oracle inside a test): the two sparse kernels (term-mask kernel, accumulator kernel), staged and
-    unstaged postings, and different slicings (1, 2, 5 slices per query) must return bit-identical lists; the lists are sorted by (score desc, id asc);
+    too large for the CPU oracle inside a test): the product kernel's collect paths, the experimental term-mask kernel, and
+    different slicings (1, 5 slices per query) must return bit-identical lists; the lists are sorted by (score desc, id asc);
     and the scores agree with an fp64 recomputation from the CSR.  (The oracle itself checks the same walk at 16384-document
     blocks x 9 blocks in test_sparse_16384_blocks_long_walk_matches_oracle.)"""
     from b200rag import _lib
@@ -172,7 +177,8 @@ def test_sparse_full_size_collect_paths_agree(eng):
     got = {}
     try:
         for flags in ("0", "1", "2", "3"):
-            _lib.set_option("sparse_flags", {"0": 0, "1": 8, "2": 2, "3": 0}[flags])      # 8: accumulator kernel, 2: no staging
+            # 0: bitmap walk + one candidate per thread and round, 11: the experimental term-mask kernel (sparse_mask.cu)
+            _lib.set_option("sparse_flags", {"0": -1, "1": 0, "2": 11, "3": 11}[flags])
             _lib.set_option("sparse_slices", {"0": -1, "1": -1, "2": 1, "3": 5}[flags])
             s, i, c = idx.search(qp, qt, qv, k)
             torch.cuda.synchronize()

@@ -1,7 +1,7 @@
 """Same-box A/B of the sparse scan (BASELINE config 4's BM25 side: 1M documents, 100K-term Zipf vocabulary, 256 queries of
 8 terms, top-500) under the kernel's switches:
 
-    option "sparse_flags"   bit 1 (2) = no shared-memory staging, bit 3 (8) = accumulator kernel for every query
+    option "sparse_flags"   bit 0 = dense collect, bit 1 = bulk append (default 3); + 8 = the experimental term-mask kernel
     option "sparse_slices"  slices per query (0 = the library's choice)
     --block-docs a,b,...    documents per postings block
     --variants flags:slices,...
@@ -31,7 +31,7 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--k", type=int, default=500)
 ap.add_argument("--reps", type=int, default=15)
 ap.add_argument("--block-docs", default="16384")
-ap.add_argument("--variants", default="0:0,0:1,0:2,0:8,1:0")
+ap.add_argument("--variants", default="3:0,3:1,3:2,0:0,11:0,11:4")
 ap.add_argument("--stats", action="store_true", help="per-phase cycle counters of one launch (b200rag_debug_set_stats_buffer)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -90,11 +90,14 @@ for bd in [int(x) for x in args.block_docs.split(",")]:
             lib.b200rag_debug_set_stats_buffer(1, None, 0)
             used = buf.cpu().numpy().astype(np.float64)
             used = used[used.sum(1) > 0]
-            tot = used[:, [0, 1, 2, 3, 9]].sum(1)
-            print(f"    {len(used)} CTAs; cycles per CTA: mean {tot.mean():.0f}  min {tot.min():.0f}  max {tot.max():.0f}; per CTA: "
-                  f"{used[:, 4].mean():.1f} blocks ({used[:, 10].mean():.1f} not staged), {used[:, 8].mean():.0f} postings, "
-                  f"{used[:, 7].mean():.0f} extra terms chained, {used[:, 5].mean():.0f} survivors staged, {used[:, 6].mean():.2f} score re-runs")
-            for i, n_ in ((0, "init + finalize"), (9, "block top (wait)"), (1, "mark"), (2, "score"), (3, "drain to top-k")):
+            if int(dense) & 8:      # sparse_mask.cu: SMS_* slots
+                names = ((0, "init + finalize"), (9, "block top (wait)"), (1, "mark"), (2, "score"), (3, "drain to top-k"))
+            else:                   # sparse_bm25.cu: phase slots of the product kernel
+                names = ((0, "init"), (2, "fetch + term 1"), (3, "terms 2.."), (4, "scan accumulators"), (5, "bulk append"),
+                         (1, "compaction"), (8, "candidate rounds"), (6, "finalize"))
+            tot = used[:, [i for i, _ in names]].sum(1)
+            print(f"    {len(used)} CTAs; cycles per CTA: mean {tot.mean():.0f}  min {tot.min():.0f}  max {tot.max():.0f}")
+            for i, n_ in names:
                 v = used[:, i].mean()
                 print(f"    {n_:18s} {v:10.0f} cycles  {100 * v / tot.mean():5.1f}%")
     del idx
