@@ -203,11 +203,12 @@ constexpr int ST2_WARPS = 4;
 
 __global__ void __launch_bounds__(ST2_WARPS * 32)
 sample_threshold2_kernel(const unsigned long long* __restrict__ cand, int cap, int nqb, int n_chunks, int rank, int n_q_pad,
-                         unsigned int* __restrict__ gthr) {
+                         unsigned int* __restrict__ gthr, const int* __restrict__ gate) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * ST2_WARPS + warp;
     if (q >= n_q_pad) return;
+    if (gate && q >= 2 * TC_BM * ((__ldg(gate) + 2 * TC_BM - 1) / (2 * TC_BM))) return;     // tier 0: pairs of query blocks that exist
     const int qb = q / TC_BM, ql = q % TC_BM;
     const int total = n_chunks * TC_SAMPLE_R;
     uint32_t* keys = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * total;
@@ -229,11 +230,11 @@ sample_threshold2_kernel(const unsigned long long* __restrict__ cand, int cap, i
 }
 
 int launch_sample_threshold2(const unsigned long long* cand, int cap, int nqb, int n_chunks, int rank, unsigned int* gthr,
-                             cudaStream_t st) {
+                             cudaStream_t st, const int* gate) {
     const int n_q_pad = nqb * TC_BM;
     const size_t smem = (size_t)ST2_WARPS * n_chunks * TC_SAMPLE_R * 4;
     B200_CUDA_CHECK(cudaFuncSetAttribute(sample_threshold2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sample_threshold2_kernel<<<(n_q_pad + ST2_WARPS - 1) / ST2_WARPS, ST2_WARPS * 32, smem, st>>>(cand, cap, nqb, n_chunks, rank, n_q_pad, gthr);
+    sample_threshold2_kernel<<<(n_q_pad + ST2_WARPS - 1) / ST2_WARPS, ST2_WARPS * 32, smem, st>>>(cand, cap, nqb, n_chunks, rank, n_q_pad, gthr, gate);
     count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;

@@ -414,9 +414,10 @@ sample_threshold_kernel(const unsigned long long* __restrict__ cand, const int* 
 __global__ void __launch_bounds__(128)
 tier0_gather_kernel(const uint16_t* __restrict__ queries, const int32_t* __restrict__ flag_list, const int32_t* __restrict__ n_flagged,
                     int dim, int n_slots, int max_served, uint16_t* __restrict__ q_out, int32_t* __restrict__ gate,
-                    int32_t* __restrict__ flag_list2) {
+                    int32_t* __restrict__ flag_list2, unsigned int* __restrict__ gthr) {
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (slot < n_slots && lane == 0) gthr[slot] = 0u;           // the re-scan starts from "no threshold yet"
     const int nf = __ldg(n_flagged);
     const int served = nf < max_served ? nf : max_served;
     if (blockIdx.x == 0 && threadIdx.x == 0) { gate[0] = served; gate[1] = nf - served; }
@@ -483,6 +484,7 @@ struct TensorPlan {
     size_t off_cand, off_cnt, off_gthr, off_flaglist, off_nflag, off_stats, off_qpad, off_exact, total;
     // tier 0: flagged queries re-scanned on the tensor path with the widest candidate set the kernels support
     int t0, t0_nq, t0_nqb, t0_kprime, t0_cap, t0_span, t0_chunks, t0_items, t0_clusters;
+    int t0_sample, t0_s_stride, t0_s_tiles, t0_s_chunks, t0_s_items;
     size_t t0_smem, off_t0_cand, off_t0_cnt, off_t0_gthr, off_t0_q, off_t0_gate, off_flaglist2;
 };
 
@@ -603,11 +605,21 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
         pl.t0_chunks = want_t0 < tiles3 ? want_t0 : tiles3;
         if (pl.t0_chunks < 1) pl.t0_chunks = 1;
         pl.t0_items = spans * pl.t0_chunks;
+        // strided sample pass of the re-scan (same sizing rule as the first pass, for k' = 640)
+        pl.t0_s_stride = option(OPT_SAMPLE_MULT, 8) * pl.t0_kprime / TC_SAMPLE_R;
+        if (pl.t0_s_stride > tiles3 / 4) pl.t0_s_stride = tiles3 / 4;
+        if (pl.t0_s_stride < 1) pl.t0_s_stride = 1;
+        pl.t0_s_tiles = tiles3 / pl.t0_s_stride;
+        pl.t0_sample = pl.t0_s_tiles >= 4 && TC_SAMPLE_R * pl.t0_s_stride >= 6 * pl.t0_kprime && option(OPT_NO_SAMPLE, 0) == 0;
+        const int want_s = pl.t0_clusters / gcd_int(qg, pl.t0_clusters);
+        pl.t0_s_chunks = want_s < pl.t0_s_tiles ? want_s : (pl.t0_s_tiles > 0 ? pl.t0_s_tiles : 1);
+        pl.t0_s_items = qg * pl.t0_s_chunks;
         if (pl.t0_smem > TC_SMEM_LIMIT || finish2_smem_bytes(dim, pl.t0_kprime) > 200 * 1024) pl.t0 = 0;
     }
     if (pl.t0) {
-        pl.off_t0_cand = take((size_t)pl.t0_chunks * pl.t0_nqb * TC_BM * pl.t0_cap * 8);
-        pl.off_t0_cnt = take((size_t)pl.t0_chunks * pl.t0_nqb * TC_BM * 4);
+        const int t0_max_chunks = pl.t0_chunks > pl.t0_s_chunks ? pl.t0_chunks : pl.t0_s_chunks;
+        pl.off_t0_cand = take((size_t)t0_max_chunks * pl.t0_nqb * TC_BM * pl.t0_cap * 8);
+        pl.off_t0_cnt = take((size_t)t0_max_chunks * pl.t0_nqb * TC_BM * 4);
         pl.off_t0_gthr = take((size_t)pl.t0_nqb * TC_BM * 4);
         pl.off_t0_q = take((size_t)pl.t0_nqb * TC_BM * dim * 2);
         pl.off_t0_gate = take(256);                          // [0] live tier-0 slots, [1] queries left for the exact scan
@@ -724,7 +736,7 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
                                                                                 pl.s_rank, pl.s_topk_cap, sp.gthr); count_launch();
                 B200_CUDA_CHECK(cudaGetLastError());
             } else {
-                rc = launch_sample_threshold2(s0.cand, s0.cap, pl.nqb, pl.s_chunks, pl.s_rank, sp.gthr, st);
+                rc = launch_sample_threshold2(s0.cand, s0.cap, pl.nqb, pl.s_chunks, pl.s_rank, sp.gthr, st, nullptr);
                 if (rc) return rc;
             }
         }
@@ -795,9 +807,9 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
         int32_t* gate = reinterpret_cast<int32_t*>(ws + pl.off_t0_gate);
         int32_t* flag_list2 = reinterpret_cast<int32_t*>(ws + pl.off_flaglist2);
         const int n_slots = pl.t0_nqb * TC_BM;
-        B200_CUDA_CHECK(cudaMemsetAsync(ws + pl.off_t0_gthr, 0, (size_t)n_slots * 4, st));
         tier0_gather_kernel<<<(n_slots + 3) / 4, 128, 0, st>>>(static_cast<const uint16_t*>(queries16), flag_list, n_flagged, dim, n_slots,
-                                                               pl.t0_nq, q_t0, gate, flag_list2); count_launch();
+                                                               pl.t0_nq, q_t0, gate, flag_list2,
+                                                               reinterpret_cast<unsigned int*>(ws + pl.off_t0_gthr)); count_launch();
         B200_CUDA_CHECK(cudaGetLastError());
         ScanParams st0;
         st0.n_rows = n_rows;
@@ -821,7 +833,23 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
         st0.row_mask = row_mask;
         st0.stats = nullptr;
         st0.gate = gate;
-        int rc = launch_scan3(corpus16, dtype, st0, pl.t0_clusters, pl.t0_cap, pl.t0_span, st);
+        int rc;
+        if (pl.t0_sample) {
+            ScanParams ss = st0;
+            ss.n_tiles = pl.t0_s_tiles;
+            ss.tile_stride = pl.t0_s_stride;
+            ss.n_chunks = pl.t0_s_chunks;
+            ss.n_items = pl.t0_s_items;
+            ss.qg_span = 1;
+            ss.kprime = TC_SAMPLE_R;
+            ss.cap = TC_SAMPLE_R;
+            ss.sample = 1;
+            rc = launch_scan3(corpus16, dtype, ss, pl.t0_clusters, pl.t0_cap, pl.t0_span, st);
+            if (rc) return rc;
+            rc = launch_sample_threshold2(ss.cand, ss.cap, pl.t0_nqb, pl.t0_s_chunks, TC_SAMPLE_R, st0.gthr, st, gate);
+            if (rc) return rc;
+        }
+        rc = launch_scan3(corpus16, dtype, st0, pl.t0_clusters, pl.t0_cap, pl.t0_span, st);
         if (rc) return rc;
         FinishParams f0 = fp;
         f0.n_q = n_slots;

@@ -39,6 +39,6 @@ size_t finish2_smem_bytes(int dim, int kprime);
 int launch_finish2(const FinishParams& fp, int dtype, cudaStream_t st);
 // Warp-per-query replacement of sample_threshold_kernel.
 int launch_sample_threshold2(const unsigned long long* cand, int cap, int nqb, int n_chunks, int rank, unsigned int* gthr,
-                             cudaStream_t st);
+                             cudaStream_t st, const int* gate);
 
 }  // namespace b200rag
