@@ -5,14 +5,13 @@
 // PROVE completeness (see dense_tc.cu's header).  Round 1 ran one 256-thread CTA per query around a block-level streaming
 // top-k: 63 M warp instructions for 1024 queries, three quarters of them in the selection's barriers, histograms and
 // bitonic passes (profiles/r1: 0.18 ms, 37 % issue utilisation, 3 CTAs per SM).  This generation:
-//   * one 128-thread CTA per query, ~10 KB of shared memory -> 16 CTAs per SM, no block-level selection at all;
-//   * warp 0 streams the chunk lists through a 512-entry buffer and keeps the k' greatest with the same register-resident
-//     radix select the scan epilogue uses (tc_common.cuh: warp_compact) -- typically two or three compactions per query;
-//     meanwhile warps 1..3 stage the query as fp32 and sum its squared norm;
-//   * one THREAD per candidate row for the re-score: the thread walks its row with 16-byte loads and keeps the eight
-//     canonical fp64 lanes in registers.  For fp16 the product of two stored values is exact in fp32, so it is formed with one
-//     FMUL and widened once (one conversion per element instead of two); bf16 products can leave the fp32 range and take the
-//     fp64 path;
+//   * one 128-thread CTA per query, ~40 KB of shared memory -> 5 CTAs per SM, no block-level selection at all;
+//   * warp 0 streams the chunk lists -- 32 survivors at a time, across as many chunks as they span -- through a 512-entry buffer
+//     and keeps the k' greatest with the same register-resident radix select the scan epilogue uses (tc_common.cuh:
+//     warp_compact): typically two or three compactions per query; meanwhile warps 1..3 convert the query to fp64;
+//   * re-score from rows staged with warp-wide 16-byte cp.async copies (coalesced 512-byte requests), eight threads per row,
+//     one per canonical fp64 lane.  (A first version of this generation let one thread walk a whole row straight from global
+//     memory: 16-byte requests from 32 different rows per warp instruction -- 262 us, slower than round 1.)
 //   * all-pairs rank count in shared memory (k' <= 640 -> at most 3200 compares per thread), no sort.
 // Which candidates survive a tie at the k'-th tensor-core score is immaterial: every dropped row has a tensor-core score
 // <= m either way, so the proof -- and with it the exact result -- does not depend on it.
@@ -21,12 +20,15 @@
 namespace b200rag {
 
 constexpr int F2_THREADS = 128;
+constexpr int F2_ROWS = F2_THREADS / 8;     // candidate rows re-scored per batch: eight threads share a row
 
 __host__ __device__ inline int finish2_sel_cap(int kprime) { return 2 * kprime <= 512 ? 512 : 2 * kprime; }
+__host__ __device__ inline int finish2_stage_rows(int dim) { return dim <= 2048 ? F2_ROWS : F2_ROWS / 2; }
 
 size_t finish2_smem_bytes(int dim, int kprime) {
     const int sel = finish2_sel_cap(kprime);
-    return (size_t)dim * 4 + (size_t)sel * 8 + (size_t)sel * 4 + (size_t)kprime * (8 + 4) + 64;
+    return (size_t)dim * 8 + (size_t)sel * 8 + (size_t)sel * 4 + (size_t)kprime * (8 + 4) + 256 * 4 +
+           (size_t)finish2_stage_rows(dim) * ((size_t)dim * 2 + 16) + 64;
 }
 
 template <int DTYPE>
@@ -40,43 +42,56 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
     const int q = p.q_list ? __ldg(p.q_list + slot_q) : slot_q;
     const int qb = slot_q / TC_BM, ql = slot_q % TC_BM;
     const int sel_cap = finish2_sel_cap(p.kprime);
-    float* qf = reinterpret_cast<float*>(smem);                                           // [dim] the query, exact in fp32
-    unsigned long long* buf = reinterpret_cast<unsigned long long*>(qf + p.dim);          // [sel_cap] (score bits << 32) | row
+    double* qd = reinterpret_cast<double*>(smem);                                         // [dim] the query in fp64
+    unsigned long long* buf = reinterpret_cast<unsigned long long*>(qd + p.dim);          // [sel_cap] (score bits << 32) | row
     uint32_t* scratch = reinterpret_cast<uint32_t*>(buf + sel_cap);                        // [sel_cap] keys of the smem select
     double* exact = reinterpret_cast<double*>(scratch + sel_cap);                          // [kprime]
     uint32_t* rows = reinterpret_cast<uint32_t*>(exact + p.kprime);                        // [kprime]
+    int* s_cnt = reinterpret_cast<int*>(rows + p.kprime);                                  // [<= 256] survivors per chunk
+    char* stage = reinterpret_cast<char*>(s_cnt + 256);
+    stage = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(stage) + 15) & ~uintptr_t(15));
     __shared__ int s_n;
     __shared__ float s_m;
     __shared__ double s_q2[F2_THREADS / 32];
     __shared__ float s_err;
     __shared__ double s_ek_sh;
 
+    // how many survivors did the scan leave in every chunk of this query?  (all threads, one round trip)
+    for (int c = tid; c < p.n_chunks; c += F2_THREADS) s_cnt[c] = __ldg(p.cand_cnt + ((size_t)(c * p.nqb + qb)) * TC_BM + ql);
+    __syncthreads();
     if (warp == 0) {
-        // ---- 1. the k' best by tensor-core score over all chunks of this query
+        // ---- 1. the k' best by tensor-core score over all chunks of this query.  The lists are short (a handful of survivors
+        //         per chunk), so each step takes 32 entries across as many chunks as they span: lane l's entry is found by a
+        //         running prefix over the chunk counts.
         int cnt = 0;
         float thr = -CUDART_INF_F;
         bool compacted = false;
-        for (int c = 0; c < p.n_chunks; ++c) {
-            const size_t slot = ((size_t)(c * p.nqb + qb)) * TC_BM + ql;
-            const int n_c = __ldg(p.cand_cnt + slot);
-            const unsigned long long* src = p.cand + slot * p.cap;
-            for (int base = 0; base < n_c; base += 32) {
-                const int i = base + lane;
-                unsigned long long e = 0ull;
-                bool pass = false;
-                if (i < n_c) {
-                    e = __ldg(src + i);
-                    pass = !compacted || __uint_as_float((uint32_t)(e >> 32)) > thr;
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                if (pass) buf[cnt + __popc(bal & ((1u << lane) - 1u))] = e;
-                cnt += __popc(bal);
-                if (cnt > sel_cap - 32) {
-                    __syncwarp();
-                    thr = fmaxf(thr, warp_compact(buf, cnt, p.kprime, sel_cap, smem_u32(scratch), lane));
-                    cnt = p.kprime;
-                    compacted = true;
-                }
+        int c_cur = 0, base = 0;                         // chunk c_cur starts at flat position `base`
+        int total = 0;
+        for (int c = lane; c < p.n_chunks; c += 32) total += s_cnt[c];
+        total = __reduce_add_sync(0xffffffffu, total);
+        for (int pos0 = 0; pos0 < total; pos0 += 32) {
+            const int pos = pos0 + lane;
+            // advance (c, b) to the chunk holding flat position `pos`: lanes walk independently from the warp-uniform start
+            int c = c_cur, b = base;
+            while (c < p.n_chunks && pos >= b + s_cnt[c]) { b += s_cnt[c]; ++c; }
+            unsigned long long e = 0ull;
+            bool pass = false;
+            if (pos < total) {
+                e = __ldg(p.cand + (((size_t)(c * p.nqb + qb)) * TC_BM + ql) * p.cap + (pos - b));
+                pass = !compacted || __uint_as_float((uint32_t)(e >> 32)) > thr;
+            }
+            // next step starts where lane 31 ended up
+            c_cur = __shfl_sync(0xffffffffu, c, 31);
+            base = __shfl_sync(0xffffffffu, b, 31);
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            if (pass) buf[cnt + __popc(bal & ((1u << lane) - 1u))] = e;
+            cnt += __popc(bal);
+            if (cnt > sel_cap - 32) {
+                __syncwarp();
+                thr = fmaxf(thr, warp_compact(buf, cnt, p.kprime, sel_cap, smem_u32(scratch), lane));
+                cnt = p.kprime;
+                compacted = true;
             }
         }
         __syncwarp();
@@ -95,11 +110,11 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
             s_ek_sh = -CUDART_INF;
         }
     } else {
-        // ---- meanwhile: the query as fp32 (16-bit values are exact in fp32) and its squared norm
+        // ---- meanwhile: the query in fp64 and its squared norm
         double q2 = 0.0;
         for (int d = tid - 32; d < p.dim; d += F2_THREADS - 32) {
             const double v = bits_to_double<DTYPE>(p.queries[(size_t)q * p.dim + d]);
-            qf[d] = (float)v;
+            qd[d] = v;
             q2 = fma(v, v, q2);
         }
 #pragma unroll
@@ -109,42 +124,48 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
     __syncthreads();
     const int n = s_n;
 
-    // ---- 2. exact canonical re-score, one thread per candidate row
+    // ---- 2. exact canonical re-score.  Rows are staged through shared memory F2_ROWS at a time with 16-byte cp.async copies
+    //         (a warp copies whole rows: coalesced 512-byte requests, nothing passes through registers), then eight threads
+    //         share a row, one per canonical lane (lane j sums d = j mod 8 in increasing d, exactly as oracle/exact_scan.c
+    //         does), and the lanes are combined in the canonical tree with shuffles.
     float my_err = 0.f;
-    const int n_vec = p.dim >> 3;
-    const float4* q4 = reinterpret_cast<const float4*>(qf);
-    for (int i = tid; i < n; i += F2_THREADS) {
-        const unsigned long long e = buf[i];
-        const uint32_t row = (uint32_t)e;
-        const uint4* x = reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim);
-        double p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0;
-#pragma unroll 4
-        for (int c = 0; c < n_vec; ++c) {
-            const uint4 v = __ldg(x + c);
-            const float4 qa = q4[2 * c], qb4 = q4[2 * c + 1];
-            if (DTYPE == B200RAG_F16) {
-                const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-                const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-                const float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
-                const float2 x3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
-                // fp16 x fp16 is exact in fp32 (22 significant bits, exponents within range): one rounding-free FMUL, one
-                // widening, one fp64 add == fma(q, x, p) of the canonical definition, bit for bit
-                p0 = __dadd_rn(p0, (double)__fmul_rn(qa.x, x0.x)); p1 = __dadd_rn(p1, (double)__fmul_rn(qa.y, x0.y));
-                p2 = __dadd_rn(p2, (double)__fmul_rn(qa.z, x1.x)); p3 = __dadd_rn(p3, (double)__fmul_rn(qa.w, x1.y));
-                p4 = __dadd_rn(p4, (double)__fmul_rn(qb4.x, x2.x)); p5 = __dadd_rn(p5, (double)__fmul_rn(qb4.y, x2.y));
-                p6 = __dadd_rn(p6, (double)__fmul_rn(qb4.z, x3.x)); p7 = __dadd_rn(p7, (double)__fmul_rn(qb4.w, x3.y));
-            } else {
-                double a, b;
-                unpack2<DTYPE>(v.x, a, b); p0 = fma((double)qa.x, a, p0); p1 = fma((double)qa.y, b, p1);
-                unpack2<DTYPE>(v.y, a, b); p2 = fma((double)qa.z, a, p2); p3 = fma((double)qa.w, b, p3);
-                unpack2<DTYPE>(v.z, a, b); p4 = fma((double)qb4.x, a, p4); p5 = fma((double)qb4.y, b, p5);
-                unpack2<DTYPE>(v.w, a, b); p6 = fma((double)qb4.z, a, p6); p7 = fma((double)qb4.w, b, p7);
+    {
+        const int RB = finish2_stage_rows(p.dim);
+        const int l8 = tid & 7, grp = tid >> 3;
+        const int vec_per_row = p.dim / 8;                        // 16-byte vectors per row
+        const int stride = p.dim * 2 + 16;                        // staged row pitch: +16 bytes keeps the rows of a warp on different banks
+        const double* qj = qd + l8;
+        for (int i0 = 0; i0 < n; i0 += RB) {
+            const int rows_here = min(RB, n - i0);
+            for (int r = warp; r < rows_here; r += F2_THREADS / 32) {
+                const uint32_t row = (uint32_t)buf[i0 + r];
+                const uint4* src = reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim);
+                const uint32_t dst = smem_u32(stage + (size_t)r * stride);
+                for (int c = lane; c < vec_per_row; c += 32)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * 16), "l"(src + c) : "memory");
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            const int i = i0 + grp;
+            const bool valid = i < n && grp < RB;
+            const uint16_t* x = reinterpret_cast<const uint16_t*>(stage + (size_t)(grp < RB ? grp : 0) * stride) + l8;
+            double acc = 0.0;
+            if (valid) {
+#pragma unroll 4
+                for (int d = 0; d < p.dim; d += 8) acc = fma(qj[d], bits_to_double<DTYPE>(x[d]), acc);
+            }
+            double t = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, 1));      // lanes 0,2,4,6: p0+p1, p2+p3, ...
+            t = __dadd_rn(t, __shfl_down_sync(0xffffffffu, t, 2));                 // lanes 0,4: (p0+p1)+(p2+p3), ...
+            t = __dadd_rn(t, __shfl_down_sync(0xffffffffu, t, 4));                 // lane 0: the canonical score
+            if (valid && l8 == 0) {
+                const unsigned long long e = buf[i];
+                rows[i] = (uint32_t)e;
+                exact[i] = t;
+                my_err = fmaxf(my_err, fabsf((float)((double)__uint_as_float((uint32_t)(e >> 32)) - t)));
+            }
+            __syncthreads();
         }
-        const double t = __dadd_rn(__dadd_rn(__dadd_rn(p0, p1), __dadd_rn(p2, p3)), __dadd_rn(__dadd_rn(p4, p5), __dadd_rn(p6, p7)));
-        exact[i] = t;
-        rows[i] = row;
-        my_err = fmaxf(my_err, fabsf((float)((double)__uint_as_float((uint32_t)(e >> 32)) - t)));
     }
     if (p.err_max) atomicMax(reinterpret_cast<int*>(&s_err), __float_as_int(my_err));       // non-negative floats order as ints
     __syncthreads();
