@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200rag.so")
 
 F16, BF16 = 0, 1
-DENSE_AUTO, DENSE_EXACT, DENSE_TENSOR = 0, 1, 2
+DENSE_AUTO, DENSE_EXACT, DENSE_TENSOR, DENSE_APPROX = 0, 1, 2, 3
 E_INVALID, E_WORKSPACE, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4
 OP_EQ, OP_NE, OP_GE, OP_LE, OP_GT, OP_LT = range(6)
 COL_F64, COL_I64, COL_I64_AS_F64, COL_CODE, COL_NEVER = range(5)

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BF16, DENSE_AUTO, DENSE_EXACT, DENSE_TENSOR, F16, check  # noqa: F401
+from ._lib import BF16, DENSE_APPROX, DENSE_AUTO, DENSE_EXACT, DENSE_TENSOR, F16, check  # noqa: F401
 
 _TORCH_DTYPE = {F16: torch.float16, BF16: torch.bfloat16}
 _DTYPE_CODE = {"f16": F16, "fp16": F16, "float16": F16, torch.float16: F16,

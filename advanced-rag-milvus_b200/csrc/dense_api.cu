@@ -66,11 +66,16 @@ int b200rag_dense_topk_masked(const void* corpus16, int64_t n_rows, int32_t dim,
         return run_exact(corpus16, n_rows, dim, dtype, queries16, n_queries, nullptr, k, id_offset, out_scores, out_ids,
                          workspace, workspace_bytes, st, nullptr, 0, row_mask);
     }
-    if (mode == B200RAG_DENSE_AUTO || mode == B200RAG_DENSE_TENSOR) {
+    if (mode == B200RAG_DENSE_AUTO || mode == B200RAG_DENSE_TENSOR || mode == B200RAG_DENSE_APPROX) {
         B200_REQUIRE(row_norm_bound > 0.0 && row_norm_bound < 1e30, "dense_topk: row_norm_bound must be positive (got %g)",
                      row_norm_bound);
+        if (mode == B200RAG_DENSE_APPROX && !tensor_supported(n_rows, dim, n_queries, k)) {
+            set_error("dense_topk: k=%d is beyond the tensor-core path (no approximate mode for it; use B200RAG_DENSE_AUTO)", k);
+            return B200RAG_E_UNSUPPORTED;
+        }
         return run_tensor(corpus16, n_rows, dim, dtype, queries16, n_queries, k, id_offset, out_scores, out_ids, out_flags,
-                          row_norm_bound, out_err, mode == B200RAG_DENSE_AUTO, workspace, workspace_bytes, st, row_mask);
+                          row_norm_bound, out_err, mode == B200RAG_DENSE_AUTO ? 1 : (mode == B200RAG_DENSE_APPROX ? 2 : 0), workspace,
+                          workspace_bytes, st, row_mask);
     }
     set_error("dense_topk: unknown mode %d", mode);
     return B200RAG_E_INVALID;

@@ -129,27 +129,46 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
     //         share a row, one per canonical lane (lane j sums d = j mod 8 in increasing d, exactly as oracle/exact_scan.c
     //         does), and the lanes are combined in the canonical tree with shuffles.
     float my_err = 0.f;
-    {
-        const int RB = finish2_stage_rows(p.dim);
+    if (p.approx) {
+        // approximate mode: the candidates' tensor-core scores ARE the result scores
+        for (int i = tid; i < n; i += F2_THREADS) {
+            const unsigned long long e = buf[i];
+            rows[i] = (uint32_t)e;
+            exact[i] = (double)__uint_as_float((uint32_t)(e >> 32));
+        }
+    } else {
+        // two half-size staging buffers: while the eight-thread groups of one half of the CTA re-score batch i, the copies of
+        // batch i + 1 are in flight (the stage is latency bound: random 1.5 KB rows from HBM)
+        const int RB = finish2_stage_rows(p.dim) / 2;             // rows per batch
         const int l8 = tid & 7, grp = tid >> 3;
         const int vec_per_row = p.dim / 8;                        // 16-byte vectors per row
         const int stride = p.dim * 2 + 16;                        // staged row pitch: +16 bytes keeps the rows of a warp on different banks
         const double* qj = qd + l8;
-        for (int i0 = 0; i0 < n; i0 += RB) {
+        auto issue = [&](int i0, int bufsel) {
             const int rows_here = min(RB, n - i0);
+            char* dstb = stage + (size_t)bufsel * RB * stride;
             for (int r = warp; r < rows_here; r += F2_THREADS / 32) {
                 const uint32_t row = (uint32_t)buf[i0 + r];
                 const uint4* src = reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim);
-                const uint32_t dst = smem_u32(stage + (size_t)r * stride);
+                const uint32_t dst = smem_u32(dstb + (size_t)r * stride);
                 for (int c = lane; c < vec_per_row; c += 32)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * 16), "l"(src + c) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        };
+        if (n > 0) issue(0, 0);
+        int bufsel = 0;
+        for (int i0 = 0; i0 < n; i0 += RB, bufsel ^= 1) {
+            if (i0 + RB < n) {
+                issue(i0 + RB, bufsel ^ 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
             __syncthreads();
             const int i = i0 + grp;
             const bool valid = i < n && grp < RB;
-            const uint16_t* x = reinterpret_cast<const uint16_t*>(stage + (size_t)(grp < RB ? grp : 0) * stride) + l8;
+            const uint16_t* x = reinterpret_cast<const uint16_t*>(stage + ((size_t)bufsel * RB + (grp < RB ? grp : 0)) * stride) + l8;
             double acc = 0.0;
             if (valid) {
 #pragma unroll 4
@@ -193,7 +212,7 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
         const double eps = 2.0 * (double)p.dim * 1.1920928955078125e-07 * sqrt(q2) * p.row_norm_bound;
         const float m = s_m;
         // proven complete iff nothing was dropped (m = -inf) or the k-th exact score clears m + eps
-        const bool proven = (m == -CUDART_INF_F) || (n >= p.k && s_ek_sh > (double)m + eps);
+        const bool proven = p.approx || (m == -CUDART_INF_F) || (n >= p.k && s_ek_sh > (double)m + eps);
         const int flag = proven ? 0 : 1;
         if (p.out_flags) p.out_flags[q] = flag | (p.q_list ? 2 : 0);      // bit 1: the query went through the tier-0 re-scan
         if (flag) p.flag_list[atomicAdd(p.n_flagged, 1)] = q;

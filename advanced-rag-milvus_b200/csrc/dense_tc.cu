@@ -653,6 +653,8 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
                int64_t id_offset, double* out_scores, int64_t* out_ids, int32_t* out_flags, double row_norm_bound,
                float* out_err, int with_fallback, void* workspace, size_t workspace_bytes, cudaStream_t st,
                const uint32_t* row_mask) {
+    const int approx = with_fallback == 2;       // B200RAG_DENSE_APPROX
+    if (approx) with_fallback = 0;
     TensorPlan pl = plan_tensor(n_rows, dim, n_q, k);
     if (pl.cap > TC_MAX_C || pl.scan_smem > TC_SMEM_LIMIT || n_rows >= ((int64_t)1 << 32) - TC_BN) {
         set_error("dense_topk(tensor): k=%d (k'=%d) or n_rows=%lld beyond the tensor-core path limits; use B200RAG_DENSE_EXACT",
@@ -782,7 +784,8 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
     fp.flag_list = flag_list;
     fp.n_flagged = n_flagged;
     fp.err_max = out_err;
-    if (option(OPT_FINISH_VERSION, 2) != 1 && finish2_smem_bytes(dim, pl.kprime) <= 200 * 1024) {
+    fp.approx = approx;
+    if (approx || option(OPT_FINISH_VERSION, 2) != 1 && finish2_smem_bytes(dim, pl.kprime) <= 200 * 1024) {
         // second generation (dense_finish.cu): warp-level selection, one thread per candidate row
         int rc = launch_finish2(fp, dtype, st);
         if (rc) return rc;

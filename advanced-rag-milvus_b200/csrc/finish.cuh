@@ -31,6 +31,7 @@ struct FinishParams {
     // tier-0 re-scan (dense_finish.cu only): launch slot -> original query, and the number of live slots (device scalar)
     const int32_t* q_list = nullptr;
     const int32_t* gate = nullptr;
+    int approx = 0;       // B200RAG_DENSE_APPROX: rank by the tensor-core (fp32) scores, no fp64 re-score, no proof
 };
 
 

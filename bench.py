@@ -372,6 +372,23 @@ def main():
                                  "ids_and_fp64_scores_equal_to_exact_scan": bool(ok_t.item()),
                                  "recall_at_k": float((ia == ix).float().mean().item()), "flagged": int(fa.sum().item())}
 
+        # approximate mode (north star: "recall@k of any approximate mode is reported against the exact scan"): rank by the
+        # tensor-core fp32 scores, no fp64 re-score / proof / fallback -- on this rank's shard, against its exact result
+        sa, ia, _ = mgr._sem.search(q_dev[1], K, engine.DENSE_AUTO)
+        sp_, ip_, _ = mgr._sem.search(q_dev[1], K, engine.DENSE_APPROX)
+        hit = (ip_.unsqueeze(2) == ia.unsqueeze(1)).any(2).float().mean()
+        ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ta.record()
+        for j in range(5):
+            mgr._sem.search(q_dev[j % POOL], K, engine.DENSE_APPROX)
+        tb.record()
+        torch.cuda.synchronize()
+        extras["approx_mode"] = {"what": "B200RAG_DENSE_APPROX on this rank's shard vs its exact top-k", "recall_at_k": float(hit.item()),
+                                 "same_order_fraction": float((ip_ == ia).float().mean().item()),
+                                 "max_rel_score_diff": float(((sp_ - sa).abs() / sa.abs().clamp(min=1e-30)).max().item()),
+                                 "ms_per_step": ta.elapsed_time(tb) / 5}
+
     # ---------------- secondary configurations (N = 1; they need the memory the headline index holds) ---
     if not args.no_extras and world == 1:
         import bench_extras as bx
@@ -392,6 +409,25 @@ def main():
             except Exception as e:                  # noqa: BLE001 - a secondary configuration must not take the headline down
                 extras[name] = {"error": repr(e)[:300]}
                 torch.cuda.empty_cache()
+
+    # ---------------- secondary configurations on N > 1 GPUs: config 5 and the sharded hybrid chain ----------
+    if not args.no_extras and world > 1:
+        import bench_extras as bx
+        del mgr
+        torch.cuda.empty_cache()
+        want = set(args.extras.split(","))
+        for key, name, fn in (("c5", "c5_sharded", lambda: bx.c5_sharded(device, world)),
+                              ("c4", "c4_sharded", lambda: bx.c4_sharded(device, world))):
+            if key not in want:
+                continue
+            try:
+                t0 = time.time()
+                extras[name] = fn()
+                extras[name]["wall_s"] = round(time.time() - t0, 1)
+            except Exception as e:                  # noqa: BLE001
+                extras[name] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
+            barrier()
 
     if rank == 0:
         peaks = load_peaks()

@@ -233,3 +233,68 @@ def near_duplicates(dev, n=1_000_000, d=768, b=1024, k=100, copies=64, reps=5):
         torch.cuda.empty_cache()
     out["slowdown"] = out["duplicated"]["ms"] / out["unique"]["ms"]
     return out
+
+
+def _max_over_ranks(ms, dev):
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def c5_sharded(dev, world, reps=5, rows_per_gpu=12_500_000, d=384, b=4096, k=10):
+    """BASELINE config 5 on the GPUs of this run: rows_per_gpu x world rows (100M at 8 GPUs) x 384 fp16 cosine top-10, batch
+    4096, through the row-sharded manager (local scan -> all-gather of k candidates -> merge on every rank)."""
+    from b200rag import distributed as bdist
+    n_total = rows_per_gpu * world
+    mgr = bdist.ShardedIndexManager(n_total, semantic_dim=d, sparse_dim=8, domain_dim=8, device=dev, dtype="f16", enable_sparse=False)
+    g = torch.Generator(device=dev).manual_seed(1000 + mgr.rank)
+    row = mgr.start
+    while row < mgr.end:
+        m = min(250_000, mgr.end - row)
+        mgr.add_vectors(torch.randn(m, d, generator=g, device=dev))
+        row += m
+    gq = torch.Generator(device=dev).manual_seed(5)                      # the same queries on every rank
+    q = [torch.randn(b, d, generator=gq, device=dev) for _ in range(4)]
+    it = [0]
+
+    def fn():
+        it[0] += 1
+        return mgr.search_batch_ids(q[it[0] % 4], "semantic_index", k)
+
+    t, (s_, i_, c_) = timed(fn, reps)
+    t = _max_over_ranks(t, dev)
+    flops = 2.0 * b * n_total * d
+    out = {"workload": f"{n_total} x {d} fp16 cosine top-{k}, batch {b}, row-sharded over {world} GPU(s) ({rows_per_gpu} rows = "
+                       f"{rows_per_gpu * d * 2 / 1e9:.1f} GB per GPU)", "ms": t, "qps": b / t * 1e3, "tflops_all_gpus": flops / t / 1e9,
+           "ceiling_qps_at_burst_peak": world * 1627.3e12 / (2.0 * rows_per_gpu * d), "ids_sorted": bool((s_[:, 1:] <= s_[:, :-1]).all())}
+    del mgr
+    torch.cuda.empty_cache()
+    return out
+
+
+def c4_sharded(dev, world, reps=6, docs=1_000_000, vocab=100_000, dim=1024):
+    """BASELINE config 4 with the corpus sharded over the GPUs of this run: dense rows and postings of this rank's document
+    range, global idf / avgdl, token sets replicated; searches merge over the ranks, RRF + MMR are split by query."""
+    from b200rag import bm25, distributed as bdist, synth
+    mgr = bdist.ShardedIndexManager(docs, semantic_dim=dim, sparse_dim=vocab, domain_dim=8, device=dev, dtype="bf16", enable_sparse=True)
+    # every rank generates the whole synthetic tf CSR (same seed) and keeps the postings of its own range
+    doc_ptr, term_ids, tf = synth.zipf_corpus_device(docs, vocab, 0, dev)
+    a, e = mgr.start, mgr.end
+    p0, p1 = int(doc_ptr[a]), int(doc_ptr[e])
+    lp, lt, lf = doc_ptr[a: e + 1] - doc_ptr[a], term_ids[p0:p1], tf[p0:p1]
+    stats = bdist.bm25_global_stats(lp, lt, lf, vocab)
+    w = bm25.bm25_weights_device(lp, lt, lf, vocab, stats=stats)
+    g = torch.Generator(device=dev).manual_seed(100 + mgr.rank)
+    mgr.add_vectors(torch.randn(e - a, dim, generator=g, device=dev), (lp.cpu(), lt, w))
+    mgr.set_token_sets(doc_ptr, term_ids.to(torch.int32), vocab)
+    del tf, w
+    out = c4(dev, reps=reps, docs=docs, vocab=vocab, dim=dim, manager=mgr)
+    for key in ("dense_ms", "sparse_ms", "rrf_ms", "mmr_ms", "hybrid_ms"):
+        out[key] = _max_over_ranks(out[key], dev)
+    out["hybrid_qps"] = 256 / out["hybrid_ms"] * 1e3
+    out["workload"] += f"; corpus row-sharded over {world} GPU(s), fusion split by query"
+    del mgr
+    torch.cuda.empty_cache()
+    return out

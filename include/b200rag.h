@@ -45,7 +45,10 @@ typedef enum { B200RAG_F16 = 0, B200RAG_BF16 = 1 } b200rag_dtype;
 typedef enum {
     B200RAG_DENSE_AUTO = 0,   /* tensor-core scan + exact re-score, exact fallback for flagged queries */
     B200RAG_DENSE_EXACT = 1,  /* CUDA-core fp64 canonical scan only (slow; ground truth / fallback)    */
-    B200RAG_DENSE_TENSOR = 2  /* tensor-core scan + exact re-score, flags reported, NO fallback        */
+    B200RAG_DENSE_TENSOR = 2, /* tensor-core scan + exact re-score, flags reported, NO fallback        */
+    B200RAG_DENSE_APPROX = 3  /* APPROXIMATE: ranks by the tensor-core fp32 scores (hardware accumulation order), no fp64 re-score,
+                                 no completeness proof, no fallback.  out_scores = those fp32 scores.  Near-ties may swap places or
+                                 cross rank k; bench.py reports recall@k against the exact modes */
 } b200rag_dense_mode;
 
 enum {

@@ -246,3 +246,24 @@ def test_filtered_scan_equals_oracle_on_the_allowed_rows(eng, oracle_lib, keep_f
         assert np.array_equal(i[:, :kk], ref_i), (keep_frac, mode)
         assert np.array_equal(s[:, :kk], ref_s), (keep_frac, mode)
         assert (i[:, kk:] == -1).all() and np.isneginf(s[:, kk:]).all()
+
+
+def test_approximate_mode_recall_and_tolerance(eng, oracle_lib):
+    """B200RAG_DENSE_APPROX ranks by the tensor-core fp32 scores (no fp64 re-score, no proof): north star -- fused scores
+    within 1e-3 relative in fp16/bf16, recall@k reported against the exact scan.  On random data it loses at most near-ties."""
+    o = oracle_lib
+    for (n, d, b, k, dt) in ((50_000, 384, 200, 20, "f16"), (30_000, 1024, 130, 100, "bf16")):
+        rng = np.random.default_rng(n)
+        x = rng.standard_normal((n, d)).astype(np.float32)
+        q = rng.standard_normal((b, d)).astype(np.float32)
+        code = o.F16 if dt == "f16" else o.BF16
+        ref_s, ref_i = o.dense_topk(o.normalize_rows(x, code), o.normalize_rows(q, code), k, code)
+        idx = eng.DenseIndex(d, dt, "COSINE", DEV)
+        idx.add(torch.from_numpy(x))
+        s, i, f = idx.search(torch.from_numpy(q), k, mode=eng.DENSE_APPROX)
+        s, i = s.cpu().numpy(), i.cpu().numpy()
+        recall = np.mean([len(set(i[r]) & set(ref_i[r])) / k for r in range(b)])
+        assert recall >= 0.995, recall
+        assert int(f.sum()) == 0 and (np.diff(s, axis=1) <= 0).all()
+        same = i == ref_i
+        assert np.abs(s[same] - ref_s[same]).max() <= 1e-3 * np.abs(ref_s[same]).max()      # tolerance stated by the north star
