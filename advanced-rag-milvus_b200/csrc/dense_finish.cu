@@ -21,14 +21,16 @@ namespace b200rag {
 
 constexpr int F2_THREADS = 128;
 constexpr int F2_ROWS = F2_THREADS / 8;     // candidate rows re-scored per batch: eight threads share a row
+constexpr int F2_GATHER = 1024;             // survivors gathered per round (8 KB, aliased with the row staging buffer)
 
 __host__ __device__ inline int finish2_sel_cap(int kprime) { return 2 * kprime <= 512 ? 512 : 2 * kprime; }
 __host__ __device__ inline int finish2_stage_rows(int dim) { return dim <= 2048 ? F2_ROWS : F2_ROWS / 2; }
 
 size_t finish2_smem_bytes(int dim, int kprime) {
     const int sel = finish2_sel_cap(kprime);
-    return (size_t)dim * 8 + (size_t)sel * 8 + (size_t)sel * 4 + (size_t)kprime * (8 + 4) + 256 * 4 +
-           (size_t)finish2_stage_rows(dim) * ((size_t)dim * 2 + 16) + 64;
+    size_t stage = (size_t)finish2_stage_rows(dim) * ((size_t)dim * 2 + 16);
+    if (stage < (size_t)F2_GATHER * 8) stage = (size_t)F2_GATHER * 8;
+    return (size_t)dim * 8 + (size_t)sel * 8 + (size_t)sel * 4 + (size_t)kprime * (8 + 4) + 256 * 4 + stage + 64;
 }
 
 template <int DTYPE>
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
     int* s_cnt = reinterpret_cast<int*>(rows + p.kprime);                                  // [<= 256] survivors per chunk
     char* stage = reinterpret_cast<char*>(s_cnt + 256);
     stage = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(stage) + 15) & ~uintptr_t(15));
-    __shared__ int s_n;
+    __shared__ int s_n, s_total;
     __shared__ float s_m;
     __shared__ double s_q2[F2_THREADS / 32];
     __shared__ float s_err;
@@ -59,41 +61,67 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
     // how many survivors did the scan leave in every chunk of this query?  (all threads, one round trip)
     for (int c = tid; c < p.n_chunks; c += F2_THREADS) s_cnt[c] = __ldg(p.cand_cnt + ((size_t)(c * p.nqb + qb)) * TC_BM + ql);
     __syncthreads();
-    if (warp == 0) {
-        // ---- 1. the k' best by tensor-core score over all chunks of this query.  The lists are short (a handful of survivors
-        //         per chunk), so each step takes 32 entries across as many chunks as they span: lane l's entry is found by a
-        //         running prefix over the chunk counts.
-        int cnt = 0;
-        float thr = -CUDART_INF_F;
-        bool compacted = false;
-        int c_cur = 0, base = 0;                         // chunk c_cur starts at flat position `base`
-        int total = 0;
-        for (int c = lane; c < p.n_chunks; c += 32) total += s_cnt[c];
-        total = __reduce_add_sync(0xffffffffu, total);
-        for (int pos0 = 0; pos0 < total; pos0 += 32) {
-            const int pos = pos0 + lane;
-            // advance (c, b) to the chunk holding flat position `pos`: lanes walk independently from the warp-uniform start
-            int c = c_cur, b = base;
-            while (c < p.n_chunks && pos >= b + s_cnt[c]) { b += s_cnt[c]; ++c; }
-            unsigned long long e = 0ull;
-            bool pass = false;
-            if (pos < total) {
-                e = __ldg(p.cand + (((size_t)(c * p.nqb + qb)) * TC_BM + ql) * p.cap + (pos - b));
-                pass = !compacted || __uint_as_float((uint32_t)(e >> 32)) > thr;
+    if (warp == 0) {                                     // exclusive prefix of the counts, in place (<= 256 chunks)
+        int carry = 0;
+        for (int c0 = 0; c0 < p.n_chunks; c0 += 32) {
+            const int c = c0 + lane;
+            const int v = c < p.n_chunks ? s_cnt[c] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
             }
-            // next step starts where lane 31 ended up
-            c_cur = __shfl_sync(0xffffffffu, c, 31);
-            base = __shfl_sync(0xffffffffu, b, 31);
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (pass) buf[cnt + __popc(bal & ((1u << lane) - 1u))] = e;
-            cnt += __popc(bal);
-            if (cnt > sel_cap - 32) {
-                __syncwarp();
-                thr = fmaxf(thr, warp_compact(buf, cnt, p.kprime, sel_cap, smem_u32(scratch), lane));
-                cnt = p.kprime;
-                compacted = true;
+            if (c < p.n_chunks) s_cnt[c] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s_total = carry;
+    }
+    __syncthreads();
+    const int total = s_total;
+    // ---- 1. the k' best by tensor-core score over all chunks of this query.  All threads first copy the survivors -- a handful
+    //         per chunk, ~8 k' in all -- into shared memory with independent loads (one round trip instead of one per 32
+    //         entries), F2_GATHER at a time into the region the re-score later stages rows in; warp 0 then selects from there.
+    unsigned long long* gathered = reinterpret_cast<unsigned long long*>(stage);
+    int cnt = 0;                                         // (warp 0's running state across the rounds)
+    float thr = -CUDART_INF_F;
+    bool compacted = false;
+    for (int g0 = 0; g0 < total; g0 += F2_GATHER) {
+        const int g_n = min(F2_GATHER, total - g0);
+        for (int i = tid; i < g_n; i += F2_THREADS) {
+            const int pos = g0 + i;
+            int lo = 0, hi = p.n_chunks - 1;             // last chunk whose prefix is <= pos
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_cnt[mid] <= pos) lo = mid;
+                else hi = mid - 1;
+            }
+            gathered[i] = __ldg(p.cand + (((size_t)(lo * p.nqb + qb)) * TC_BM + ql) * p.cap + (pos - s_cnt[lo]));
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int i0 = 0; i0 < g_n; i0 += 32) {
+                const int i = i0 + lane;
+                unsigned long long e = 0ull;
+                bool pass = false;
+                if (i < g_n) {
+                    e = gathered[i];
+                    pass = !compacted || __uint_as_float((uint32_t)(e >> 32)) > thr;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) buf[cnt + __popc(bal & ((1u << lane) - 1u))] = e;
+                cnt += __popc(bal);
+                if (cnt > sel_cap - 32) {
+                    __syncwarp();
+                    thr = fmaxf(thr, warp_compact(buf, cnt, p.kprime, sel_cap, smem_u32(scratch), lane));
+                    cnt = p.kprime;
+                    compacted = true;
+                }
             }
         }
+        __syncthreads();
+    }
+    if (warp == 0) {
         __syncwarp();
         if (cnt > p.kprime) {
             thr = fmaxf(thr, warp_compact(buf, cnt, p.kprime, sel_cap, smem_u32(scratch), lane));
@@ -110,7 +138,7 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
             s_ek_sh = -CUDART_INF;
         }
     } else {
-        // ---- meanwhile: the query in fp64 and its squared norm
+        // ---- the query in fp64 and its squared norm
         double q2 = 0.0;
         for (int d = tid - 32; d < p.dim; d += F2_THREADS - 32) {
             const double v = bits_to_double<DTYPE>(p.queries[(size_t)q * p.dim + d]);
@@ -137,38 +165,26 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
             exact[i] = (double)__uint_as_float((uint32_t)(e >> 32));
         }
     } else {
-        // two half-size staging buffers: while the eight-thread groups of one half of the CTA re-score batch i, the copies of
-        // batch i + 1 are in flight (the stage is latency bound: random 1.5 KB rows from HBM)
-        const int RB = finish2_stage_rows(p.dim) / 2;             // rows per batch
+        const int RB = finish2_stage_rows(p.dim);
         const int l8 = tid & 7, grp = tid >> 3;
         const int vec_per_row = p.dim / 8;                        // 16-byte vectors per row
         const int stride = p.dim * 2 + 16;                        // staged row pitch: +16 bytes keeps the rows of a warp on different banks
         const double* qj = qd + l8;
-        auto issue = [&](int i0, int bufsel) {
+        for (int i0 = 0; i0 < n; i0 += RB) {
             const int rows_here = min(RB, n - i0);
-            char* dstb = stage + (size_t)bufsel * RB * stride;
             for (int r = warp; r < rows_here; r += F2_THREADS / 32) {
                 const uint32_t row = (uint32_t)buf[i0 + r];
                 const uint4* src = reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim);
-                const uint32_t dst = smem_u32(dstb + (size_t)r * stride);
+                const uint32_t dst = smem_u32(stage + (size_t)r * stride);
                 for (int c = lane; c < vec_per_row; c += 32)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * 16), "l"(src + c) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        if (n > 0) issue(0, 0);
-        int bufsel = 0;
-        for (int i0 = 0; i0 < n; i0 += RB, bufsel ^= 1) {
-            if (i0 + RB < n) {
-                issue(i0 + RB, bufsel ^ 1);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-            } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
             const int i = i0 + grp;
             const bool valid = i < n && grp < RB;
-            const uint16_t* x = reinterpret_cast<const uint16_t*>(stage + ((size_t)bufsel * RB + (grp < RB ? grp : 0)) * stride) + l8;
+            const uint16_t* x = reinterpret_cast<const uint16_t*>(stage + (size_t)(grp < RB ? grp : 0) * stride) + l8;
             double acc = 0.0;
             if (valid) {
 #pragma unroll 4
