@@ -168,6 +168,7 @@ def make_sharded_manager_class():
         _compactable = False
 
         def __init__(self, n_total: int, *args, group: Optional[dist.ProcessGroup] = None, **kwargs):
+            kwargs.setdefault("use_graphs", False)             # (the search chain contains a collective; opt in explicitly)
             super().__init__(*args, **kwargs)
             self.group = group
             self.rank, self.world = _rank(group), _world(group)

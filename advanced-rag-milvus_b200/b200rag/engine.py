@@ -52,8 +52,16 @@ class _Workspace:
     def __init__(self):
         self._buf = {}
         self._lock = threading.Lock()
+        self._capture = threading.local()       # .bufs: list collecting the buffers handed out while a CUDA graph is captured
 
     def get(self, device: torch.device, nbytes: int) -> torch.Tensor:
+        bufs = getattr(self._capture, "bufs", None)
+        if bufs is not None:
+            # CUDA-graph capture (B200IndexManager): the scratch must belong to the graph -- allocated from its private pool,
+            # kept alive by it, never shared with eager calls or other graphs
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            bufs.append(buf)
+            return buf
         key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
         with self._lock:
             buf = self._buf.get(key)
@@ -65,6 +73,13 @@ class _Workspace:
     def release(self) -> None:
         with self._lock:
             self._buf.clear()
+
+    def begin_capture(self) -> list:
+        self._capture.bufs = []
+        return self._capture.bufs
+
+    def end_capture(self) -> None:
+        self._capture.bufs = None
 
 
 _WS = _Workspace()

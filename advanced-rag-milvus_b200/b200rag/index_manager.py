@@ -447,7 +447,8 @@ class B200IndexManager:
     def __init__(self, semantic_dim: int = 1536, sparse_dim: int = 10000, domain_dim: int = 768,
                  device: str = "cuda", dtype: str = "f16", enable_sparse: Optional[bool] = None,
                  sparse_block_docs: int = 16384, host: str = "", port: int = 0, connect: bool = True,
-                 micro_batch: bool = False, max_batch: int = 256, max_wait_ms: float = 0.5, **_ignored):
+                 micro_batch: bool = False, max_batch: int = 256, max_wait_ms: float = 0.5,
+                 use_graphs: Optional[bool] = None, **_ignored):
         # host / port / connect / enable_sharding / num_shards are accepted for signature compatibility with
         # MilvusIndexManager(...) (indexing.py:86-96); there is no server to connect to.
         self.semantic_dim, self.sparse_dim, self.domain_dim = int(semantic_dim), int(sparse_dim), int(domain_dim)
@@ -483,6 +484,12 @@ class B200IndexManager:
         self._live_words: Optional[Tuple[int, torch.Tensor]] = None
         self._mask_cache: "OrderedDict[str, Tuple[int, int, Optional[torch.Tensor]]]" = OrderedDict()
         self._pinned: Dict[Tuple, torch.Tensor] = {}
+        # CUDA graphs of the dense search chain (prepare, sample, scan, finish, gated fallbacks: ~15 launches), replayed by
+        # search_batch_arrays for repeated (collection, batch, k, filter) shapes: the host cost of a search drops to one copy +
+        # one launch, which is what bounds batch-1 latency and small shards.  Off when B200RAG_GRAPHS=0.
+        self.use_graphs = (os.getenv("B200RAG_GRAPHS", "1") != "0") if use_graphs is None else bool(use_graphs)
+        self._graphs: "OrderedDict[Tuple, Any]" = OrderedDict()
+        self._graph_seen: Dict[Tuple, int] = {}
         self.collections: Dict[str, _Collection] = {"semantic_index": _Collection("semantic_index", "dense", self),
                                                     "domain_index": _Collection("domain_index", "dense", self)}
         if enable_sparse:
@@ -695,6 +702,8 @@ class B200IndexManager:
         self._gen += 1
         self._tok_dev = None
         self._mask_cache.clear()
+        self._graphs.clear()                                 # captured pointers / sizes are stale
+        self._graph_seen.clear()
 
     async def index_chunks(self, chunks: List[Any], domain: Optional[str] = None) -> Dict[str, Any]:
         """Reference MilvusIndexManager.index_chunks (indexing.py:264-437): embed every chunk through the generator
@@ -915,6 +924,61 @@ class B200IndexManager:
         s, i, c = self._sparse.search(qp, qt, qv, k, doc_mask=words)
         return s.to(torch.float64), i, c
 
+    GRAPH_CACHE_SIZE = 4
+    GRAPH_AFTER_CALLS = 3                                    # a shape is captured when it shows up for the third time
+
+    def _search_for_host(self, queries: Any, collection_name: str, k: int, filters: Optional[str]):
+        """search_batch_ids for callers that copy the result to the host right away (search_batch_arrays): dense searches of a
+        repeated shape are replayed from a CUDA graph.  The graph's outputs are reused by the next replay, which is why this
+        path is not offered to callers that keep device tensors."""
+        if (not self.use_graphs or collection_name not in _DENSE or collection_name not in self.collections or k <= 0):
+            return self.search_batch_ids(queries, collection_name, k, filters)
+        idx = self._dense_of(collection_name)
+        q = queries if torch.is_tensor(queries) else torch.as_tensor(np.asarray(queries, dtype=np.float32))
+        if q.dim() == 1:
+            q = q[None, :]
+        if idx.n == 0 or q.dim() != 2 or q.shape[1] != idx.dim or q.shape[0] == 0:
+            return self.search_batch_ids(q, collection_name, k, filters)
+        m, words = self._filter_words(filters)
+        if m == 0:
+            return self._search_masked(q, collection_name, k, m, words)
+        stream = torch.cuda.current_stream(self.device)
+        key = (collection_name, int(q.shape[0]), k, filters or "", self._gen, stream.cuda_stream, threading.get_ident())
+        entry = self._graphs.get(key)
+        if entry is None:
+            seen = self._graph_seen.get(key, 0) + 1
+            self._graph_seen[key] = seen
+            if seen < self.GRAPH_AFTER_CALLS or seen > self.GRAPH_AFTER_CALLS + 2:      # (a failed capture is not retried forever)
+                return self._search_masked(q, collection_name, k, m, words)
+            entry = self._capture_search(q, collection_name, k, m, words)
+            if entry is None:
+                return self._search_masked(q, collection_name, k, m, words)
+            self._graphs[key] = entry
+            while len(self._graphs) > self.GRAPH_CACHE_SIZE:
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
+        graph, q_static, out, _keep = entry
+        q_static.copy_(q, non_blocking=True)
+        graph.replay()
+        return out
+
+    def _capture_search(self, q: torch.Tensor, collection_name: str, k: int, m: int, words: Optional[torch.Tensor]):
+        """Capture one dense search into a CUDA graph (static fp32 query buffer in, static result tensors out)."""
+        q_static = torch.empty(tuple(q.shape), dtype=torch.float32, device=self.device)
+        q_static.copy_(q, non_blocking=True)
+        bufs = engine._WS.begin_capture()
+        try:
+            torch.cuda.current_stream(self.device).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._search_masked(q_static, collection_name, k, m, words)
+        except Exception:  # noqa: BLE001 - anything that cannot be captured keeps running eagerly
+            return None
+        finally:
+            engine._WS.end_capture()
+        return graph, q_static, out, (list(bufs), words)
+
     def _pinned_like(self, tag: str, t: torch.Tensor) -> torch.Tensor:
         key = (tag, tuple(t.shape), t.dtype, threading.get_ident())
         buf = self._pinned.get(key)
@@ -930,7 +994,7 @@ class B200IndexManager:
         """The columnar plugin call: the batched search with HOST results -- numpy rows / scores / counts, copied through
         pinned buffers with one synchronisation -- and the payload one gather away (`.hits()`, `.chunk_ids()`)."""
         with self._lock:
-            s, i, c = self.search_batch_ids(queries, collection_name, top_k, filters)
+            s, i, c = self._search_for_host(queries, collection_name, int(top_k), filters)
             hs, hi, hc = self._pinned_like("s", s), self._pinned_like("i", i), self._pinned_like("c", c)
             hs.copy_(s, non_blocking=True)
             hi.copy_(i, non_blocking=True)
@@ -1151,3 +1215,4 @@ class B200IndexManager:
             self._dev_cols.clear()
             self._mask_cache.clear()
             self._pinned.clear()
+            self._graphs.clear()

@@ -305,3 +305,34 @@ def test_mmr_large_vocabularies_match_oracle(vocab):
         sets = [frozenset(ti[dp[d]: dp[d + 1]].tolist()) for d in cand[q, : n[q]]]
         ref = fusion.mmr_select(list(rel[q, : n[q]]), sets, ks[q], lam[q])
         assert picks[q, : int(pn[q])].cpu().tolist() == ref, q
+
+
+def test_graph_replay_returns_the_same_results_as_eager_search(oracle_lib):
+    """search_batch_arrays replays a captured CUDA graph from the third call of a (collection, batch, k, filter) shape on: every
+    replay must equal the oracle for ITS queries, with and without a filter, and an insert must drop the stale graphs."""
+    from b200rag import synth
+    from b200rag.index_manager import eval_filter_host
+    o = oracle_lib
+    m, x, _, contents, meta = _manager(n=30000)
+    assert m.use_graphs
+    xb = o.normalize_rows(x, o.F16)
+    expr = "entropy >= 0.5"
+    rows = np.flatnonzero(eval_filter_host(m.payload, expr))
+    for it in range(7):
+        q = synth.dense_rows(40, 64, 500 + it)
+        qb = o.normalize_rows(q, o.F16)
+        arr = m.search_batch_arrays(torch.from_numpy(q).pin_memory(), "semantic_index", 10)
+        s, i = o.dense_topk(xb, qb, 10, o.F16)
+        assert np.array_equal(arr.rows, i) and np.array_equal(arr.scores, s), it
+        fa = m.search_batch_arrays(q, "semantic_index", 10, filters=expr)
+        s, i = o.dense_topk(xb[rows], qb, 10, o.F16)
+        assert np.array_equal(fa.rows, rows[i]) and np.array_equal(fa.scores, s), it
+        one = m.search_batch_arrays(q[0], "semantic_index", 5)
+        s1, i1 = o.dense_topk(xb, qb[:1], 5, o.F16)
+        assert np.array_equal(one.rows, i1) and np.array_equal(one.scores, s1), it
+    assert len(m._graphs) == 3                                       # the three shapes above
+    m.add(["new0"], ["fresh text"], 10.0 * x[:1], None, None, None)
+    assert len(m._graphs) == 0
+    for it in range(4):
+        arr = m.search_batch_arrays(x[:1], "semantic_index", 2)
+        assert arr.chunk_ids()[0] == ["c000000", "new0"] and arr.scores[0, 0] == arr.scores[0, 1]
