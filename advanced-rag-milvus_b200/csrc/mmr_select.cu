@@ -23,6 +23,13 @@
 
 namespace b200rag {
 
+// mmr_inv.cu: the inverted-list kernel (third generation), the product path for n_max <= 1024 and vocabularies up to ~1M tokens
+size_t mmr_inv_smem_bytes(int vocab_words);
+size_t mmr_inv_workspace_bytes(int n_queries, int t_cap);
+int launch_mmr_inv(const int32_t* cand_doc, const double* cand_rel, const int32_t* cand_n, int n_queries, int n_max,
+                   const int64_t* doc_tok_ptr, const int32_t* doc_tok_ids, int vocab_words, const double* lambda, const int32_t* k_sel,
+                   int k_max, int32_t* out_pick, int32_t* out_n, void* workspace, int t_cap, cudaStream_t st);
+
 constexpr int MMR_MAX_THREADS = 1024;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int MMR_G = 4;      // candidates a warp keeps in flight
@@ -37,11 +44,12 @@ mmr_select_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict
                   int n_max, const int64_t* __restrict__ doc_tok_ptr, const int32_t* __restrict__ doc_tok_ids, int vocab_words,
                   const double* __restrict__ lambda, const int32_t* __restrict__ k_sel, int k_max,
                   int32_t* __restrict__ out_pick, int32_t* __restrict__ out_n, int cache_cap, int n_hi,
-                  uint32_t* __restrict__ bits_global) {
+                  uint32_t* __restrict__ bits_global, int only_marked) {
     extern __shared__ __align__(16) char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     const int q = blockIdx.x;
+    if (only_marked && out_n[q] != -2) return;            // served by mmr_select_inv_kernel (mmr_inv.cu)
     double* rel = reinterpret_cast<double*>(smem);                 // [n_max]
     double* max_sim = rel + n_max;                                 // [n_max]
     int64_t* tok_begin = reinterpret_cast<int64_t*>(max_sim + n_max);   // [n_max] start of the candidate's token list
@@ -284,10 +292,11 @@ __global__ void __launch_bounds__(MMT_THREADS, 1)
 mmr_select_sorted_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict__ cand_rel, const int32_t* __restrict__ cand_n,
                          int n_max, const int64_t* __restrict__ doc_tok_ptr, const int32_t* __restrict__ doc_tok_ids, int vocab_words,
                          const double* __restrict__ lambda, const int32_t* __restrict__ k_sel, int k_max,
-                         int32_t* __restrict__ out_pick, int32_t* __restrict__ out_n, int cache_cap, int n_hi) {
+                         int32_t* __restrict__ out_pick, int32_t* __restrict__ out_n, int cache_cap, int n_hi, int only_marked) {
     extern __shared__ __align__(16) char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = blockIdx.x;
+    if (only_marked && out_n[q] != -2) return;            // served by mmr_select_inv_kernel (mmr_inv.cu)
     uint32_t* bits = reinterpret_cast<uint32_t*>(smem);                              // [vocab_words]
     uint16_t* cache = reinterpret_cast<uint16_t*>(bits + vocab_words);               // [cache_cap]
     __shared__ int s_hist[MMT_LEN_BINS];
@@ -502,9 +511,16 @@ static bool mmr_bits_in_smem(int n_max, int vocab_words) {
     return mmr_fixed_bytes(n_max) + (size_t)vocab_words * 4 + (size_t)n_max * 4 + 8 <= 200 * 1024;
 }
 
+// Incidences (candidate, token) the inverted-list kernel has room for per query: 256 tokens per candidate on average.
+static int mmr_inv_t_cap(int n_max) { return n_max * 256; }
+static bool mmr_inv_usable(int n_max, int vocab_words) {
+    return n_max <= 1024 && mmr_inv_smem_bytes(vocab_words) <= 200 * 1024 && option(OPT_MMR_PATH, 0) == 0;
+}
+
 size_t b200rag_mmr_select_workspace_bytes(int32_t n_queries, int32_t n_max, int32_t vocab_size) {
     if (n_queries <= 0 || n_max <= 0 || vocab_size <= 0) return 256;
     const int vocab_words = (vocab_size + 31) / 32;
+    if (mmr_inv_usable(n_max, vocab_words)) return mmr_inv_workspace_bytes(n_queries, mmr_inv_t_cap(n_max));
     if (mmr_bits_in_smem(n_max, vocab_words)) return 256;
     return align_up((size_t)n_queries * vocab_words * 4, 256) + 256;      // one bitset slice per query
 }
@@ -521,7 +537,18 @@ int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const in
     // tokens >= (n_hi << 16) do not exist; n_hi thresholds per candidate give the high bits of cached tokens back
     int n_hi = (vocab_size - 1) >> 16;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (n_max >= 32 && n_max <= MMT_THREADS && n_hi <= 2 && option(OPT_MMR_PATH, 0) == 0) {
+    // Product path: the inverted-list kernel (mmr_inv.cu).  It marks the queries it cannot hold (out_n = -2); the bitset kernels
+    // below are then launched for exactly those -- every other CTA of theirs leaves at once.  With a workspace that is too small
+    // (callers of ABI version 1 passed 256 bytes) the bitset kernels serve every query, as before.
+    int only_marked = 0;
+    if (mmr_inv_usable(n_max, vocab_words) && workspace &&
+        workspace_bytes >= mmr_inv_workspace_bytes(n_queries, mmr_inv_t_cap(n_max)) && ((uintptr_t)workspace & 255) == 0) {
+        int rc = launch_mmr_inv(cand_doc, cand_rel, cand_n, n_queries, n_max, doc_tok_ptr, doc_tok_ids, vocab_words, lambda, k_sel,
+                                k_max, out_pick, out_n, workspace, mmr_inv_t_cap(n_max), st);
+        if (rc) return rc;
+        only_marked = 1;
+    }
+    if (n_max >= 32 && n_max <= MMT_THREADS && n_hi <= 2 && option(OPT_MMR_PATH, 0) != 1) {
         // fast path: one thread per candidate, transposed token cache (static shared memory of the kernel: ~7 KB)
         const size_t limit = 227 * 1024 - 8192;
         const size_t bits_bytes = (size_t)vocab_words * 4;
@@ -530,7 +557,7 @@ int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const in
             const size_t smem_t = bits_bytes + (size_t)cap * 2;
             B200_CUDA_CHECK(cudaFuncSetAttribute(mmr_select_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
             mmr_select_sorted_kernel<<<n_queries, MMT_THREADS, smem_t, st>>>(cand_doc, cand_rel, cand_n, n_max, doc_tok_ptr, doc_tok_ids,
-                                                                              vocab_words, lambda, k_sel, k_max, out_pick, out_n, cap, n_hi);
+                                                                              vocab_words, lambda, k_sel, k_max, out_pick, out_n, cap, n_hi, only_marked);
             count_launch();
             B200_CUDA_CHECK(cudaGetLastError());
             return B200RAG_OK;
@@ -566,7 +593,7 @@ int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const in
     // one warp per candidate in the intersection phase: as many warps as there are candidates, up to 32
     const int threads = n_max >= 32 ? MMR_MAX_THREADS : (n_max >= 8 ? 256 : 128);
     mmr_select_kernel<<<n_queries, threads, smem, st>>>(cand_doc, cand_rel, cand_n, n_max, doc_tok_ptr, doc_tok_ids,
-                                                           vocab_words, lambda, k_sel, k_max, out_pick, out_n, cache_cap, n_hi, bits_global); count_launch();
+                                                           vocab_words, lambda, k_sel, k_max, out_pick, out_n, cache_cap, n_hi, bits_global, only_marked); count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;
 }

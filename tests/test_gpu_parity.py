@@ -390,15 +390,16 @@ def test_mmr_batch_matches_oracle_random(eng):
         assert picks[q, : int(n[q])].cpu().tolist() == ref, q
 
 
-@pytest.mark.parametrize("force_warp_kernel", [False, True])
-def test_mmr_config4_scale_matches_oracle(eng, force_warp_kernel):
+@pytest.mark.parametrize("mmr_path", [-1, 2, 1])
+def test_mmr_config4_scale_matches_oracle(eng, mmr_path):
     """BASELINE config-4 shape for the diversification: ~1000 candidates with ~90 unique tokens each out of a 100K-term
-    Zipf vocabulary (token ids beyond 65535 exercise the 16-bit token cache), lambda 0.7, k = 100.  Both MMR kernels
-    (thread-per-candidate fast path, warp-per-candidate general path) against the oracle restatement of the reference."""
+    Zipf vocabulary (token ids beyond 65535 exercise the 16-bit token cache), lambda 0.7, k = 100.  All three MMR kernels
+    (-1: inverted candidate lists, the product path; 2: thread-per-candidate bitset probes; 1: warp-per-candidate general path)
+    against the oracle restatement of the reference."""
     from b200rag import synth
     from b200rag import _lib
     from oracle import fusion
-    _lib.set_option("mmr_path", 1 if force_warp_kernel else -1)
+    _lib.set_option("mmr_path", mmr_path)
     vocab, n_docs, b, n_max, k = 100_000, 4000, 3, 1000, 100
     dp, ti, _ = synth.zipf_corpus(n_docs, vocab, 3)
     rng = np.random.default_rng(17)
