@@ -30,6 +30,8 @@ constexpr int MI_WARPS = MI_THREADS / 32;
 constexpr unsigned MI_FULL = 0xffffffffu;
 constexpr int MI_MAX_D = 65535;             // compact ids are u16
 constexpr int MI_MAX_LEN = 1024;            // tokens per document (the picked document's lists are scanned by one thread each)
+constexpr int MI_STAGE = 32768;             // incidences of one pick staged in shared memory per round (64 KB)
+constexpr uint32_t MI_PAD = 0xffffu;        // filler of lists of odd length (lists are copied as aligned 4-byte words)
 
 __device__ __forceinline__ bool mi_better(double ob, int oi, double b, int bi) {
     return oi != 0x7fffffff && (bi == 0x7fffffff || ob > b || (ob == b && oi < bi));
@@ -74,9 +76,10 @@ mmr_select_inv_kernel(const int32_t* __restrict__ cand_doc, const double* __rest
     uint32_t* bits = reinterpret_cast<uint32_t*>(smem);                          // [vocab_words] tokens present among the candidates
     uint16_t* wpre = reinterpret_cast<uint16_t*>(bits + vocab_words);             // [vocab_words] compact id of a word's first token
     uint32_t* cand_off = reinterpret_cast<uint32_t*>(wpre + vocab_words + (vocab_words & 1));   // [MI_THREADS] start of c's fwd list
-    uint32_t* inter = cand_off + MI_THREADS;                                      // [MI_THREADS] per-candidate intersection counters
-    uint32_t* s_b = inter + MI_THREADS;                                           // [MI_THREADS] picked doc: begin of token t's list
+    uint32_t* inter = cand_off + MI_THREADS;                                      // [MI_THREADS + 32] per-candidate intersection counters (+ a sink for the filler)
+    uint32_t* s_b = inter + MI_THREADS + 32;                                           // [MI_THREADS] picked doc: begin of token t's list
     uint32_t* s_pre = s_b + MI_THREADS;                                           // [MI_THREADS] picked doc: flat prefix of list lengths
+    uint16_t* stage = reinterpret_cast<uint16_t*>(s_pre + MI_THREADS);            // [MI_STAGE] the pick's inverted lists, back to back
     __shared__ int s_wsum[33];
     __shared__ double s_best[MI_WARPS];
     __shared__ int s_best_idx[MI_WARPS];
@@ -142,7 +145,7 @@ mmr_select_inv_kernel(const int32_t* __restrict__ cand_doc, const double* __rest
             for (int w = w0; w < w1; ++w) { wpre[w] = (uint16_t)run; run += __popc(bits[w]); }
         }
     }
-    if (n_distinct > MI_MAX_D) {
+    if (n_distinct > MI_MAX_D || total_tok + n_distinct > t_cap) {        // (every list may grow by one filler entry)
         if (tid == 0) out_n[q] = -2;
         return;
     }
@@ -167,16 +170,22 @@ mmr_select_inv_kernel(const int32_t* __restrict__ cand_doc, const double* __rest
     {
         const int per = (n_distinct + MI_THREADS) / MI_THREADS;            // covers indices 1 .. n_distinct
         const int i0 = 1 + tid * per, i1 = min(n_distinct + 1, i0 + per);
+        // lists are padded to an even length so that every list starts on a 4-byte boundary of inv (cp.async granularity)
         int sum = 0;
-        for (int i = i0; i < i1; ++i) sum += (int)start[i];
+        for (int i = i0; i < i1; ++i) sum += ((int)start[i] + 1) & ~1;
         int tot = 0;
         int run = mi_block_scan(sum, s_wsum, &tot);
         // start[i] (i >= 1) holds count(i - 1); the exclusive prefix over those slots leaves begin(id) in start[id + 1]
-        for (int i = i0; i < i1; ++i) { const int cnt = (int)start[i]; start[i] = (uint32_t)run; run += cnt; }
+        for (int i = i0; i < i1; ++i) {
+            const int cnt = (int)start[i];
+            start[i] = (uint32_t)run;
+            if (cnt & 1) inv[run + cnt] = (uint16_t)MI_PAD;            // filler behind a list of odd length
+            run += (cnt + 1) & ~1;
+        }
     }
     __syncthreads();
-    // the scatter takes its slot from start[id + 1] and advances it, so afterwards start[id + 1] = end(id):
-    // list(id) = [start[id], start[id + 1])  with start[0] = 0 never touched
+    // the scatter takes its slot from start[id + 1] and advances it, so afterwards start[id + 1] = end(id) (before the filler):
+    // list(id) occupies [even(start[id]), start[id + 1]) plus the filler; start[0] = 0 is never touched
     for (int cc = warp; cc < n; cc += MI_WARPS) {
         const int lc = (int)(doc_tok_ptr[docs[cc] + 1] - doc_tok_ptr[docs[cc]]);
         const uint16_t* src = fwd + cand_off[cc];
@@ -235,26 +244,36 @@ mmr_select_inv_kernel(const int32_t* __restrict__ cand_doc, const double* __rest
         if (tid < len_p) {
             // (ld.cg: the scatter advanced these slots with L2 atomics after this SM had read them -- its L1 may be stale)
             const int id = __ldcg(fwd + cand_off[pick] + tid);
-            lb = __ldcg(start + id);                          // begin(id) = end(id - 1); start[0] = 0
-            ll = __ldcg(start + id + 1) - lb;
+            lb = (__ldcg(start + id) + 1u) & ~1u;             // begin(id): end(id - 1) rounded up over its filler; start[0] = 0
+            ll = ((__ldcg(start + id + 1) - lb) + 1u) & ~1u;  // padded length (the filler counts into a sink slot)
         }
         int total = 0;
         const int pre = mi_block_scan((int)ll, s_wsum, &total);
         s_b[tid] = lb;
         s_pre[tid] = (uint32_t)pre;
         __syncthreads();
-        // 3. one flat pass over all incidences (token of the pick, candidate holding it)
-        for (int w = tid; w < total; w += MI_THREADS) {
-            int lo = 0, hi = len_p - 1;                       // last token whose prefix is <= w
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if ((int)s_pre[mid] <= w) lo = mid;
-                else hi = mid - 1;
+        // 3. the lists are copied into shared memory back to back -- aligned 4-byte cp.async copies, a warp per list, nothing
+        //    waits on a load until all of them are in flight -- and then counted as one flat array: which token an entry
+        //    belongs to no longer matters
+        for (int r0 = 0; r0 < total; r0 += MI_STAGE) {        // (one round unless the pick shares > 32768 incidences)
+            for (int t = warp; t < len_p; t += MI_WARPS) {
+                const int p0 = (int)s_pre[t], p1 = t + 1 < len_p ? (int)s_pre[t + 1] : total;
+                const int a0 = max(p0, r0), a1 = min(p1, r0 + MI_STAGE);          // this round's part of list t (even bounds)
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(inv + s_b[t] + (uint32_t)(a0 - p0));
+                uint32_t* dst = reinterpret_cast<uint32_t*>(stage + (a0 - r0));
+                for (int j = lane; j < (a1 - a0) / 2; j += 32)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + j)), "l"(src + j) : "memory");
             }
-            const int cc = __ldcg(inv + s_b[lo] + (uint32_t)(w - (int)s_pre[lo]));
-            atomicAdd(&inter[cc], 1u);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            const int n_here = min(MI_STAGE, total - r0);
+            for (int w = tid; w < n_here; w += MI_THREADS) {
+                const uint32_t cc = stage[w];
+                atomicAdd(&inter[cc < MI_THREADS ? cc : MI_THREADS], 1u);        // (filler -> sink slot)
+            }
+            __syncthreads();
         }
-        __syncthreads();
         // 4. every candidate folds its intersection into its running maximum (integer fractions; divide only on change)
         {
             const int in = (int)inter[tid];
@@ -277,7 +296,8 @@ mmr_select_inv_kernel(const int32_t* __restrict__ cand_doc, const double* __rest
 }
 
 size_t mmr_inv_smem_bytes(int vocab_words) {
-    return (size_t)vocab_words * 4 + (size_t)(vocab_words + (vocab_words & 1)) * 2 + (size_t)4 * MI_THREADS * 4 + 64;
+    return (size_t)vocab_words * 4 + (size_t)(vocab_words + (vocab_words & 1)) * 2 + (size_t)(4 * MI_THREADS + 32) * 4 +
+           (size_t)MI_STAGE * 2 + 64;
 }
 
 // Per query: forward + inverted lists (u16 each, t_cap entries) and the list starts (u32, 65536 + 1 entries).
