@@ -1,26 +1,30 @@
-// mmr_inv.cu -- greedy MMR on token-set Jaccard, third kernel generation: per-query INVERTED candidate lists  (K6).
+// mmr_inv.cu -- greedy MMR on token-set Jaccard, third kernel generation: heavy-token bitsets + light-token inverted lists  (K6).
 //
 // Same arithmetic and tie rule as mmr_select.cu (reference src/advanced_rag/retrieval.py:493-516).  What changes is how
 // |tokens(c) & tokens(pick)| is found for every candidate c after a pick.  The first two generations probe, for every alive
-// candidate, each of its ~90 tokens against a bitset of the picked document: n x len probes per pick (10^5 at config 4),
-// although two random documents share only ~20 tokens.  Here the candidate x token incidence of the query is transposed ONCE:
+// candidate, each of its ~90 tokens against a bitset of the picked document: n x len probes per pick (10^5 at config 4).
+// A first inverted-list version (candidate lists per token, counting sort through global memory) cut the per-pick work to
+// sum_c |tokens(c) & tokens(pick)| ~ 28K counter increments but paid 0.8 ms per query to build the lists: a handful of very
+// common tokens sit in almost every candidate, so both the build's atomics and the per-pick increments pile up on them
+// (measured: profiles/r2_mmr.md).  This version splits the query's vocabulary in two:
 //
-//   build   1. every token of every candidate is marked in a vocabulary bitmap (shared memory); a prefix popcount turns a
-//              token id into a COMPACT id 0 .. D-1 (D = distinct tokens among the query's candidates, < 65536);
-//           2. the candidates' lists are rewritten as compact ids (fwd, u16, global workspace) and counted per compact id;
-//           3. an exclusive scan turns the counts into list starts and a scatter fills  inv[start[id] ..] = the candidates
-//              that hold token id  (counting sort, candidate order inside a list is irrelevant).
-//   pick    the picked document's ~90 compact ids name ~90 inverted lists; their postings -- one per (token, candidate)
-//           incidence, i.e. exactly sum_c |tokens(c) & tokens(pick)| of them, ~25 per thread instead of ~90 probes -- are walked
-//           as one flat index space and counted into per-candidate shared-memory counters.
+//   heavy   tokens seen in at least two of the first 32 candidates (the sample runs in shared memory; in a Zipf corpus that is
+//           the ~300 tokens held by more than a few percent of the candidates), at most 384 of them.  Every candidate keeps a
+//           384-bit set of its heavy tokens; |heavy(c) & heavy(pick)| is twelve AND + POPC per candidate per pick, no atomics.
+//   light   every other token.  Their (token, candidate) incidences -- ~70 per candidate -- are bucketed by a hash of the token
+//           into 4096 lists (counting sort: the counters live in shared memory and a light token is by construction rare, so
+//           nothing piles up; the entries  token << 10 | candidate  go to a global workspace that stays in L2).  After a pick,
+//           a warp per light token of the picked document reads that token's bucket (one coalesced line, ~17 entries) and bumps
+//           the counter of every candidate whose entry carries the same token: sum_c |light(c) & light(pick)| ~ 300 increments.
+//   Which tokens are called heavy never changes a result -- the two parts always add up to the exact intersection -- it only
+//   moves work between the two mechanisms, so the sample needs no guarantee.
 //   The running max similarity is kept as an integer fraction: inter/union > num/den  <=>  inter*den > num*union, exact in
 //   64-bit integers and equivalent to comparing the correctly rounded fp64 quotients (distinct fractions with denominators
 //   < 2^17 differ by more than 2^-34); the fp64 division -- ~50 instructions -- runs only when a candidate's maximum changes.
 //
-// One 1024-thread CTA per query, thread = candidate; ~30 KB of shared memory at a 100K-token vocabulary, so two CTAs share an
-// SM and 256 queries run in one wave.  Queries the scheme cannot hold (more than 65535 distinct tokens, a document of more than
-// 1024 tokens, more incidences than the workspace has room for) are marked and served by the bitset kernels of mmr_select.cu,
-// which are launched behind this one and leave at once for every other query.
+// One 1024-thread CTA per query, thread = candidate; ~100 KB of shared memory at a 100K-token vocabulary, so two CTAs share an
+// SM.  Queries the scheme cannot hold (more incidences than the workspace has room for) are marked and served by the bitset
+// kernels of mmr_select.cu, which are launched behind this one and leave at once for every other query.
 #include "common.cuh"
 
 namespace b200rag {
@@ -28,14 +32,15 @@ namespace b200rag {
 constexpr int MI_THREADS = 1024;
 constexpr int MI_WARPS = MI_THREADS / 32;
 constexpr unsigned MI_FULL = 0xffffffffu;
-constexpr int MI_MAX_D = 65535;             // compact ids are u16
-constexpr int MI_MAX_LEN = 1024;            // tokens per document (the picked document's lists are scanned by one thread each)
-constexpr int MI_STAGE = 32768;             // incidences of one pick staged in shared memory per round (64 KB)
-constexpr uint32_t MI_PAD = 0xffffu;        // filler of lists of odd length (lists are copied as aligned 4-byte words)
+constexpr int MI_H_WORDS = 12;              // heavy-token bitset words per candidate
+constexpr int MI_H = MI_H_WORDS * 32;       // heavy tokens per query (384)
+constexpr int MI_SAMPLE = 32;               // candidates sampled for the heavy set (one per warp)
+constexpr int MI_NB_LOG = 12;
+constexpr int MI_NB = 1 << MI_NB_LOG;       // hash buckets of the light-token incidences
+constexpr int MI_CAND_BITS = 10;            // entry = token << 10 | candidate  (token ids < 2^22)
+constexpr int MI_TOK_UNROLL = 4;            // tokens a lane (build) / a warp (pick) has in flight
 
-__device__ __forceinline__ bool mi_better(double ob, int oi, double b, int bi) {
-    return oi != 0x7fffffff && (bi == 0x7fffffff || ob > b || (ob == b && oi < bi));
-}
+__device__ __forceinline__ uint32_t mi_bucket(int t) { return ((uint32_t)t * 2654435761u) >> (32 - MI_NB_LOG); }
 
 // exclusive block scan of one int per thread (1024 threads); returns the prefix, *total = sum.  Two barriers.
 __device__ __forceinline__ int mi_block_scan(int v, int* s_wsum, int* total) {
@@ -68,26 +73,24 @@ __global__ void __launch_bounds__(MI_THREADS, 2)
 mmr_select_inv_kernel(const int32_t* __restrict__ cand_doc, const double* __restrict__ cand_rel, const int32_t* __restrict__ cand_n,
                       int n_max, const int64_t* __restrict__ doc_tok_ptr, const int32_t* __restrict__ doc_tok_ids, int vocab_words,
                       const double* __restrict__ lambda, const int32_t* __restrict__ k_sel, int k_max,
-                      int32_t* __restrict__ out_pick, int32_t* __restrict__ out_n,
-                      uint16_t* __restrict__ ws_fwd, uint16_t* __restrict__ ws_inv, uint32_t* __restrict__ ws_start, int t_cap) {
+                      int32_t* __restrict__ out_pick, int32_t* __restrict__ out_n, uint32_t* __restrict__ ws_ent, int t_cap) {
     extern __shared__ __align__(16) char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = blockIdx.x;
-    uint32_t* bits = reinterpret_cast<uint32_t*>(smem);                          // [vocab_words] tokens present among the candidates
-    uint16_t* wpre = reinterpret_cast<uint16_t*>(bits + vocab_words);             // [vocab_words] compact id of a word's first token
-    uint32_t* cand_off = reinterpret_cast<uint32_t*>(wpre + vocab_words + (vocab_words & 1));   // [MI_THREADS] start of c's fwd list
-    uint32_t* inter = cand_off + MI_THREADS;                                      // [MI_THREADS + 32] per-candidate intersection counters (+ a sink for the filler)
-    uint32_t* s_b = inter + MI_THREADS + 32;                                           // [MI_THREADS] picked doc: begin of token t's list
-    uint32_t* s_pre = s_b + MI_THREADS;                                           // [MI_THREADS] picked doc: flat prefix of list lengths
-    uint16_t* stage = reinterpret_cast<uint16_t*>(s_pre + MI_THREADS);            // [MI_STAGE] the pick's inverted lists, back to back
+    long long* s_tb = reinterpret_cast<long long*>(smem);                         // [MI_THREADS] first token of candidate c
+    int* s_len = reinterpret_cast<int*>(s_tb + MI_THREADS);                       // [MI_THREADS] tokens of candidate c
+    uint32_t* inter = reinterpret_cast<uint32_t*>(s_len + MI_THREADS);            // [MI_THREADS] light-token intersection counters
+    uint32_t* bstart = inter + MI_THREADS;                                        // [MI_NB] bucket counts -> starts -> ends
+    uint32_t* hb = bstart + MI_NB;                                                // [MI_THREADS][MI_H_WORDS] heavy sets
+    uint32_t* seen1 = hb;                                                         // [vocab_words] sample: token seen (aliases hb, dead before hb is filled)
+    uint32_t* heavy = hb + MI_H_WORDS * MI_THREADS;                               // [vocab_words] sample: token seen twice = heavy
+    uint16_t* hpre = reinterpret_cast<uint16_t*>(heavy + vocab_words);            // [vocab_words] heavy rank of a word's first token
     __shared__ int s_wsum[33];
-    __shared__ double s_best[MI_WARPS];
+    __shared__ unsigned long long s_key[MI_WARPS];
     __shared__ int s_best_idx[MI_WARPS];
-    __shared__ int s_pick, s_done, s_fail;
+    __shared__ int s_done;
 
-    uint16_t* fwd = ws_fwd + (size_t)q * t_cap;
-    uint16_t* inv = ws_inv + (size_t)q * t_cap;
-    uint32_t* start = ws_start + (size_t)q * (MI_MAX_D + 1);
+    uint32_t* ent = ws_ent + (size_t)q * t_cap;
 
     const int n = min(min(cand_n[q], n_max), MI_THREADS);
     const int k = min(min(k_sel[q], k_max), n);
@@ -103,96 +106,118 @@ mmr_select_inv_kernel(const int32_t* __restrict__ cand_doc, const double* __rest
     // ---- this thread's candidate
     const int c = tid;
     double rel = 0.0;
-    long long tbeg = 0;
     int len = 0;
     bool alive = c < n;
-    if (alive) {
-        rel = cand_rel[(size_t)q * n_max + c];
-        tbeg = doc_tok_ptr[docs[c]];
-        len = (int)(doc_tok_ptr[docs[c] + 1] - tbeg);
+    {
+        long long tbeg = 0;
+        if (alive) {
+            rel = cand_rel[(size_t)q * n_max + c];
+            tbeg = doc_tok_ptr[docs[c]];
+            len = (int)(doc_tok_ptr[docs[c] + 1] - tbeg);
+        }
+        s_tb[tid] = tbeg;
+        s_len[tid] = len;
     }
-    for (int i = tid; i < vocab_words; i += MI_THREADS) bits[i] = 0u;
+    for (int i = tid; i < vocab_words; i += MI_THREADS) { seen1[i] = 0u; heavy[i] = 0u; }
+    for (int i = tid; i < MI_NB; i += MI_THREADS) bstart[i] = 0u;
     inter[tid] = 0u;
-    if (tid == 0) { s_done = 0; s_fail = 0; }
+    if (tid == 0) s_done = 0;
     int total_tok = 0;
-    const int off = mi_block_scan(len, s_wsum, &total_tok);   // (its barriers also publish the zeroed arrays)
-    cand_off[tid] = (uint32_t)off;
-    if (len > MI_MAX_LEN) s_fail = 1;
-    __syncthreads();
-    if (total_tok > t_cap || s_fail) {                        // not representable here: mmr_select.cu's kernels take the query
+    mi_block_scan(len, s_wsum, &total_tok);                   // (its barriers also publish the zeroed arrays)
+    if (total_tok > t_cap) {                                  // not representable here: mmr_select.cu's kernels take the query
         if (tid == 0) out_n[q] = -2;
         return;
     }
-    // ---- build 1: mark every candidate token (warp per candidate, coalesced reads)
-    for (int cc = warp; cc < n; cc += MI_WARPS) {
-        const long long tb = doc_tok_ptr[docs[cc]];
-        const int lc = (int)(doc_tok_ptr[docs[cc] + 1] - tb);
+    // ---- build 1: the heavy set = tokens in at least two of the first MI_SAMPLE candidates (one candidate per warp)
+    if (warp < min(n, MI_SAMPLE)) {
+        const long long tb = s_tb[warp];
+        const int lc = s_len[warp];
         for (int i = lane; i < lc; i += 32) {
             const int t = __ldg(doc_tok_ids + tb + i);
-            atomicOr(&bits[t >> 5], 1u << (t & 31));
+            const uint32_t bit = 1u << (t & 31);
+            if (atomicOr(&seen1[t >> 5], bit) & bit) atomicOr(&heavy[t >> 5], bit);
         }
     }
     __syncthreads();
-    // compact id of the first token of every bitmap word = exclusive prefix of the words' popcounts
-    int n_distinct = 0;
-    {
+    {   // heavy rank of a token = prefix popcount of the heavy bitmap; only the first MI_H stay heavy (the bits of the others
+        // are cleared, so "heavy" is a single bit test from here on)
         const int per = (vocab_words + MI_THREADS - 1) / MI_THREADS;
         const int w0 = tid * per, w1 = min(vocab_words, w0 + per);
         int sum = 0;
-        for (int w = w0; w < w1; ++w) sum += __popc(bits[w]);
-        int run = mi_block_scan(sum, s_wsum, &n_distinct);
-        if (n_distinct <= MI_MAX_D) {
-            for (int w = w0; w < w1; ++w) { wpre[w] = (uint16_t)run; run += __popc(bits[w]); }
+        for (int w = w0; w < w1; ++w) sum += __popc(heavy[w]);
+        int n_heavy = 0;
+        int run = mi_block_scan(sum, s_wsum, &n_heavy);
+        for (int w = w0; w < w1; ++w) {
+            uint32_t hw = heavy[w];
+            const int keep = max(0, MI_H - run);
+            hpre[w] = (uint16_t)min(run, MI_H);
+            run += __popc(hw);
+            if (__popc(hw) > keep) {
+                while (__popc(hw) > keep) hw &= ~(0x80000000u >> __clz(hw));
+                heavy[w] = hw;
+            }
         }
     }
-    if (n_distinct > MI_MAX_D || total_tok + n_distinct > t_cap) {        // (every list may grow by one filler entry)
-        if (tid == 0) out_n[q] = -2;
-        return;
-    }
-    for (int i = tid; i <= n_distinct; i += MI_THREADS) start[i] = 0u;
+    __syncthreads();                                          // (seen1 is dead: hb takes its place)
+    for (int i = tid; i < MI_H_WORDS * MI_THREADS; i += MI_THREADS) hb[i] = 0u;
     __syncthreads();
-    // ---- build 2: compact forward lists + per-token counts (counts go to start[id + 1]: the scan below makes them list starts)
+    // ---- build 2: heavy sets + bucket counts of the light incidences (warp per candidate, MI_TOK_UNROLL loads in flight)
     for (int cc = warp; cc < n; cc += MI_WARPS) {
-        const long long tb = doc_tok_ptr[docs[cc]];
-        const int lc = (int)(doc_tok_ptr[docs[cc] + 1] - tb);
-        uint16_t* dst = fwd + cand_off[cc];
-        for (int i = lane; i < lc; i += 32) {
-            const int t = __ldg(doc_tok_ids + tb + i);
-            const uint32_t wbits = bits[t >> 5];
-            const int id = (int)wpre[t >> 5] + __popc(wbits & ((1u << (t & 31)) - 1u));
-            dst[i] = (uint16_t)id;
-            atomicAdd(&start[id + 1], 1u);
+        const long long tb = s_tb[cc];
+        const int lc = s_len[cc];
+        for (int i0 = 0; i0 < lc; i0 += 32 * MI_TOK_UNROLL) {
+            int t[MI_TOK_UNROLL];
+#pragma unroll
+            for (int u = 0; u < MI_TOK_UNROLL; ++u) {
+                const int i = i0 + u * 32 + lane;
+                t[u] = i < lc ? __ldg(doc_tok_ids + tb + i) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < MI_TOK_UNROLL; ++u) {
+                if (t[u] < 0) continue;
+                const uint32_t hw = heavy[t[u] >> 5], bit = 1u << (t[u] & 31);
+                if (hw & bit) {
+                    const int r = (int)hpre[t[u] >> 5] + __popc(hw & (bit - 1u));
+                    atomicOr(&hb[cc * MI_H_WORDS + (r >> 5)], 1u << (r & 31));
+                } else {
+                    atomicAdd(&bstart[mi_bucket(t[u])], 1u);
+                }
+            }
         }
     }
     __syncthreads();
-    // ---- build 3: exclusive scan of the counts in place.  start[id] = first slot of id's list; the scatter then advances
-    //      start[id] to the END of the list, so afterwards list(id) = [id ? start[id - 1] : 0, start[id])
-    {
-        const int per = (n_distinct + MI_THREADS) / MI_THREADS;            // covers indices 1 .. n_distinct
-        const int i0 = 1 + tid * per, i1 = min(n_distinct + 1, i0 + per);
-        // lists are padded to an even length so that every list starts on a 4-byte boundary of inv (cp.async granularity)
+    {   // counts -> exclusive starts
+        constexpr int per = MI_NB / MI_THREADS;
+        uint32_t cnt[per];
         int sum = 0;
-        for (int i = i0; i < i1; ++i) sum += ((int)start[i] + 1) & ~1;
+#pragma unroll
+        for (int j = 0; j < per; ++j) { cnt[j] = bstart[tid * per + j]; sum += (int)cnt[j]; }
         int tot = 0;
         int run = mi_block_scan(sum, s_wsum, &tot);
-        // start[i] (i >= 1) holds count(i - 1); the exclusive prefix over those slots leaves begin(id) in start[id + 1]
-        for (int i = i0; i < i1; ++i) {
-            const int cnt = (int)start[i];
-            start[i] = (uint32_t)run;
-            if (cnt & 1) inv[run + cnt] = (uint16_t)MI_PAD;            // filler behind a list of odd length
-            run += (cnt + 1) & ~1;
-        }
+#pragma unroll
+        for (int j = 0; j < per; ++j) { bstart[tid * per + j] = (uint32_t)run; run += (int)cnt[j]; }
     }
     __syncthreads();
-    // the scatter takes its slot from start[id + 1] and advances it, so afterwards start[id + 1] = end(id) (before the filler):
-    // list(id) occupies [even(start[id]), start[id + 1]) plus the filler; start[0] = 0 is never touched
+    // ---- build 3: scatter the light incidences; a bucket's start advances to its END, so afterwards
+    //      bucket(b) = [b ? bstart[b - 1] : 0, bstart[b])
     for (int cc = warp; cc < n; cc += MI_WARPS) {
-        const int lc = (int)(doc_tok_ptr[docs[cc] + 1] - doc_tok_ptr[docs[cc]]);
-        const uint16_t* src = fwd + cand_off[cc];
-        for (int i = lane; i < lc; i += 32) {
-            const int id = src[i];
-            const uint32_t pos = atomicAdd(&start[id + 1], 1u);
-            inv[pos] = (uint16_t)cc;
+        const long long tb = s_tb[cc];
+        const int lc = s_len[cc];
+        for (int i0 = 0; i0 < lc; i0 += 32 * MI_TOK_UNROLL) {
+            int t[MI_TOK_UNROLL];
+#pragma unroll
+            for (int u = 0; u < MI_TOK_UNROLL; ++u) {
+                const int i = i0 + u * 32 + lane;
+                t[u] = i < lc ? __ldg(doc_tok_ids + tb + i) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < MI_TOK_UNROLL; ++u) {
+                if (t[u] < 0) continue;
+                if (!((heavy[t[u] >> 5] >> (t[u] & 31)) & 1u)) {
+                    const uint32_t pos = atomicAdd(&bstart[mi_bucket(t[u])], 1u);
+                    ent[pos] = ((uint32_t)t[u] << MI_CAND_BITS) | (uint32_t)cc;
+                }
+            }
         }
     }
     __syncthreads();
@@ -201,82 +226,89 @@ mmr_select_inv_kernel(const int32_t* __restrict__ cand_doc, const double* __rest
     int max_num = 0, max_den = 1;                              // running max Jaccard of this candidate as a fraction
     double max_sim = 0.0;
     for (int step = 0; step < k; ++step) {
-        // 1. argmax with "earliest wins"
-        double best = -1e9;
-        int best_i = 0x7fffffff;
+        // 1. argmax with "earliest wins".  The fp64 score becomes an order-preserving 64-bit key (-0.0 is folded into +0.0 first,
+        //    as the comparison treats them equal), reduced with three redux.sync per level: max of the high words, max of the
+        //    low words among the lanes that hold it, min index among the lanes that hold both.  Key 0 = not a contender (dead,
+        //    or a score that does not beat the reference's -1e9 start value).  Every warp repeats the second level on the 32
+        //    warp results, so one barrier publishes the pick to the whole CTA.
+        unsigned long long key = 0ull;
         if (alive) {
             const double sc = step == 0 ? rel : __dsub_rn(__dmul_rn(lam, rel), __dmul_rn(one_minus, max_sim));
-            if (sc > best) { best = sc; best_i = c; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(MI_FULL, best, o);
-            const int oi = __shfl_xor_sync(MI_FULL, best_i, o);
-            if (mi_better(ob, oi, best, best_i)) { best = ob; best_i = oi; }
-        }
-        if (lane == 0) { s_best[warp] = best; s_best_idx[warp] = best_i; }
-        __syncthreads();
-        if (warp == 0) {
-            double b = s_best[lane];
-            int bi = s_best_idx[lane];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ob = __shfl_xor_sync(MI_FULL, b, o);
-                const int oi = __shfl_xor_sync(MI_FULL, bi, o);
-                if (mi_better(ob, oi, b, bi)) { b = ob; bi = oi; }
+            if (sc > -1e9) {
+                const long long b = __double_as_longlong(__dadd_rn(sc, 0.0));
+                key = (unsigned long long)b ^ (b < 0 ? 0xffffffffffffffffull : 0x8000000000000000ull);
             }
-            if (lane == 0) {
-                s_pick = bi;
-                if (bi != 0x7fffffff) {
-                    out_pick[(size_t)q * k_max + step] = bi;
-                    s_done = step + 1;
+        }
+        {
+            const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+            const unsigned m_hi = __reduce_max_sync(MI_FULL, hi);
+            const unsigned m_lo = __reduce_max_sync(MI_FULL, hi == m_hi ? lo : 0u);
+            const unsigned m_i = __reduce_min_sync(MI_FULL, (hi == m_hi && lo == m_lo) ? (unsigned)c : 0x7fffffffu);
+            if (lane == 0) { s_key[warp] = ((unsigned long long)m_hi << 32) | m_lo; s_best_idx[warp] = (int)m_i; }
+        }
+        __syncthreads();
+        int pick;
+        {
+            const unsigned long long wk = s_key[lane];
+            const unsigned hi = (unsigned)(wk >> 32), lo = (unsigned)wk;
+            const unsigned m_hi = __reduce_max_sync(MI_FULL, hi);
+            const unsigned m_lo = __reduce_max_sync(MI_FULL, hi == m_hi ? lo : 0u);
+            const unsigned m_i = __reduce_min_sync(MI_FULL, (hi == m_hi && lo == m_lo) ? (unsigned)s_best_idx[lane] : 0x7fffffffu);
+            pick = (m_hi | m_lo) ? (int)m_i : 0x7fffffff;
+        }
+        if (pick == 0x7fffffff) break;                        // nothing beat -1e9 (the reference would fail here too)
+        if (tid == 0) {
+            out_pick[(size_t)q * k_max + step] = pick;
+            s_done = step + 1;
+        }
+        if (step + 1 == k) break;
+        if (c == pick) alive = false;
+        // 2. light part: a warp per light token of the picked document reads that token's bucket
+        const long long tb_p = s_tb[pick];
+        const int len_p = s_len[pick];
+        for (int j0 = 0; j0 < len_p; j0 += MI_WARPS * MI_TOK_UNROLL) {
+            int t[MI_TOK_UNROLL];
+            uint32_t e0[MI_TOK_UNROLL], e1[MI_TOK_UNROLL], v[MI_TOK_UNROLL];
+#pragma unroll
+            for (int u = 0; u < MI_TOK_UNROLL; ++u) {
+                const int j = j0 + u * MI_WARPS + warp;
+                t[u] = j < len_p ? __ldg(doc_tok_ids + tb_p + j) : -1;          // (one address per warp: a broadcast load)
+            }
+#pragma unroll
+            for (int u = 0; u < MI_TOK_UNROLL; ++u) {
+                e0[u] = e1[u] = 0u;
+                if (t[u] >= 0 && !((heavy[t[u] >> 5] >> (t[u] & 31)) & 1u)) {
+                    const uint32_t b = mi_bucket(t[u]);
+                    e0[u] = b ? bstart[b - 1] : 0u;
+                    e1[u] = bstart[b];
+                }
+                // (ld.cg: the entries were written by this CTA a moment ago; read them where they were written, in L2)
+                v[u] = e0[u] + lane < e1[u] ? __ldcg(ent + e0[u] + lane) : 0xffffffffu;
+            }
+#pragma unroll
+            for (int u = 0; u < MI_TOK_UNROLL; ++u) {
+                if (v[u] != 0xffffffffu && (int)(v[u] >> MI_CAND_BITS) == t[u]) atomicAdd(&inter[v[u] & (MI_THREADS - 1)], 1u);
+                for (uint32_t e = e0[u] + 32 + lane; e < e1[u]; e += 32) {       // (buckets longer than a warp: rare)
+                    const uint32_t x = __ldcg(ent + e);
+                    if ((int)(x >> MI_CAND_BITS) == t[u]) atomicAdd(&inter[x & (MI_THREADS - 1)], 1u);
                 }
             }
         }
-        __syncthreads();
-        const int pick = s_pick;
-        if (pick == 0x7fffffff) break;                        // nothing beat -1e9 (the reference would fail here too)
-        if (step + 1 == k) break;
-        if (c == pick) alive = false;
-        // 2. the picked document's inverted lists: thread t < len_p owns token t of the pick
-        const int len_p = (int)(doc_tok_ptr[docs[pick] + 1] - doc_tok_ptr[docs[pick]]);
-        uint32_t lb = 0, ll = 0;
-        if (tid < len_p) {
-            // (ld.cg: the scatter advanced these slots with L2 atomics after this SM had read them -- its L1 may be stale)
-            const int id = __ldcg(fwd + cand_off[pick] + tid);
-            lb = (__ldcg(start + id) + 1u) & ~1u;             // begin(id): end(id - 1) rounded up over its filler; start[0] = 0
-            ll = ((__ldcg(start + id + 1) - lb) + 1u) & ~1u;  // padded length (the filler counts into a sink slot)
-        }
-        int total = 0;
-        const int pre = mi_block_scan((int)ll, s_wsum, &total);
-        s_b[tid] = lb;
-        s_pre[tid] = (uint32_t)pre;
-        __syncthreads();
-        // 3. the lists are copied into shared memory back to back -- aligned 4-byte cp.async copies, a warp per list, nothing
-        //    waits on a load until all of them are in flight -- and then counted as one flat array: which token an entry
-        //    belongs to no longer matters
-        for (int r0 = 0; r0 < total; r0 += MI_STAGE) {        // (one round unless the pick shares > 32768 incidences)
-            for (int t = warp; t < len_p; t += MI_WARPS) {
-                const int p0 = (int)s_pre[t], p1 = t + 1 < len_p ? (int)s_pre[t + 1] : total;
-                const int a0 = max(p0, r0), a1 = min(p1, r0 + MI_STAGE);          // this round's part of list t (even bounds)
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(inv + s_b[t] + (uint32_t)(a0 - p0));
-                uint32_t* dst = reinterpret_cast<uint32_t*>(stage + (a0 - r0));
-                for (int j = lane; j < (a1 - a0) / 2; j += 32)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + j)), "l"(src + j) : "memory");
+        // 3. heavy part: twelve AND + POPC against the pick's heavy set (a broadcast read per word)
+        int in_heavy = 0;
+        {
+            const uint4* mine = reinterpret_cast<const uint4*>(hb + c * MI_H_WORDS);
+            const uint4* theirs = reinterpret_cast<const uint4*>(hb + pick * MI_H_WORDS);
+#pragma unroll
+            for (int w = 0; w < MI_H_WORDS / 4; ++w) {         // (48-byte rows: 128-bit loads of 8 consecutive rows hit 32 distinct banks)
+                const uint4 a = mine[w], b = theirs[w];
+                in_heavy += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();
-            const int n_here = min(MI_STAGE, total - r0);
-            for (int w = tid; w < n_here; w += MI_THREADS) {
-                const uint32_t cc = stage[w];
-                atomicAdd(&inter[cc < MI_THREADS ? cc : MI_THREADS], 1u);        // (filler -> sink slot)
-            }
-            __syncthreads();
         }
+        __syncthreads();
         // 4. every candidate folds its intersection into its running maximum (integer fractions; divide only on change)
         {
-            const int in = (int)inter[tid];
+            const int in = in_heavy + (int)inter[tid];
             inter[tid] = 0u;
             if (alive && in > 0) {
                 const int uni = len + len_p - in;             // > 0 because in > 0
@@ -296,27 +328,23 @@ mmr_select_inv_kernel(const int32_t* __restrict__ cand_doc, const double* __rest
 }
 
 size_t mmr_inv_smem_bytes(int vocab_words) {
-    return (size_t)vocab_words * 4 + (size_t)(vocab_words + (vocab_words & 1)) * 2 + (size_t)(4 * MI_THREADS + 32) * 4 +
-           (size_t)MI_STAGE * 2 + 64;
+    return (size_t)MI_THREADS * (8 + 4 + 4) + (size_t)MI_NB * 4 + (size_t)MI_H_WORDS * MI_THREADS * 4 + (size_t)vocab_words * 4 +
+           (size_t)(vocab_words + (vocab_words & 1)) * 2 + 64;
 }
 
-// Per query: forward + inverted lists (u16 each, t_cap entries) and the list starts (u32, 65536 + 1 entries).
-size_t mmr_inv_workspace_bytes(int n_queries, int t_cap) {
-    return align_up((size_t)n_queries * t_cap * 2, 256) * 2 + align_up((size_t)n_queries * (MI_MAX_D + 1) * 4, 256) + 256;
-}
+// the sample's first bitmap aliases the heavy sets, and token ids must fit the entries' 22 bits
+bool mmr_inv_vocab_ok(int vocab_words) { return vocab_words <= MI_H_WORDS * MI_THREADS && vocab_words <= (1 << (32 - MI_CAND_BITS - 5)); }
+
+// Per query: the light (token, candidate) incidences, one u32 each, t_cap of them.
+size_t mmr_inv_workspace_bytes(int n_queries, int t_cap) { return align_up((size_t)n_queries * t_cap * 4, 256) + 256; }
 
 int launch_mmr_inv(const int32_t* cand_doc, const double* cand_rel, const int32_t* cand_n, int n_queries, int n_max,
                    const int64_t* doc_tok_ptr, const int32_t* doc_tok_ids, int vocab_words, const double* lambda, const int32_t* k_sel,
                    int k_max, int32_t* out_pick, int32_t* out_n, void* workspace, int t_cap, cudaStream_t st) {
-    char* ws = static_cast<char*>(workspace);
-    const size_t lists = align_up((size_t)n_queries * t_cap * 2, 256);
-    uint16_t* fwd = reinterpret_cast<uint16_t*>(ws);
-    uint16_t* inv = reinterpret_cast<uint16_t*>(ws + lists);
-    uint32_t* start = reinterpret_cast<uint32_t*>(ws + 2 * lists);
     const size_t smem = mmr_inv_smem_bytes(vocab_words);
     B200_CUDA_CHECK(cudaFuncSetAttribute(mmr_select_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mmr_select_inv_kernel<<<n_queries, MI_THREADS, smem, st>>>(cand_doc, cand_rel, cand_n, n_max, doc_tok_ptr, doc_tok_ids, vocab_words,
-                                                                 lambda, k_sel, k_max, out_pick, out_n, fwd, inv, start, t_cap);
+                                                                 lambda, k_sel, k_max, out_pick, out_n, static_cast<uint32_t*>(workspace), t_cap);
     count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;

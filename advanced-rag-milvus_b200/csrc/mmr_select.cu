@@ -25,6 +25,7 @@ namespace b200rag {
 
 // mmr_inv.cu: the inverted-list kernel (third generation), the product path for n_max <= 1024 and vocabularies up to ~1M tokens
 size_t mmr_inv_smem_bytes(int vocab_words);
+bool mmr_inv_vocab_ok(int vocab_words);
 size_t mmr_inv_workspace_bytes(int n_queries, int t_cap);
 int launch_mmr_inv(const int32_t* cand_doc, const double* cand_rel, const int32_t* cand_n, int n_queries, int n_max,
                    const int64_t* doc_tok_ptr, const int32_t* doc_tok_ids, int vocab_words, const double* lambda, const int32_t* k_sel,
@@ -514,7 +515,8 @@ static bool mmr_bits_in_smem(int n_max, int vocab_words) {
 // Incidences (candidate, token) the inverted-list kernel has room for per query: 256 tokens per candidate on average.
 static int mmr_inv_t_cap(int n_max) { return n_max * 256; }
 static bool mmr_inv_usable(int n_max, int vocab_words) {
-    return n_max <= 1024 && mmr_inv_smem_bytes(vocab_words) <= 200 * 1024 && option(OPT_MMR_PATH, 0) == 0;
+    const int path = option(OPT_MMR_PATH, 0);             // 0 auto, 1 general bitset kernel, 2 bitset kernels, 3 inverted lists ONLY
+    return n_max <= 1024 && mmr_inv_vocab_ok(vocab_words) && mmr_inv_smem_bytes(vocab_words) <= 200 * 1024 && (path == 0 || path == 3);
 }
 
 size_t b200rag_mmr_select_workspace_bytes(int32_t n_queries, int32_t n_max, int32_t vocab_size) {
@@ -547,6 +549,7 @@ int b200rag_mmr_select(const int32_t* cand_doc, const double* cand_rel, const in
                                 k_max, out_pick, out_n, workspace, mmr_inv_t_cap(n_max), st);
         if (rc) return rc;
         only_marked = 1;
+        if (option(OPT_MMR_PATH, 0) == 3) return B200RAG_OK;      // (tests: queries the kernel could not hold keep out_n = -2)
     }
     if (n_max >= 32 && n_max <= MMT_THREADS && n_hi <= 2 && option(OPT_MMR_PATH, 0) != 1) {
         // fast path: one thread per candidate, transposed token cache (static shared memory of the kernel: ~7 KB)

@@ -390,11 +390,12 @@ def test_mmr_batch_matches_oracle_random(eng):
         assert picks[q, : int(n[q])].cpu().tolist() == ref, q
 
 
-@pytest.mark.parametrize("mmr_path", [-1, 2, 1])
+@pytest.mark.parametrize("mmr_path", [-1, 3, 2, 1])
 def test_mmr_config4_scale_matches_oracle(eng, mmr_path):
     """BASELINE config-4 shape for the diversification: ~1000 candidates with ~90 unique tokens each out of a 100K-term
     Zipf vocabulary (token ids beyond 65535 exercise the 16-bit token cache), lambda 0.7, k = 100.  All three MMR kernels
-    (-1: inverted candidate lists, the product path; 2: thread-per-candidate bitset probes; 1: warp-per-candidate general path)
+    (-1: the product dispatch; 3: inverted candidate lists ONLY -- a query it could not hold would come back with n = -2;
+    2: thread-per-candidate bitset probes; 1: warp-per-candidate general path)
     against the oracle restatement of the reference."""
     from b200rag import synth
     from b200rag import _lib
@@ -418,6 +419,39 @@ def test_mmr_config4_scale_matches_oracle(eng, mmr_path):
         sets = [frozenset(ti[dp[d]: dp[d + 1]].tolist()) for d in cand[q, : n[q]]]
         ref = fusion.mmr_select(list(rel[q, : n[q]]), sets, [k, k, 37][q], [0.7, 0.5, 0.8][q])
         assert picks[q, : int(pn[q])].cpu().tolist() == ref, q
+
+
+def test_mmr_heavy_cap_and_long_documents(eng):
+    """The heavy/light MMR kernel outside its comfort zone: a 3000-token vocabulary where the sample calls far more than 384
+    tokens heavy (the cap moves the rest to the light lists), documents of up to 1500 tokens (several rounds of the per-pick
+    walk, buckets longer than a warp), duplicates of one document (similarity 1.0, exact score ties) and empty documents."""
+    from b200rag import _lib
+    from oracle import fusion
+    rng = np.random.default_rng(23)
+    vocab, n_docs, b, n_max, k = 3000, 400, 4, 300, 40
+    docs = [np.sort(rng.choice(vocab, size=int(rng.integers(100, 1500)), replace=False)) for _ in range(n_docs)]
+    docs[7] = docs[3].copy()
+    docs[11] = docs[3].copy()
+    docs[5] = np.zeros(0, np.int64)
+    dp = np.zeros(n_docs + 1, np.int64)
+    dp[1:] = np.cumsum([len(d) for d in docs])
+    ti = np.concatenate(docs).astype(np.int32)
+    cand = np.stack([rng.choice(n_docs, size=n_max, replace=False) for _ in range(b)]).astype(np.int32)
+    cand[0, :4] = [3, 7, 11, 5]
+    n = np.asarray([n_max, 299, 17, 1], np.int32)
+    rel = np.sort(rng.random((b, n_max)) * 0.016, axis=1)[:, ::-1].copy()
+    rel[0, 1] = rel[0, 2]
+    lam, ks = [0.7, 0.0, 0.5, 0.9], [k, k, 17, 5]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    _lib.set_option("mmr_path", 3)
+    try:
+        picks, pn = eng.mmr_select(t(cand), t(rel), t(n), t(dp), t(ti), vocab, t(np.asarray(lam)), t(np.asarray(ks, np.int32)), k)
+    finally:
+        _lib.set_option("mmr_path", -1)
+    for q in range(b):
+        sets = [frozenset(docs[d].tolist()) for d in cand[q, : n[q]]]
+        ref = fusion.mmr_select(list(rel[q, : n[q]]), sets, ks[q], lam[q])
+        assert int(pn[q]) == len(ref) and picks[q, : int(pn[q])].cpu().tolist() == ref, q
 
 
 def test_sparse_filtered_matches_oracle(eng, oracle_lib):
