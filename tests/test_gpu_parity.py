@@ -423,13 +423,14 @@ def test_mmr_config4_scale_matches_oracle(eng, mmr_path):
 
 def test_mmr_heavy_cap_and_long_documents(eng):
     """The heavy/light MMR kernel outside its comfort zone: a 3000-token vocabulary where the sample calls far more than 384
-    tokens heavy (the cap moves the rest to the light lists), documents of up to 1500 tokens (several rounds of the per-pick
-    walk, buckets longer than a warp), duplicates of one document (similarity 1.0, exact score ties) and empty documents."""
+    tokens heavy (the cap moves the rest to the light lists), two documents of 1500 and 1100 tokens (several rounds of the per-pick
+    walk, buckets longer than a warp; the average stays under the workspace's 256 tokens per candidate), duplicates of one document (similarity 1.0, exact score ties) and empty documents."""
     from b200rag import _lib
     from oracle import fusion
     rng = np.random.default_rng(23)
     vocab, n_docs, b, n_max, k = 3000, 400, 4, 300, 40
-    docs = [np.sort(rng.choice(vocab, size=int(rng.integers(100, 1500)), replace=False)) for _ in range(n_docs)]
+    docs = [np.sort(rng.choice(vocab, size=int(rng.integers(60, 300)), replace=False)) for _ in range(n_docs)]
+    docs[20], docs[21] = (np.sort(rng.choice(vocab, size=m, replace=False)) for m in (1500, 1100))
     docs[7] = docs[3].copy()
     docs[11] = docs[3].copy()
     docs[5] = np.zeros(0, np.int64)
@@ -437,7 +438,7 @@ def test_mmr_heavy_cap_and_long_documents(eng):
     dp[1:] = np.cumsum([len(d) for d in docs])
     ti = np.concatenate(docs).astype(np.int32)
     cand = np.stack([rng.choice(n_docs, size=n_max, replace=False) for _ in range(b)]).astype(np.int32)
-    cand[0, :4] = [3, 7, 11, 5]
+    cand[0, :6] = [3, 7, 11, 5, 20, 21]
     n = np.asarray([n_max, 299, 17, 1], np.int32)
     rel = np.sort(rng.random((b, n_max)) * 0.016, axis=1)[:, ::-1].copy()
     rel[0, 1] = rel[0, 2]
@@ -451,7 +452,7 @@ def test_mmr_heavy_cap_and_long_documents(eng):
     for q in range(b):
         sets = [frozenset(docs[d].tolist()) for d in cand[q, : n[q]]]
         ref = fusion.mmr_select(list(rel[q, : n[q]]), sets, ks[q], lam[q])
-        assert int(pn[q]) == len(ref) and picks[q, : int(pn[q])].cpu().tolist() == ref, q
+        assert int(pn[q]) == len(ref) and picks[q, : int(pn[q])].cpu().tolist() == ref, (q, int(pn[q]))     # (-2 = not served here)
 
 
 def test_sparse_filtered_matches_oracle(eng, oracle_lib):
