@@ -21,6 +21,7 @@
 //     if the exact k-th score exceeds m + eps the exact top-k is inside the candidate set.  Otherwise the query is
 //     flagged and (AUTO mode) re-run on the exact CUDA-core path.  eps = 2 * dim * 2^-23 * |q| * row_norm_bound bounds
 //     the fp32 accumulation error of the tensor-core path (checked empirically in tests/test_gpu_dense_tc.py).
+#include <cmath>
 #include "tc_common.cuh"
 #include "select.cuh"
 #include "finish.cuh"
@@ -558,14 +559,31 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     // stride * Gamma(r): with r = 16 and r * stride = 8 k' the chance that fewer than k' rows survive (the query is then
     // flagged and re-run on the slow exact path) is P(Gamma(16) < 2) ~ 5e-10 per query; at r = 8, 6 k' it was 6e-5 and
     // showed up as a handful of fallbacks per thousand batches.  12 k' (1e-12) cost 5 % of the scan at 1.25M-row shards:
-    // every survivor is appended by the epilogue and gathered again by the finish kernel.  Small corpora cap the stride
-    // (>= 4 sampled tiles); below r * stride = 6 k' (2e-8) the pass is skipped.
+    // every survivor is appended by the epilogue and gathered again by the finish kernel.
     pl.s_rank = TC_SAMPLE_R;
     pl.s_stride = option(OPT_SAMPLE_MULT, 8) * pl.kprime / TC_SAMPLE_R;       // (A/B knob: rows above the threshold, in k')
-    if (pl.s_stride > pl.n_tiles / 4) pl.s_stride = pl.n_tiles / 4;
     if (pl.s_stride < 1) pl.s_stride = 1;
-    pl.s_tiles = pl.n_tiles / pl.s_stride;
-    pl.sample = pl.s_tiles >= 4 && pl.s_rank * pl.s_stride >= 6 * pl.kprime && option(OPT_NO_SAMPLE, 0) == 0;
+    {
+        // Small shards searched deeply (125K rows, k = 500: 8 k' would be a single sampled tile).  The sample ranks 32-row GROUP
+        // maxima: with G sampled groups the r-th best of them sits where a group's maximum exceeds it with probability
+        // r / (G + 1), i.e. a row does with probability -ln(1 - r / (G + 1)) / 32  (= r / (32 G), the r * stride rule, while
+        // G >> r; more rows than that rule says when G is a few r, down to ~9 % of the corpus at G = r).  Sampled tiles are
+        // given up one at a time, never below r groups, until the estimate reaches 6 k'; the pass runs if it reaches 5 k'
+        // (chance of fewer than k' survivors, which costs the flagged re-scan: < 1e-6 per query) and is skipped otherwise.
+        const int groups_per_tile = pl.tile_rows / 32;
+        const int s_min_tiles = (TC_SAMPLE_R + groups_per_tile - 1) / groups_per_tile;
+        auto rows_above = [&](int tiles) {
+            const double frac = (double)pl.s_rank / ((double)tiles * groups_per_tile + 1.0);
+            return frac < 1.0 ? (double)n_rows * -log1p(-frac) / 32.0 : 0.0;
+        };
+        int tiles = pl.n_tiles / pl.s_stride;
+        if (tiles < 4 * s_min_tiles) tiles = 4 * s_min_tiles < pl.n_tiles ? 4 * s_min_tiles : pl.n_tiles;
+        while (tiles > s_min_tiles && rows_above(tiles) < 6.0 * pl.kprime) --tiles;
+        pl.s_stride = tiles > 0 ? pl.n_tiles / tiles : 1;
+        if (pl.s_stride < 1) pl.s_stride = 1;
+        pl.s_tiles = pl.n_tiles / pl.s_stride;
+        pl.sample = pl.s_tiles >= s_min_tiles && rows_above(pl.s_tiles) >= 5.0 * pl.kprime && option(OPT_NO_SAMPLE, 0) == 0;
+    }
     pl.s_chunks = want < pl.s_tiles ? want : (pl.s_tiles > 0 ? pl.s_tiles : 1);
     pl.s_items = qgroups * pl.s_chunks;
     pl.s_kprime = TC_SAMPLE_R;
