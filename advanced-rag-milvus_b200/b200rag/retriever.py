@@ -361,6 +361,29 @@ class B200HybridRetriever:
         orig = lsc.permute(1, 0, 2).reshape(b, -1).gather(1, first)
         return BatchResult(rows, scores, mask, n_out, torch.div(first, kmax, rounding_mode="floor").to(torch.int32), orig)
 
+    def rerank_batch(self, res: "BatchResult", top_k: Optional[int] = None,
+                     recency: Optional[torch.Tensor] = None) -> "BatchResult":
+        """`rerank` (reference retrieval.py:518-563) with the LearnedRanker for a whole device-resident batch: one launch of
+        b200rag_rerank_learned scores  base_weight*score + method_bonus*|retrieval_methods| + recency_weight*recency  in the
+        reference's fp64 operation order and stable-sorts every list; the columns of `res` are re-ordered on the device.
+        recency: f64 [B,T] (1 / (1 + age in days), retrieval.py:473-483) or None.  `original_score` keeps what the reference
+        calls original_retrieval_score (the fused score before the re-rank)."""
+        if not self.config.enable_reranking:
+            return res
+        if not (self.learned_ranker and self.config.enable_learned_ranker):
+            raise ValueError("rerank_batch runs the LearnedRanker; cross-encoder re-ranking goes through rerank()")
+        k_out = int(top_k or self.config.rerank_top_k)
+        c = self.learned_ranker.config
+        pos, new_scores, cnt = engine.rerank_learned(res.scores.contiguous(), res.mask.contiguous(), res.n.contiguous(), k_out,
+                                                     c.base_weight, c.method_bonus, c.recency_weight, recency)
+        take = pos.to(torch.int64).clamp(min=0)
+        valid = pos >= 0
+        rows = torch.where(valid, res.rows.gather(1, take), torch.full_like(take, -1))
+        mask = torch.where(valid, res.mask.gather(1, take), torch.zeros_like(pos))
+        first = torch.where(valid, res.first_method.gather(1, take), torch.zeros_like(pos))
+        orig = torch.where(valid, res.scores.gather(1, take), torch.full_like(new_scores, float("-inf")))
+        return BatchResult(rows, new_scores, mask, cnt, first, orig)
+
     def retrieve_batch_embedded(self, semantic: Any, sparse: Sequence[Any], configs: Sequence[RetrievalConfig],
                                 domain: Any = None, filter_expr: Optional[str] = None) -> "BatchResult":
         """The hot path for pre-embedded queries: dense top-2k + sparse top-2k (+ domain top-k) -> RRF -> MMR.
