@@ -192,34 +192,79 @@ def make_sharded_manager_class():
                 self.payload.set_virtual(self.n_total)
                 self._live.extend(np.ones(self.n_total, dtype=np.bool_))
 
-        def _search_masked(self, queries: Any, collection_name: str, k: int, m: int, words: Optional[torch.Tensor]):
-            if words is not None:                              # the replicated global mask: this rank's words
+        def _local_words(self, m: int, words: Optional[torch.Tensor]):
+            """This rank's slice of the replicated global row mask and the number of rows it allows here."""
+            if words is not None:
                 words = words[self.start // 32: (self.end + 31) // 32].contiguous()
-                m_local = _popcount_words(words) if m else 0
+                return (_popcount_words(words) if m else 0), words
+            return self._sem.n, None                           # no filter, nothing deleted: every local row
+
+        def _local_dense(self, q: torch.Tensor, collection_name: str, k: int, m_local: int, words: Optional[torch.Tensor]):
+            """Exact local top-k of this rank's row range, written by the finish kernel straight into the [2, B, k] message."""
+            idx = self._dense_of(collection_name)
+            msg, ps, pi = self._send.planes(q.shape[0], k)
+            if idx.n == 0 or m_local == 0:
+                ps.fill_(float("-inf"))
+                pi.fill_(-1)
             else:
-                m_local = self._sem.n                          # no filter, nothing deleted: every local row
+                idx.search(q, k, row_mask=words, out=(ps, pi))
+            return msg, ps, pi
+
+        def _search_masked(self, queries: Any, collection_name: str, k: int, m: int, words: Optional[torch.Tensor]):
+            m_local, words = self._local_words(m, words)
             if self.world == 1:
                 return super()._search_masked(queries, collection_name, k, m_local, words)
-            dense = collection_name != "sparse_index"
-            if dense:
-                idx = self._dense_of(collection_name)
+            if collection_name != "sparse_index":
                 q = queries if torch.is_tensor(queries) else torch.as_tensor(np.asarray(queries, dtype=np.float32))
                 q = q[None, :] if q.dim() == 1 else q
-                b = q.shape[0]
-                msg, ps, pi = self._send.planes(b, k)
-                if idx.n == 0 or m_local == 0:
-                    ps.fill_(float("-inf"))
-                    pi.fill_(-1)
-                else:
-                    idx.search(q, k, row_mask=words, out=(ps, pi))       # straight into the send buffer
+                msg, ps, pi = self._local_dense(q, collection_name, k, m_local, words)
             else:
                 s, i, _ = super()._search_masked(queries, collection_name, k, m_local, words)
-                b = s.shape[0]
-                msg, ps, pi = self._send.planes(b, k)
+                msg, ps, pi = self._send.planes(s.shape[0], k)
                 ps.copy_(s)
                 pi.copy_(i)
             ms, mi = gather_and_merge(ps, pi, k, engine.merge_topk, self.group, engine.merge_gathered, message=msg)
             return ms, mi, (mi >= 0).sum(1).to(torch.int32)
+
+        def search_own_queries_arrays(self, queries_local: Any, collection_name: str, top_k: int = 20,
+                                      filters: Optional[str] = None):
+            """The SPMD front door of a row-sharded dense collection: EVERY rank calls it with ITS OWN queries (host or device
+            fp32 [per, dim], the same `per` on every rank -- each rank serves its own clients) and gets the global exact
+            top-k of those queries back as host arrays (SearchArrays, like search_batch_arrays).
+
+            The queries are all-gathered over NVLink (instead of every rank copying the whole batch from its host), every rank
+            searches its row range for the whole batch, and ONE all-to-all hands each rank the candidates of its own queries
+            from all row ranges, so a rank merges and copies back 1/world of the result."""
+            from .index_manager import SearchArrays
+            if collection_name not in self.collections:
+                raise ValueError(f"Collection {collection_name} not found")
+            if collection_name == "sparse_index":
+                raise ValueError("search_own_queries_arrays serves the dense collections")
+            k = int(top_k)
+            with self._lock:
+                q = queries_local if torch.is_tensor(queries_local) else torch.as_tensor(np.asarray(queries_local, dtype=np.float32))
+                q = q[None, :] if q.dim() == 1 else q
+                q = q.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+                per, world = q.shape[0], self.world
+                if world == 1:
+                    return self.search_batch_arrays(q, collection_name, k, filters)
+                q_all = torch.empty((world * per, q.shape[1]), dtype=torch.float32, device=self.device)
+                dist.all_gather_into_tensor(q_all, q, group=self.group)
+                m, words = self._filter_words(filters)
+                m_local, words = self._local_words(m, words)
+                msg, _, _ = self._local_dense(q_all, collection_name, k, m_local, words)
+                # [2, world * per, k] planes -> one [2, per, k] block per destination rank
+                send = msg.view(2, world, per, k).permute(1, 0, 2, 3).contiguous()
+                recv = torch.empty_like(send)
+                dist.all_to_all_single(recv, send, group=self.group)
+                ms, mi = engine.merge_gathered(recv, k)
+                cnt = (mi >= 0).sum(1).to(torch.int32)
+                hs, hi, hc = self._pinned_like("s", ms), self._pinned_like("i", mi), self._pinned_like("c", cnt)
+                hs.copy_(ms, non_blocking=True)
+                hi.copy_(mi, non_blocking=True)
+                hc.copy_(cnt, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                return SearchArrays(hi.numpy().copy(), hs.numpy().copy(), hc.numpy().copy(), self.payload)
 
         def compact(self) -> None:
             if self._n_dead:

@@ -311,24 +311,47 @@ def main():
     # Every step: pinned fp32 host queries -> manager.search_batch_arrays -> numpy rows / scores / counts on the host.  The
     # call is synchronous (the caller holds the step's results when it returns), so H2D, search and D2H of one step do not
     # overlap with the next; nothing is skipped or cached.
-    for it in range(max(args.warmup, 4)):          # (the third call of a shape captures its CUDA graph)
-        mgr.search_batch_arrays(q_host[it % POOL], COL, K)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    checksum = 0
-    t_wall0 = time.perf_counter()
-    e0.record()
-    for it in range(args.steps):
-        arr = mgr.search_batch_arrays(q_host[(args.warmup + it) % POOL], COL, K)
-        checksum += int(arr.rows[0, 0]) + int(arr.counts[-1])
-    e1.record()
-    barrier()
-    e2e_wall_ms = (time.perf_counter() - t_wall0) * 1e3
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
+    # At N > 1 the batch enters SPMD-style: rank r brings queries [r*B/N, (r+1)*B/N) from ITS host (every rank serves its own
+    # clients), the manager all-gathers them over NVLink, and each rank receives, merges and copies back the results of its own
+    # queries (ShardedIndexManager.search_own_queries_arrays).  Summed over ranks the step still moves the whole batch's
+    # queries H2D and the whole result D2H.  extras.e2e_replicated is the other calling convention (every rank passes the
+    # whole batch and gets the whole result).
+    own = world > 1 and B % world == 0
+    per = B // world if own else B
+
+    def e2e_call(j):
+        if own:
+            return mgr.search_own_queries_arrays(q_host[j % POOL][rank * per: (rank + 1) * per], COL, K)
+        return mgr.search_batch_arrays(q_host[j % POOL], COL, K)
+
+    def timed_e2e(call):
+        for it in range(max(args.warmup, 4)):          # (the third call of a shape captures its CUDA graph)
+            call(it)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        chk = 0
+        t_wall0 = time.perf_counter()
+        e0.record()
+        for it in range(args.steps):
+            arr = call(args.warmup + it)
+            chk += int(arr.rows[0, 0]) + int(arr.counts[-1])
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t_wall0) * 1e3
+        return max_over_ranks(max(e0.elapsed_time(e1), 0.0)), wall, chk
+
+    e2e_ms, e2e_wall_ms, checksum = timed_e2e(e2e_call)
     e2e_value = B * args.steps / (e2e_ms * 1e-3)
+    e2e_replicated = None
+    if own and not args.no_extras:
+        rep_ms, _, _ = timed_e2e(lambda j: mgr.search_batch_arrays(q_host[j % POOL], COL, K))
+        e2e_replicated = {"what": "every rank passes the whole batch from its host and receives the whole result",
+                          "qps": B * args.steps / (rep_ms * 1e-3), "ms_per_step": rep_ms / args.steps}
 
     # ---------------- extras ------------------------------------------------------------------
     extras = {}
+    if e2e_replicated is not None:
+        extras["e2e_replicated"] = e2e_replicated
     if not args.no_extras:
         lat = []
         q1 = [q_host[j % POOL][j: j + 1].clone().pin_memory() for j in range(60)]
@@ -454,7 +477,8 @@ def main():
             "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"{args.rows}x{D} fp16 exact cosine top-{K}, query batch {B}, row-sharded over {world} GPU(s)",
                        "api": "B200IndexManager.search_batch_ids (value) / .search_batch_arrays (e2e)" if world == 1 else
-                              "ShardedIndexManager.search_batch_ids (value) / .search_batch_arrays (e2e)",
+                              "ShardedIndexManager.search_batch_ids (value) / .search_own_queries_arrays (e2e: every rank brings "
+                              "B/N of the batch from its host and reads back those queries' results)",
                        "l2": f"inputs larger than L2 ({n_local * D * 2 / 1e9:.1f} GB per GPU streamed every step)",
                        "mode": "AUTO (tcgen05 scan + exact fp64 re-score, exact fallback for unproven queries)",
                        "flagged_queries_in_timed_region": int(flags_total.item())},

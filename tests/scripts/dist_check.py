@@ -76,6 +76,13 @@ rows = np.flatnonzero(keep)
 fa = mgr.search_batch_arrays(q, "semantic_index", 25, filters="entropy >= 0.5")
 rs, ri = oracle.dense_topk(xb[rows], qb, 25, oracle.F16)
 report("manager dense, filter + deleted rows", np.array_equal(fa.rows, rows[ri]) and np.array_equal(fa.scores, rs))
+# the SPMD front door: every rank brings ITS OWN queries (48 -> world slices of equal size, the rest padded with query 0)
+per = -(-48 // world)
+own = np.stack([q[j] if j < 48 else q[0] for j in range(rank * per, (rank + 1) * per)])
+oa = mgr.search_own_queries_arrays(own, "semantic_index", 25, filters="entropy >= 0.5")
+want = [j if j < 48 else 0 for j in range(rank * per, (rank + 1) * per)]
+report("manager dense, own queries (all-gather queries, all-to-all candidates)",
+       np.array_equal(oa.rows, rows[ri[want]]) and np.array_equal(oa.scores, rs[want]) and (oa.counts == 25).all())
 hits = mgr.search_batch(q[:2], "semantic_index", 3, filters="entropy >= 0.5")
 report("manager payload lookup", [h["id"] for h in hits[1]] == [ids[r] for r in rows[ri[1, :3]]] and
        hits[1][0]["metadata"]["entropy"] == meta[rows[ri[1, 0]]]["entropy"])

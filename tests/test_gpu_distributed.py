@@ -19,4 +19,4 @@ def test_two_rank_nccl_search_matches_the_oracle():
            "--master-port", "29531", os.path.join(root, "tests", "scripts", "dist_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("bit-exact vs oracle") == 14 and "MISMATCH" not in r.stdout          # 2 ranks x 7 checks
+    assert r.stdout.count("bit-exact vs oracle") == 16 and "MISMATCH" not in r.stdout          # 2 ranks x 8 checks
