@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--extras", default="c1,c2,c4,c5,dups", help="comma list of secondary configurations to run (N = 1)")
+    ap.add_argument("--extras", default="c1,c2,c4,c5,dups,ingest", help="comma list of secondary configurations to run (N = 1)")
     return ap.parse_args()
 
 
@@ -424,7 +424,8 @@ def main():
                               ("c2", "c2", lambda: bx.dense_config(device, 1_000_000, 768, 1024, 100, "IP")),
                               ("c4", "c4", lambda: bx.c4(device)),
                               ("c5", "c5_shard", lambda: bx.dense_config(device, 12_500_000, 384, 4096, 10, "COSINE", reps=5)),
-                              ("dups", "near_duplicates", lambda: bx.near_duplicates(device))):
+                              ("dups", "near_duplicates", lambda: bx.near_duplicates(device)),
+                              ("ingest", "filters_and_ingest", lambda: bx.filters_and_ingest(device))):
             if key not in want:
                 continue
             try:

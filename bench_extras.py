@@ -298,3 +298,43 @@ def c4_sharded(dev, world, reps=6, docs=1_000_000, vocab=100_000, dim=1024):
     del mgr
     torch.cuda.empty_cache()
     return out
+
+
+def filters_and_ingest(dev, rows=10_000_000, reps=10):
+    """SURVEY 8f-1 / 8f-2 at corpus scale.  (1) The predicate kernel over 10M rows: three ANDed terms over a float column, an
+    integer column and a dictionary-coded string column -> row bit mask (what a NEW filter expression costs before the masked
+    search runs; repeated expressions hit the manager's mask cache).  (2) Appending 100K documents to a 1M-document blocked
+    postings index: only the tail block is rebuilt."""
+    import ctypes
+    from b200rag import _lib, bm25, engine, synth
+    g = torch.Generator(device=dev).manual_seed(11)
+    ent = torch.rand(rows, generator=g, device=dev, dtype=torch.float64)
+    chunk = torch.randint(0, 16, (rows,), generator=g, device=dev, dtype=torch.int64)
+    code = torch.randint(0, 5000, (rows,), generator=g, device=dev, dtype=torch.int32)
+    terms = []
+    for col, kind, op, fv, iv in ((ent, _lib.COL_F64, _lib.OP_GE, 0.5, 0), (chunk, _lib.COL_I64, _lib.OP_LT, 0.0, 12),
+                                  (code, _lib.COL_CODE, _lib.OP_NE, 0.0, 7)):
+        t = _lib.FilterTerm()
+        t.column, t.lut, t.fvalue, t.ivalue, t.kind, t.op, t.lut_size = col.data_ptr(), None, fv, iv, kind, op, 0
+        terms.append(t)
+    ms, (words, count) = timed(lambda: engine.filter_mask(terms, rows, dev), reps)
+    want = int(((ent >= 0.5) & (chunk < 12) & (code != 7)).sum())
+    out = {"predicate": {"rows": rows, "terms": 3, "ms": ms, "allowed_rows": int(count.item()), "matches_torch": int(count.item()) == want,
+                         "bytes_read": rows * (8 + 8 + 4), "gbs": rows * 20 / (ms * 1e-3) / 1e9}}
+    del ent, chunk, code
+    docs, add, vocab = 1_000_000, 100_000, 100_000
+    dp, ti, tf = synth.zipf_corpus_device(docs + add, vocab, 21, dev)
+    w = bm25.bm25_weights_device(dp, ti, tf, vocab)
+    a1 = int(dp[docs])
+    t0 = time.perf_counter()
+    sidx = engine.SparseIndex(dp[: docs + 1].cpu(), ti[:a1], w[:a1], vocab, dev)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    b0 = sidx.blocks_built
+    t0 = time.perf_counter()
+    sidx.append((dp[docs:] - dp[docs]).cpu(), ti[a1:], w[a1:])
+    torch.cuda.synchronize()
+    t_app = time.perf_counter() - t0
+    out["sparse_append"] = {"docs": docs, "appended": add, "build_s": t_build, "append_s": t_app,
+                            "blocks_total": int(sidx._n_blocks), "blocks_rebuilt_by_append": int(sidx.blocks_built - b0)}
+    return out
