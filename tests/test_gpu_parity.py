@@ -421,6 +421,38 @@ def test_mmr_config4_scale_matches_oracle(eng, mmr_path):
         assert picks[q, : int(pn[q])].cpu().tolist() == ref, q
 
 
+@pytest.mark.parametrize("vocab", [700_000, 2_500_000])
+@pytest.mark.parametrize("mmr_path", [-1, 1])
+def test_mmr_large_vocabulary_matches_oracle(eng, vocab, mmr_path):
+    """Corpus-wide whitespace vocabularies of 1M+ chunk corpora: above 589 824 tokens the general kernel runs without its
+    16-bit token cache (round 1 wrote past its shared memory there), above ~1.8M the per-pick bitset moves to the
+    workspace in global memory.  The heavy/light kernel does not take vocabularies this large; the dispatch must fall through."""
+    from b200rag import _lib
+    from oracle import fusion
+    rng = np.random.default_rng(31)
+    n_docs, b, n_max, k = 500, 3, 200, 25
+    docs = [np.sort(rng.choice(vocab, size=int(rng.integers(5, 60)), replace=False)) for _ in range(n_docs)]
+    common = np.sort(rng.choice(vocab, size=30, replace=False))
+    docs = [np.union1d(d, common[rng.random(30) < 0.5]) for d in docs]        # shared tokens: non-trivial similarities
+    dp = np.zeros(n_docs + 1, np.int64)
+    dp[1:] = np.cumsum([len(d) for d in docs])
+    ti = np.concatenate(docs).astype(np.int32)
+    cand = np.stack([rng.choice(n_docs, size=n_max, replace=False) for _ in range(b)]).astype(np.int32)
+    n = np.asarray([n_max, 150, 33], np.int32)
+    rel = np.sort(rng.random((b, n_max)) * 0.016, axis=1)[:, ::-1].copy()
+    lam, ks = [0.7, 0.3, 0.5], [k, k, 10]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    _lib.set_option("mmr_path", mmr_path)
+    try:
+        picks, pn = eng.mmr_select(t(cand), t(rel), t(n), t(dp), t(ti), vocab, t(np.asarray(lam)), t(np.asarray(ks, np.int32)), k)
+    finally:
+        _lib.set_option("mmr_path", -1)
+    for q in range(b):
+        sets = [frozenset(docs[d].tolist()) for d in cand[q, : n[q]]]
+        ref = fusion.mmr_select(list(rel[q, : n[q]]), sets, ks[q], lam[q])
+        assert picks[q, : int(pn[q])].cpu().tolist() == ref, q
+
+
 def test_mmr_heavy_cap_and_long_documents(eng):
     """The heavy/light MMR kernel outside its comfort zone: a 3000-token vocabulary where the sample calls far more than 384
     tokens heavy (the cap moves the rest to the light lists), two documents of 1500 and 1100 tokens (several rounds of the per-pick
