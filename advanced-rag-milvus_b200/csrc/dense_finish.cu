@@ -24,11 +24,14 @@ constexpr int F2_ROWS = F2_THREADS / 8;     // candidate rows re-scored per batc
 constexpr int F2_GATHER = 1024;             // survivors gathered per round (8 KB, aliased with the row staging buffer)
 
 __host__ __device__ inline int finish2_sel_cap(int kprime) { return 2 * kprime <= 512 ? 512 : 2 * kprime; }
-__host__ __device__ inline int finish2_stage_rows(int dim) { return dim <= 2048 ? F2_ROWS : F2_ROWS / 2; }
+constexpr int F2_SEG = 384;                 // elements of a row staged at a time (768 bytes): the staging buffer does not grow with dim,
+                                            // so eight CTAs fit an SM and 1024 queries finish in ONE wave (at 16 whole 768-d rows:
+                                            // five per SM, 1.4 waves)
+__host__ __device__ inline int finish2_seg(int dim) { return dim < F2_SEG ? dim : F2_SEG; }
 
 size_t finish2_smem_bytes(int dim, int kprime) {
     const int sel = finish2_sel_cap(kprime);
-    size_t stage = (size_t)finish2_stage_rows(dim) * ((size_t)dim * 2 + 16);
+    size_t stage = (size_t)F2_ROWS * ((size_t)finish2_seg(dim) * 2 + 16);
     if (stage < (size_t)F2_GATHER * 8) stage = (size_t)F2_GATHER * 8;
     return (size_t)dim * 8 + (size_t)sel * 8 + (size_t)sel * 4 + (size_t)kprime * (8 + 4) + 256 * 4 + stage + 64;
 }
@@ -165,30 +168,34 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
             exact[i] = (double)__uint_as_float((uint32_t)(e >> 32));
         }
     } else {
-        const int RB = finish2_stage_rows(p.dim);
+        constexpr int RB = F2_ROWS;
         const int l8 = tid & 7, grp = tid >> 3;
-        const int vec_per_row = p.dim / 8;                        // 16-byte vectors per row
-        const int stride = p.dim * 2 + 16;                        // staged row pitch: +16 bytes keeps the rows of a warp on different banks
+        const int seg = finish2_seg(p.dim);
+        const int stride = seg * 2 + 16;                          // staged row pitch: +16 bytes keeps the rows of a warp on different banks
         const double* qj = qd + l8;
         for (int i0 = 0; i0 < n; i0 += RB) {
             const int rows_here = min(RB, n - i0);
-            for (int r = warp; r < rows_here; r += F2_THREADS / 32) {
-                const uint32_t row = (uint32_t)buf[i0 + r];
-                const uint4* src = reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim);
-                const uint32_t dst = smem_u32(stage + (size_t)r * stride);
-                for (int c = lane; c < vec_per_row; c += 32)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * 16), "l"(src + c) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();
             const int i = i0 + grp;
-            const bool valid = i < n && grp < RB;
-            const uint16_t* x = reinterpret_cast<const uint16_t*>(stage + (size_t)(grp < RB ? grp : 0) * stride) + l8;
+            const bool valid = i < n;
+            const uint16_t* x = reinterpret_cast<const uint16_t*>(stage + (size_t)grp * stride) + l8;
             double acc = 0.0;
-            if (valid) {
+            for (int d0 = 0; d0 < p.dim; d0 += seg) {             // (a lane's chain runs on across the segments, in increasing d)
+                const int dl = min(seg, p.dim - d0);
+                for (int r = warp; r < rows_here; r += F2_THREADS / 32) {
+                    const uint32_t row = (uint32_t)buf[i0 + r];
+                    const uint4* src = reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim + d0);
+                    const uint32_t dst = smem_u32(stage + (size_t)r * stride);
+                    for (int c = lane; c < dl / 8; c += 32)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * 16), "l"(src + c) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncthreads();
+                if (valid) {
 #pragma unroll 4
-                for (int d = 0; d < p.dim; d += 8) acc = fma(qj[d], bits_to_double<DTYPE>(x[d]), acc);
+                    for (int d = 0; d < dl; d += 8) acc = fma(qj[d0 + d], bits_to_double<DTYPE>(x[d]), acc);
+                }
+                __syncthreads();
             }
             double t = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, 1));      // lanes 0,2,4,6: p0+p1, p2+p3, ...
             t = __dadd_rn(t, __shfl_down_sync(0xffffffffu, t, 2));                 // lanes 0,4: (p0+p1)+(p2+p3), ...
@@ -199,7 +206,6 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
                 exact[i] = t;
                 my_err = fmaxf(my_err, fabsf((float)((double)__uint_as_float((uint32_t)(e >> 32)) - t)));
             }
-            __syncthreads();
         }
     }
     if (p.err_max) atomicMax(reinterpret_cast<int*>(&s_err), __float_as_int(my_err));       // non-negative floats order as ints
