@@ -750,7 +750,7 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
             s0.qg_span = 1;
             int rc = launch(s0);
             if (rc) return rc;
-            if (option(OPT_FINISH_VERSION, 2) == 1) {
+            if (option(OPT_FINISH_VERSION, 0) == 1) {
                 size_t tsm = BlockTopK<FN_THREADS, uint32_t>::smem_bytes(pl.s_topk_cap) + 64;
                 sample_threshold_kernel<<<pl.nqb * TC_BM, FN_THREADS, tsm, st>>>(s0.cand, s0.cand_cnt, s0.cap, pl.nqb, pl.s_chunks,
                                                                                 pl.s_rank, pl.s_topk_cap, sp.gthr); count_launch();
@@ -803,8 +803,13 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
     fp.n_flagged = n_flagged;
     fp.err_max = out_err;
     fp.approx = approx;
-    if (approx || option(OPT_FINISH_VERSION, 2) != 1 && finish2_smem_bytes(dim, pl.kprime) <= 200 * 1024) {
-        // second generation (dense_finish.cu): warp-level selection, one thread per candidate row
+    // Which finish kernel: the second generation (dense_finish.cu: 128 threads, warp-level selection) wins while k' is small --
+    // 118 vs 183 us at B = 1024, k = 100 -- but its selection is one warp's serial walk over ~8 k' survivors and its rank
+    // all-pairs, so the first generation (256 threads, block-wide streaming top-k, bitonic sort) is faster for deep searches:
+    // B = 256, k = 500: 0.80 vs 1.19 ms per search, k = 200: 0.60 vs 0.69 ms.  Option finish_version: 0 auto, 1 / 2 forced.
+    const int fin = option(OPT_FINISH_VERSION, 0);
+    const bool fin2 = fin == 2 || (fin == 0 && pl.kprime <= 160);
+    if (approx || (fin2 && finish2_smem_bytes(dim, pl.kprime) <= 200 * 1024)) {
         int rc = launch_finish2(fp, dtype, st);
         if (rc) return rc;
     } else if (dtype == B200RAG_F16) {
