@@ -64,6 +64,9 @@ SIGNATURES = {
     "b200rag_rrf_fuse_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "b200rag_rrf_fuse": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200rag_fuse_select": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p]),
     "b200rag_rerank_learned": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_double, c_double, c_double,
                                               c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200rag_pairwise_jaccard_workspace_bytes": (c_size_t, [c_int32, c_int32]),

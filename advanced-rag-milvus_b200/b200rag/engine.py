@@ -245,6 +245,34 @@ def rrf_fuse(list_ids: torch.Tensor, list_len: torch.Tensor, weights: torch.Tens
     return out
 
 
+def fuse_select(fused: "FusedBatch", picks: Optional[torch.Tensor], use_mmr: Optional[torch.Tensor], top_k: torch.Tensor,
+                list_scores: torch.Tensor, t_max: int):
+    """The tail of the fusion stage (reference retrieval.py:322-333, 485-491, 512-516): per query the MMR picks or the first
+    top_k fused entries, with their columns.  fused = rrf_fuse output; picks i32 [B,t_max] / use_mmr i32 [B] or None; top_k
+    i32 [B]; list_scores f64 [L,B,K].  Returns (rows i64, scores f64, mask i32, n i32 [B], first_method i32, original f64)."""
+    nl, b, kmax = list_scores.shape
+    dev = list_scores.device
+    tot = fused.ids.shape[1]
+    if tot != nl * kmax or list_scores.dtype != torch.float64 or top_k.dtype != torch.int32 or not list_scores.is_contiguous():
+        raise ValueError("fuse_select: list_scores must be contiguous f64 [L,B,K] matching the fused width, top_k i32")
+    for t in (picks, use_mmr):
+        if t is not None and (t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous()):
+            raise ValueError("fuse_select: picks / use_mmr must be contiguous CUDA i32 tensors")
+    rows = torch.empty((b, t_max), dtype=torch.int64, device=dev)
+    scores = torch.empty((b, t_max), dtype=torch.float64, device=dev)
+    mask = torch.empty((b, t_max), dtype=torch.int32, device=dev)
+    first = torch.empty((b, t_max), dtype=torch.int32, device=dev)
+    orig = torch.empty((b, t_max), dtype=torch.float64, device=dev)
+    n = torch.empty((b,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().b200rag_fuse_select(fused.ids.data_ptr(), fused.scores.data_ptr(), fused.mask.data_ptr(), fused.first.data_ptr(),
+                                              fused.n.data_ptr(), b, tot, picks.data_ptr() if picks is not None else None,
+                                              use_mmr.data_ptr() if use_mmr is not None else None, top_k.data_ptr(),
+                                              list_scores.data_ptr(), nl, kmax, int(t_max), rows.data_ptr(), scores.data_ptr(),
+                                              mask.data_ptr(), first.data_ptr(), orig.data_ptr(), n.data_ptr(), _stream_ptr(dev)))
+    return rows, scores, mask, n, first, orig
+
+
 def mmr_select(cand_doc: torch.Tensor, cand_rel: torch.Tensor, cand_n: torch.Tensor, doc_tok_ptr: torch.Tensor,
                doc_tok_ids: torch.Tensor, vocab_size: int, lam: torch.Tensor, k_sel: torch.Tensor, k_max: int
                ) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -324,42 +324,50 @@ class B200HybridRetriever:
                            (packed >> 32).to(torch.int32), out[:, 4 * t_max].to(torch.int32),
                            (packed & 0xffffffff).to(torch.int32), out[:, 2 * t_max: 3 * t_max].contiguous().view(torch.float64))
 
+    def _config_columns(self, configs: Sequence[RetrievalConfig], n_lists: int):
+        """Per-query fusion parameters as device columns: weights f64 [B,L], top_k i32 [B], lambda f64 [B], use_mmr i32 [B].
+        One packed host array -> one copy; batches that repeat a configuration pattern (the usual case: one profile for the
+        whole batch) reuse the columns of the last call."""
+        key = (n_lists, tuple((c.dense_weight, c.sparse_weight, c.top_k, c.mmr_lambda, c.enable_mmr) for c in configs))
+        hit = self._cfg_cache.get(key) if hasattr(self, "_cfg_cache") else None
+        if hit is None:
+            if not hasattr(self, "_cfg_cache") or len(self._cfg_cache) > 16:
+                self._cfg_cache = {}
+            host = np.asarray([[c.dense_weight, c.sparse_weight, DOMAIN_WEIGHT, c.top_k, c.mmr_lambda, float(c.enable_mmr)]
+                               for c in configs], dtype=np.float64)
+            cols = torch.from_numpy(host).to(self.device)
+            hit = (cols[:, :n_lists].contiguous(), cols[:, 3].to(torch.int32), cols[:, 4].contiguous(),
+                   cols[:, 5].to(torch.int32), bool(host[:, 5].any()))
+            self._cfg_cache[key] = hit
+        return hit
+
     def _fuse_local(self, lists: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]], configs: Sequence[RetrievalConfig],
                     t_max: int) -> "BatchResult":
         dev = self.device
         b = len(configs)
         kmax = max(int(ids.shape[1]) for _, ids, _ in lists)
-        lid = torch.full((len(lists), b, kmax), -1, dtype=torch.int64, device=dev)
-        lsc = torch.zeros((len(lists), b, kmax), dtype=torch.float64, device=dev)
-        llen = torch.zeros((len(lists), b), dtype=torch.int32, device=dev)
-        for li, (sc, ids, cnt) in enumerate(lists):
-            lid[li, :, : ids.shape[1]] = ids
-            lsc[li, :, : ids.shape[1]] = sc
-            llen[li] = cnt
-        w = torch.tensor([[c.dense_weight, c.sparse_weight, DOMAIN_WEIGHT][: len(lists)] for c in configs],
-                         dtype=torch.float64, device=dev)
-        fused = engine.rrf_fuse(lid.contiguous(), llen.contiguous(), w, RRF_K)
-        top = torch.tensor([c.top_k for c in configs], dtype=torch.int32, device=dev)
-        tot = fused.ids.shape[1]
-        pos = torch.arange(t_max, device=dev)[None, :].expand(b, t_max).clone()
-        n_out = torch.minimum(fused.n, top)
-        if any(c.enable_mmr for c in configs):
+        if all(int(ids.shape[1]) == kmax for _, ids, _ in lists):
+            lid = torch.stack([ids for _, ids, _ in lists])
+            lsc = torch.stack([sc for sc, _, _ in lists])
+            llen = torch.stack([cnt for _, _, cnt in lists])
+        else:
+            lid = torch.full((len(lists), b, kmax), -1, dtype=torch.int64, device=dev)
+            lsc = torch.zeros((len(lists), b, kmax), dtype=torch.float64, device=dev)
+            llen = torch.zeros((len(lists), b), dtype=torch.int32, device=dev)
+            for li, (sc, ids, cnt) in enumerate(lists):
+                lid[li, :, : ids.shape[1]] = ids
+                lsc[li, :, : ids.shape[1]] = sc
+                llen[li] = cnt
+        w, top, lam, use, any_mmr = self._config_columns(configs, len(lists))
+        fused = engine.rrf_fuse(lid, llen, w, RRF_K)
+        picks = None
+        if any_mmr:
             tok_ptr, tok_ids, vocab = self.index_manager.token_sets()
-            lam = torch.tensor([c.mmr_lambda for c in configs], dtype=torch.float64, device=dev)
-            use = torch.tensor([c.enable_mmr for c in configs], dtype=torch.bool, device=dev)
-            k_sel = torch.where(use, top, torch.zeros_like(top))             # k_sel = 0: the kernel skips the query
-            picks, _ = engine.mmr_select(fused.ids.clamp(min=0).to(torch.int32).contiguous(), fused.scores, fused.n,
-                                         tok_ptr, tok_ids, vocab, lam, k_sel.contiguous(), t_max)
-            pos = torch.where(use[:, None], picks.to(torch.int64).clamp(min=0), pos)
-        pos = pos.clamp(max=tot - 1)
-        valid = torch.arange(t_max, device=dev)[None, :] < n_out[:, None]
-        rows = torch.where(valid, fused.ids.gather(1, pos), torch.full_like(pos, -1))
-        scores = torch.where(valid, fused.scores.gather(1, pos),
-                             torch.full((b, t_max), float("-inf"), dtype=torch.float64, device=dev))
-        mask = torch.where(valid, fused.mask.gather(1, pos), torch.zeros((b, t_max), dtype=torch.int32, device=dev))
-        first = fused.first.gather(1, pos).to(torch.int64).clamp(min=0)          # list * kmax + rank0 of the payload hit
-        orig = lsc.permute(1, 0, 2).reshape(b, -1).gather(1, first)
-        return BatchResult(rows, scores, mask, n_out, torch.div(first, kmax, rounding_mode="floor").to(torch.int32), orig)
+            k_sel = top * use                                                  # k_sel = 0: the kernel skips the query
+            picks, _ = engine.mmr_select(fused.ids.clamp(min=0).to(torch.int32), fused.scores, fused.n,
+                                         tok_ptr, tok_ids, vocab, lam, k_sel, t_max)
+        rows, scores, mask, n_out, first, orig = engine.fuse_select(fused, picks, use if any_mmr else None, top, lsc, t_max)
+        return BatchResult(rows, scores, mask, n_out, first, orig)
 
     def rerank_batch(self, res: "BatchResult", top_k: Optional[int] = None,
                      recency: Optional[torch.Tensor] = None) -> "BatchResult":

@@ -167,6 +167,38 @@ rrf_fuse_kernel(const int64_t* __restrict__ list_ids, const int32_t* __restrict_
     if (tid == 0) out_n[q] = n;
 }
 
+
+// The tail of the fusion stage for a batch (reference retrieval.py:485-491 the fused order, :512-516 the MMR picks, :322-333
+// [:top_k] and the per-hit tags): slot j of query q takes fused position  picks[q][j]  where the query diversifies and  j
+// otherwise, and the columns of that fused entry are gathered -- row id, fused score, method mask, the method whose hit
+// supplies the payload and that method's own score (original_score).  One thread per (query, slot); replaces ~20 small
+// tensor operations per batch.
+__global__ void fuse_select_kernel(const int64_t* __restrict__ fused_ids, const double* __restrict__ fused_scores,
+                                   const int32_t* __restrict__ fused_mask, const int32_t* __restrict__ fused_first,
+                                   const int32_t* __restrict__ fused_n, int n_queries, int tot, const int32_t* __restrict__ picks,
+                                   const int32_t* __restrict__ use_mmr, const int32_t* __restrict__ top_k,
+                                   const double* __restrict__ list_scores, int k_max, int t_max, int64_t* __restrict__ out_rows,
+                                   double* __restrict__ out_scores, int32_t* __restrict__ out_mask, int32_t* __restrict__ out_first_method,
+                                   double* __restrict__ out_original, int32_t* __restrict__ out_n) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_queries * t_max) return;
+    const int q = idx / t_max, j = idx % t_max;
+    const int n_out = min(fused_n[q], top_k[q]);
+    if (j == 0) out_n[q] = n_out;
+    int pos = j;
+    if (picks && use_mmr && use_mmr[q]) pos = max(picks[(size_t)q * t_max + j], 0);
+    pos = min(pos, tot - 1);
+    const size_t at = (size_t)q * tot + pos;
+    const bool valid = j < n_out;
+    out_rows[idx] = valid ? fused_ids[at] : -1;
+    out_scores[idx] = valid ? fused_scores[at] : -CUDART_INF;
+    out_mask[idx] = valid ? fused_mask[at] : 0;
+    const int first = max(fused_first[at], 0);                 // list * k_max + rank0 of the hit that supplies the payload
+    const int list = first / k_max;
+    out_first_method[idx] = list;
+    out_original[idx] = list_scores[((size_t)list * n_queries + q) * k_max + (first - list * k_max)];
+}
+
 }  // namespace b200rag
 
 using namespace b200rag;
@@ -196,6 +228,24 @@ int b200rag_rrf_fuse(const int64_t* list_ids, const int32_t* list_len, int32_t n
     B200_CUDA_CHECK(cudaFuncSetAttribute(rrf_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rrf_fuse_kernel<<<n_queries, RRF_THREADS, smem, st>>>(list_ids, list_len, n_lists, n_queries, k_max, weights, rrf_k,
                                                          table_size, sort_cap, out_ids, out_scores, out_mask, out_first, out_n); count_launch();
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200RAG_OK;
+}
+
+int b200rag_fuse_select(const int64_t* fused_ids, const double* fused_scores, const int32_t* fused_mask, const int32_t* fused_first,
+                        const int32_t* fused_n, int32_t n_queries, int32_t tot, const int32_t* picks, const int32_t* use_mmr,
+                        const int32_t* top_k, const double* list_scores, int32_t n_lists, int32_t k_max, int32_t t_max,
+                        int64_t* out_rows, double* out_scores, int32_t* out_mask, int32_t* out_first_method, double* out_original,
+                        int32_t* out_n, void* stream) {
+    B200_REQUIRE(fused_ids && fused_scores && fused_mask && fused_first && fused_n && top_k && list_scores && out_rows &&
+                 out_scores && out_mask && out_first_method && out_original && out_n, "fuse_select: null pointer");
+    B200_REQUIRE(n_queries >= 0 && n_lists >= 1 && k_max >= 1 && tot == n_lists * k_max && t_max >= 1, "fuse_select: bad sizes");
+    if (n_queries == 0) return B200RAG_OK;
+    const long long total = (long long)n_queries * t_max;
+    fuse_select_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        fused_ids, fused_scores, fused_mask, fused_first, fused_n, n_queries, tot, picks, use_mmr, top_k, list_scores, k_max, t_max,
+        out_rows, out_scores, out_mask, out_first_method, out_original, out_n);
+    count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;
 }

@@ -199,6 +199,10 @@ def c4(dev, reps=8, docs=1_000_000, vocab=100_000, dim=1024, batch=256, depth=50
         return retr.fuse_batch([a, b_], cfg_h)
 
     t_all, res = timed(hybrid, max(3, reps // 2))
+
+    a_fix = mgr.search_batch_ids(qd[0], "semantic_index", depth)
+    b_fix = mgr.search_batch_ids(qs[0], "sparse_index", depth)
+    t_fuse, _ = timed(lambda: retr.fuse_batch([a_fix, b_fix], cfg_h), max(3, reps // 2))
     flops = 2.0 * batch * docs * dim
     out = {"workload": f"{docs} x {dim} bf16 dense top-{depth} + BM25 ({docs} docs, {vocab} terms) top-{depth} -> RRF -> MMR 0.7, k {k}, batch {batch}",
            "dense_ms": t_dense, "dense_full_scan_kernel_ms": t_dense_scan, "dense_tflops": flops / t_dense / 1e9,
@@ -206,7 +210,8 @@ def c4(dev, reps=8, docs=1_000_000, vocab=100_000, dim=1024, batch=256, depth=50
            "sparse_gbs": sp_bytes / t_sparse / 1e6 if sp_bytes else None,
            "sparse_hbm_frac": sp_bytes / (t_sparse * 1e-3) / 1e9 / HBM_GBS if sp_bytes else None,
            "rrf_ms": t_rrf, "mmr_ms": t_mmr, "fused_candidates_mean": float(fused.n.float().mean()),
-           "hybrid_ms": t_all, "hybrid_qps": batch / t_all * 1e3, "results_per_query": float(res.n.float().mean())}
+           "hybrid_ms": t_all, "hybrid_qps": batch / t_all * 1e3,
+           "fuse_batch_ms": t_fuse, "results_per_query": float(res.n.float().mean())}
     if manager is None:
         del mgr
         torch.cuda.empty_cache()

@@ -228,6 +228,22 @@ int b200rag_rrf_fuse(const int64_t* list_ids, const int32_t* list_len, int32_t n
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * The tail of the fusion stage for a batch: which fused entries a query returns and their columns.  Replaces the list
+ * slicing and per-hit tagging at the end of HybridRetriever._retrieve_inner (reference retrieval.py:322-333, 441-461,
+ * 485-491, 512-516): slot j of query q is fused position picks[q][j] (clamped at 0) if use_mmr[q], else j; valid while
+ * j < min(fused_n[q], top_k[q]).
+ *   fused_*      the outputs of b200rag_rrf_fuse, [n_queries, tot] with tot = n_lists * k_max
+ *   picks        i32 [n_queries, t_max] from b200rag_mmr_select, or NULL;  use_mmr i32 [n_queries] or NULL
+ *   list_scores  f64 [n_lists, n_queries, k_max]  the retrieval methods' own scores (original_score of a hit)
+ *   out_rows i64 [n_queries, t_max] (-1 pads), out_scores f64 (-inf pads), out_mask i32 (0 pads),
+ *   out_first_method i32 (index of the list whose hit supplies the payload), out_original f64, out_n i32 [n_queries] */
+int b200rag_fuse_select(const int64_t* fused_ids, const double* fused_scores, const int32_t* fused_mask, const int32_t* fused_first,
+                        const int32_t* fused_n, int32_t n_queries, int32_t tot, const int32_t* picks, const int32_t* use_mmr,
+                        const int32_t* top_k, const double* list_scores, int32_t n_lists, int32_t k_max, int32_t t_max,
+                        int64_t* out_rows, double* out_scores, int32_t* out_mask, int32_t* out_first_method, double* out_original,
+                        int32_t* out_n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Greedy MMR selection on token-set Jaccard (K6).  Replaces HybridRetriever._mmr_diversify (reference
  * retrieval.py:493-516) for a batch.
  *   cand_doc  i32 [n_queries, n_max]  row of each candidate in the token CSR, in fused order
