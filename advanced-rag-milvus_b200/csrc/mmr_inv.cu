@@ -335,18 +335,27 @@ size_t mmr_inv_smem_bytes(int vocab_words) {
 // the sample's first bitmap aliases the heavy sets, and token ids must fit the entries' 22 bits
 bool mmr_inv_vocab_ok(int vocab_words) { return vocab_words <= MI_H_WORDS * MI_THREADS && vocab_words <= (1 << (32 - MI_CAND_BITS - 5)); }
 
-// Per query: the light (token, candidate) incidences, one u32 each, t_cap of them.
-size_t mmr_inv_workspace_bytes(int n_queries, int t_cap) { return align_up((size_t)n_queries * t_cap * 4, 256) + 256; }
+// Per query IN FLIGHT: the light (token, candidate) incidences, one u32 each, t_cap of them.  Large batches are launched
+// MI_WAVE queries at a time over the same region (the launches are ordered on the stream), so the workspace stops growing
+// at MI_WAVE queries (1 GB at 1000 candidates) instead of 4 GB for a 4096-query batch.
+constexpr int MI_WAVE = 1024;
+size_t mmr_inv_workspace_bytes(int n_queries, int t_cap) {
+    return align_up((size_t)(n_queries < MI_WAVE ? n_queries : MI_WAVE) * t_cap * 4, 256) + 256;
+}
 
 int launch_mmr_inv(const int32_t* cand_doc, const double* cand_rel, const int32_t* cand_n, int n_queries, int n_max,
                    const int64_t* doc_tok_ptr, const int32_t* doc_tok_ids, int vocab_words, const double* lambda, const int32_t* k_sel,
                    int k_max, int32_t* out_pick, int32_t* out_n, void* workspace, int t_cap, cudaStream_t st) {
     const size_t smem = mmr_inv_smem_bytes(vocab_words);
     B200_CUDA_CHECK(cudaFuncSetAttribute(mmr_select_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mmr_select_inv_kernel<<<n_queries, MI_THREADS, smem, st>>>(cand_doc, cand_rel, cand_n, n_max, doc_tok_ptr, doc_tok_ids, vocab_words,
-                                                                 lambda, k_sel, k_max, out_pick, out_n, static_cast<uint32_t*>(workspace), t_cap);
-    count_launch();
-    B200_CUDA_CHECK(cudaGetLastError());
+    for (int q0 = 0; q0 < n_queries; q0 += MI_WAVE) {
+        const int nq = n_queries - q0 < MI_WAVE ? n_queries - q0 : MI_WAVE;
+        mmr_select_inv_kernel<<<nq, MI_THREADS, smem, st>>>(cand_doc + (size_t)q0 * n_max, cand_rel + (size_t)q0 * n_max, cand_n + q0, n_max,
+                                                              doc_tok_ptr, doc_tok_ids, vocab_words, lambda + q0, k_sel + q0, k_max,
+                                                              out_pick + (size_t)q0 * k_max, out_n + q0, static_cast<uint32_t*>(workspace), t_cap);
+        count_launch();
+        B200_CUDA_CHECK(cudaGetLastError());
+    }
     return B200RAG_OK;
 }
 

@@ -453,6 +453,31 @@ def test_mmr_large_vocabulary_matches_oracle(eng, vocab, mmr_path):
         assert picks[q, : int(pn[q])].cpu().tolist() == ref, q
 
 
+def test_mmr_batches_beyond_one_wave_agree_with_the_bitset_kernels(eng):
+    """More than 1024 queries: the heavy/light kernel is launched in waves over one workspace region; every query must
+    come back exactly as the round-1 bitset kernels (themselves oracle-checked above) return it."""
+    from b200rag import _lib, synth
+    vocab, n_docs, b, n_max, k = 5000, 3000, 1100, 48, 12
+    dp, ti, _ = synth.zipf_corpus(n_docs, vocab, 9, mean_len=25)
+    rng = np.random.default_rng(5)
+    cand = rng.integers(0, n_docs, size=(b, n_max)).astype(np.int32)
+    n = rng.integers(1, n_max + 1, size=b).astype(np.int32)
+    rel = np.sort(rng.random((b, n_max)) * 0.016, axis=1)[:, ::-1].copy()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    args = (t(cand), t(rel), t(n), t(dp), t(ti.astype(np.int32)), vocab, t(rng.choice([0.3, 0.7, 1.0], size=b)),
+            t(rng.integers(0, k + 1, size=b).astype(np.int32)), k)
+    out = {}
+    for path in (3, 2):
+        _lib.set_option("mmr_path", path)
+        try:
+            picks, pn = eng.mmr_select(*args)
+        finally:
+            _lib.set_option("mmr_path", -1)
+        out[path] = (picks.cpu().numpy(), pn.cpu().numpy())
+    assert (out[3][1] >= 0).all()
+    assert np.array_equal(out[3][1], out[2][1]) and np.array_equal(out[3][0], out[2][0])
+
+
 def test_mmr_heavy_cap_and_long_documents(eng):
     """The heavy/light MMR kernel outside its comfort zone: a 3000-token vocabulary where the sample calls far more than 384
     tokens heavy (the cap moves the rest to the light lists), two documents of 1500 and 1100 tokens (several rounds of the per-pick
