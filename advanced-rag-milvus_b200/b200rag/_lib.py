@@ -60,7 +60,7 @@ SIGNATURES = {
     "b200rag_merge_topk_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "b200rag_merge_topk": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                           c_void_p, c_size_t, c_void_p]),
-    "b200rag_merge_gathered": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "b200rag_merge_gathered": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200rag_rrf_fuse_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "b200rag_rrf_fuse": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -223,8 +223,8 @@ def make_sharded_manager_class():
                 msg, ps, pi = self._send.planes(s.shape[0], k)
                 ps.copy_(s)
                 pi.copy_(i)
-            ms, mi = gather_and_merge(ps, pi, k, engine.merge_topk, self.group, engine.merge_gathered, message=msg)
-            return ms, mi, (mi >= 0).sum(1).to(torch.int32)
+            return gather_and_merge(ps, pi, k, engine.merge_topk, self.group,
+                                    lambda g, kk: engine.merge_gathered(g, kk, with_counts=True), message=msg)
 
         def search_own_queries_arrays(self, queries_local: Any, collection_name: str, top_k: int = 20,
                                       filters: Optional[str] = None):
@@ -257,8 +257,7 @@ def make_sharded_manager_class():
                 send = msg.view(2, world, per, k).permute(1, 0, 2, 3).contiguous()
                 recv = torch.empty_like(send)
                 dist.all_to_all_single(recv, send, group=self.group)
-                ms, mi = engine.merge_gathered(recv, k)
-                cnt = (mi >= 0).sum(1).to(torch.int32)
+                ms, mi, cnt = engine.merge_gathered(recv, k, with_counts=True)
                 hs, hi, hc = self._pinned_like("s", ms), self._pinned_like("i", mi), self._pinned_like("c", cnt)
                 hs.copy_(ms, non_blocking=True)
                 hi.copy_(mi, non_blocking=True)

@@ -202,8 +202,9 @@ def merge_topk(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tup
     return scores, ids
 
 
-def merge_gathered(gathered: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """All-gather buffer i64 [G, 2, B, k] (per rank a plane of fp64 score bit patterns and a plane of ids) -> global top-k."""
+def merge_gathered(gathered: torch.Tensor, k: int, with_counts: bool = False):
+    """All-gather buffer i64 [G, 2, B, k] (per rank a plane of fp64 score bit patterns and a plane of ids) -> global top-k
+    (scores f64 [B,k], ids i64 [B,k][, valid counts i32 [B]])."""
     _require_cuda(gathered, "gathered")
     if gathered.dtype != torch.int64 or gathered.dim() != 4 or gathered.shape[1] != 2 or gathered.shape[3] != k:
         raise ValueError("merge_gathered expects an int64 [G, 2, B, k] tensor")
@@ -211,9 +212,11 @@ def merge_gathered(gathered: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.
     dev = gathered.device
     scores = torch.empty((b, k), dtype=torch.float64, device=dev)
     ids = torch.empty((b, k), dtype=torch.int64, device=dev)
+    counts = torch.empty((b,), dtype=torch.int32, device=dev) if with_counts else None
     with torch.cuda.device(dev):
-        check(_lib.load().b200rag_merge_gathered(gathered.data_ptr(), g, b, k, scores.data_ptr(), ids.data_ptr(), _stream_ptr(dev)))
-    return scores, ids
+        check(_lib.load().b200rag_merge_gathered(gathered.data_ptr(), g, b, k, scores.data_ptr(), ids.data_ptr(),
+                                                 counts.data_ptr() if with_counts else None, _stream_ptr(dev)))
+    return (scores, ids, counts) if with_counts else (scores, ids)
 
 
 @dataclass

@@ -174,7 +174,7 @@ merge_topk_kernel(const double* __restrict__ cand_scores, const int64_t* __restr
 // into its send buffer (b200rag/distributed.py; no pack pass between the search and the collective).  Same ranking rule.
 __global__ void __launch_bounds__(MG_THREADS)
 merge_gathered_kernel(const int64_t* __restrict__ gathered, int n_ranks, int n_queries, int k, int cap,
-                      double* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+                      double* __restrict__ out_scores, int64_t* __restrict__ out_ids, int32_t* __restrict__ out_counts) {
     extern __shared__ __align__(16) char smem[];
     const int tid = threadIdx.x;
     const int q = blockIdx.x;
@@ -207,6 +207,7 @@ merge_gathered_kernel(const int64_t* __restrict__ gathered, int n_ranks, int n_q
         out_scores[(size_t)q * k + i] = i < n ? unmono64(oh[i]) : -CUDART_INF;
         out_ids[(size_t)q * k + i] = i < n ? (int64_t)(~ol[i]) : -1;
     }
+    if (out_counts && tid == 0) out_counts[q] = min(n, k);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -329,7 +330,7 @@ int b200rag_merge_topk(const double* cand_scores, const int64_t* cand_ids, int32
 }
 
 int b200rag_merge_gathered(const int64_t* gathered, int32_t n_ranks, int32_t n_queries, int32_t k,
-                           double* out_scores, int64_t* out_ids, void* stream) {
+                           double* out_scores, int64_t* out_ids, int32_t* out_counts, void* stream) {
     B200_REQUIRE(gathered && out_scores && out_ids, "merge_gathered: null pointer");
     B200_REQUIRE(n_ranks >= 1 && n_queries >= 0 && k > 0, "merge_gathered: bad sizes");
     if (n_queries == 0) return B200RAG_OK;
@@ -341,7 +342,7 @@ int b200rag_merge_gathered(const int64_t* gathered, int32_t n_ranks, int32_t n_q
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     B200_CUDA_CHECK(cudaFuncSetAttribute(merge_gathered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_gathered_kernel<<<n_queries, MG_THREADS, smem, st>>>(gathered, n_ranks, n_queries, k, cap, out_scores, out_ids); count_launch();
+    merge_gathered_kernel<<<n_queries, MG_THREADS, smem, st>>>(gathered, n_ranks, n_queries, k, cap, out_scores, out_ids, out_counts); count_launch();
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;
 }

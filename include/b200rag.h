@@ -205,9 +205,10 @@ int b200rag_merge_topk(const double* cand_scores, const int64_t* cand_ids, int32
 /* Same reduce, reading the NCCL all-gather buffer in place: gathered i64 [n_ranks, 2, n_queries, k] = per rank a plane of
  * k fp64 score bit patterns per query followed by a plane of k ids per query (id < 0 = empty slot) -- i.e. the out_scores and
  * out_ids arrays of b200rag_dense_topk, which a rank points straight at the two halves of its send buffer.  No pack, unpack
- * or transpose pass between the search, the collective and the merge. */
+ * or transpose pass between the search, the collective and the merge.  out_counts i32 [n_queries] (may be NULL): valid results
+ * per query. */
 int b200rag_merge_gathered(const int64_t* gathered, int32_t n_ranks, int32_t n_queries, int32_t k,
-                           double* out_scores, int64_t* out_ids, void* stream);
+                           double* out_scores, int64_t* out_ids, int32_t* out_counts, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Weighted Reciprocal Rank Fusion (K5).  Replaces HybridRetriever._fuse_results (reference
