@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
             s_err = 0.f;
             s_ek_sh = -CUDART_INF;
         }
-    } else {
+    } else if (!p.fin_sel) {
         // ---- the query in fp64 and its squared norm
         double q2 = 0.0;
         for (int d = tid - 32; d < p.dim; d += F2_THREADS - 32) {
@@ -154,6 +154,15 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
     }
     __syncthreads();
     const int n = s_n;
+    if (p.fin_sel) {                                     // split finish: hand the selection over and leave
+        for (int i = tid; i < n; i += F2_THREADS) p.fin_sel[(size_t)slot_q * p.kprime + i] = buf[i];
+        if (tid == 0) {
+            p.fin_n[slot_q] = n;
+            p.fin_m[slot_q] = s_m;
+            if (p.err_max) p.err_max[q] = 0.f;
+        }
+        return;
+    }
 
     // ---- 2. exact canonical re-score.  Rows are staged through shared memory F2_ROWS at a time with 16-byte cp.async copies
     //         (a warp copies whole rows: coalesced 512-byte requests, nothing passes through registers), then eight threads
@@ -250,6 +259,145 @@ int launch_finish2(const FinishParams& fp, int dtype, cudaStream_t st) {
     } else {
         B200_CUDA_CHECK(cudaFuncSetAttribute(dense_finish2_kernel<B200RAG_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dense_finish2_kernel<B200RAG_BF16><<<fp.n_q, F2_THREADS, smem, st>>>(fp); count_launch();
+    }
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200RAG_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- split finish
+// finish3 = dense_finish2_kernel in split mode (selection only) + the two kernels below.  The monolithic kernel re-scores a
+// query's k' candidate rows 16 at a time inside the query's CTA: k'/16 dependent gather round trips per query, and with 256
+// queries x k' = 640 only 256 CTAs to hide them.  Here the re-score is its own grid over (16-row batch, query): every
+// candidate row of the whole batch is in flight at once (B = 1024, k' = 128: 8192 CTAs; B = 256, k' = 640: 10240).
+template <int DTYPE>
+__global__ void __launch_bounds__(F2_THREADS) finish3_rescore_kernel(const FinishParams p) {
+    extern __shared__ __align__(16) char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slot_q = blockIdx.y, i0 = blockIdx.x * F2_ROWS;
+    const int n = p.fin_n[slot_q];
+    if (i0 >= n) return;
+    double* qd = reinterpret_cast<double*>(smem);                                         // [dim] the query in fp64
+    char* stage = reinterpret_cast<char*>(qd + p.dim);
+    const unsigned long long* sel = p.fin_sel + (size_t)slot_q * p.kprime;
+    for (int d = tid; d < p.dim; d += F2_THREADS) qd[d] = bits_to_double<DTYPE>(p.queries[(size_t)slot_q * p.dim + d]);
+    const int rows_here = min(F2_ROWS, n - i0);
+    const int l8 = tid & 7, grp = tid >> 3;
+    const int seg = finish2_seg(p.dim);
+    const int stride = seg * 2 + 16;
+    const double* qj = qd + l8;
+    const int i = i0 + grp;
+    const bool valid = i < n;
+    const uint16_t* x = reinterpret_cast<const uint16_t*>(stage + (size_t)grp * stride) + l8;
+    double acc = 0.0;
+    for (int d0 = 0; d0 < p.dim; d0 += seg) {                     // (a lane's chain runs on across the segments, in increasing d)
+        const int dl = min(seg, p.dim - d0);
+        for (int r = warp; r < rows_here; r += F2_THREADS / 32) {
+            const uint32_t row = (uint32_t)sel[i0 + r];
+            const uint4* src = reinterpret_cast<const uint4*>(p.corpus + (size_t)row * p.dim + d0);
+            const uint32_t dst = smem_u32(stage + (size_t)r * stride);
+            for (int c = lane; c < dl / 8; c += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * 16), "l"(src + c) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                          // (also publishes qd on the first round)
+        if (valid) {
+#pragma unroll 4
+            for (int d = 0; d < dl; d += 8) acc = fma(qj[d0 + d], bits_to_double<DTYPE>(x[d]), acc);
+        }
+        __syncthreads();
+    }
+    double t = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, 1));
+    t = __dadd_rn(t, __shfl_down_sync(0xffffffffu, t, 2));
+    t = __dadd_rn(t, __shfl_down_sync(0xffffffffu, t, 4));
+    if (valid && l8 == 0) {
+        p.fin_exact[(size_t)slot_q * p.kprime + i] = t;
+        if (p.err_max) {
+            const float err = fabsf((float)((double)__uint_as_float((uint32_t)(sel[i] >> 32)) - t));
+            atomicMax(reinterpret_cast<int*>(p.err_max + slot_q), __float_as_int(err));       // non-negative floats order as ints
+        }
+    }
+}
+
+constexpr int F3_RANK_THREADS = 256;
+
+template <int DTYPE>
+__global__ void __launch_bounds__(F3_RANK_THREADS) finish3_rank_kernel(const FinishParams p) {
+    extern __shared__ __align__(16) char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = blockIdx.x;
+    double* exact = reinterpret_cast<double*>(smem);                                      // [kprime]
+    uint32_t* rows = reinterpret_cast<uint32_t*>(exact + p.kprime);                       // [kprime]
+    __shared__ double s_q2[F3_RANK_THREADS / 32];
+    __shared__ double s_ek_sh;
+    const int n = p.fin_n[q];
+    for (int i = tid; i < n; i += F3_RANK_THREADS) {
+        exact[i] = p.fin_exact[(size_t)q * p.kprime + i];
+        rows[i] = (uint32_t)p.fin_sel[(size_t)q * p.kprime + i];
+    }
+    double q2 = 0.0;
+    for (int d = tid; d < p.dim; d += F3_RANK_THREADS) {
+        const double v = bits_to_double<DTYPE>(p.queries[(size_t)q * p.dim + d]);
+        q2 = fma(v, v, q2);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, off);
+    if (lane == 0) s_q2[warp] = q2;
+    if (tid == 0) s_ek_sh = -CUDART_INF;
+    __syncthreads();
+    const int kk = min(p.k, n);
+    for (int i = tid; i < n; i += F3_RANK_THREADS) {
+        const double e = exact[i];
+        const uint32_t r = rows[i];
+        int rk = 0;
+        for (int j = 0; j < n; ++j) rk += (exact[j] > e) || (exact[j] == e && rows[j] < r);
+        if (rk < p.k) {
+            p.out_scores[(size_t)q * p.k + rk] = e;
+            p.out_ids[(size_t)q * p.k + rk] = p.id_offset + (int64_t)r;
+        }
+        if (rk == kk - 1) s_ek_sh = e;
+    }
+    for (int i = kk + tid; i < p.k; i += F3_RANK_THREADS) {
+        p.out_scores[(size_t)q * p.k + i] = -CUDART_INF;
+        p.out_ids[(size_t)q * p.k + i] = -1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double q2s = 0.0;                                  // (the proof's epsilon only needs |q| to a few ulps: any summation order)
+        for (int w = 0; w < F3_RANK_THREADS / 32; ++w) q2s += s_q2[w];
+        const double eps = 2.0 * (double)p.dim * 1.1920928955078125e-07 * sqrt(q2s) * p.row_norm_bound;
+        const float m = p.fin_m[q];
+        const bool proven = (m == -CUDART_INF_F) || (n >= p.k && s_ek_sh > (double)m + eps);
+        const int flag = proven ? 0 : 1;
+        if (p.out_flags) p.out_flags[q] = flag;
+        if (flag) p.flag_list[atomicAdd(p.n_flagged, 1)] = q;
+    }
+}
+
+size_t finish3_workspace_bytes(int n_q, int kprime) {
+    return align_up((size_t)n_q * kprime * 8, 256) * 2 + align_up((size_t)n_q * 4, 256) * 2;
+}
+
+int launch_finish3(FinishParams fp, int dtype, void* fin_ws, cudaStream_t st) {
+    char* w = static_cast<char*>(fin_ws);
+    const size_t plane = align_up((size_t)fp.n_q * fp.kprime * 8, 256), small = align_up((size_t)fp.n_q * 4, 256);
+    fp.fin_sel = reinterpret_cast<unsigned long long*>(w);
+    fp.fin_exact = reinterpret_cast<double*>(w + plane);
+    fp.fin_n = reinterpret_cast<int*>(w + 2 * plane);
+    fp.fin_m = reinterpret_cast<float*>(w + 2 * plane + small);
+    int rc = launch_finish2(fp, dtype, st);                       // split mode: selection only
+    if (rc) return rc;
+    const size_t smem_b = (size_t)fp.dim * 8 + (size_t)F2_ROWS * ((size_t)finish2_seg(fp.dim) * 2 + 16) + 16;
+    const size_t smem_c = (size_t)fp.kprime * 12 + 16;
+    const dim3 grid_b((fp.kprime + F2_ROWS - 1) / F2_ROWS, fp.n_q);
+    if (dtype == B200RAG_F16) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(finish3_rescore_kernel<B200RAG_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        finish3_rescore_kernel<B200RAG_F16><<<grid_b, F2_THREADS, smem_b, st>>>(fp); count_launch();
+        finish3_rank_kernel<B200RAG_F16><<<fp.n_q, F3_RANK_THREADS, smem_c, st>>>(fp); count_launch();
+    } else {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(finish3_rescore_kernel<B200RAG_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        finish3_rescore_kernel<B200RAG_BF16><<<grid_b, F2_THREADS, smem_b, st>>>(fp); count_launch();
+        finish3_rank_kernel<B200RAG_BF16><<<fp.n_q, F3_RANK_THREADS, smem_c, st>>>(fp); count_launch();
     }
     B200_CUDA_CHECK(cudaGetLastError());
     return B200RAG_OK;

@@ -482,7 +482,7 @@ struct TensorPlan {
     int sample, s_stride, s_tiles, s_chunks, s_items, s_kprime, s_cap, s_rank, s_topk_cap;   // strided sample pass
     int stage_rows;
     size_t scan_smem, finish_smem;
-    size_t off_cand, off_cnt, off_gthr, off_flaglist, off_nflag, off_stats, off_qpad, off_exact, total;
+    size_t off_cand, off_cnt, off_gthr, off_flaglist, off_nflag, off_stats, off_qpad, off_exact, off_fin, total;
     // tier 0: flagged queries re-scanned on the tensor path with the widest candidate set the kernels support
     int t0, t0_nq, t0_nqb, t0_kprime, t0_cap, t0_span, t0_chunks, t0_items, t0_clusters;
     int t0_sample, t0_s_stride, t0_s_tiles, t0_s_chunks, t0_s_items;
@@ -605,6 +605,7 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
     pl.off_flaglist = take((size_t)n_q * 4);
     pl.off_qpad = take((size_t)pl.nqb * TC_BM * dim * 2);      // query block padded with zero rows (no TMA out-of-bounds rows)
     pl.off_nflag = take(256);
+    pl.off_fin = take(finish3_workspace_bytes(n_q, pl.kprime));          // split finish: selections + exact scores
     // tier 0 (CTA-pair scan generation only; pointless when the first pass already runs at the widest k')
     pl.t0 = option(OPT_NO_TIER0, 0) == 0 && pl.kprime < TC_T0_KPRIME && n_rows > 0;
     if (pl.t0) {
@@ -809,7 +810,10 @@ int run_tensor(const void* corpus16, int64_t n_rows, int dim, int dtype, const v
     // B = 256, k = 500: 0.80 vs 1.19 ms per search, k = 200: 0.60 vs 0.69 ms.  Option finish_version: 0 auto, 1 / 2 forced.
     const int fin = option(OPT_FINISH_VERSION, 0);
     const bool fin2 = fin == 2 || (fin == 0 && pl.kprime <= 160);
-    if (approx || (fin2 && finish2_smem_bytes(dim, pl.kprime) <= 200 * 1024)) {
+    if (!approx && fin == 3 && finish2_smem_bytes(dim, pl.kprime) <= 200 * 1024 && n_rows > 0) {
+        int rc = launch_finish3(fp, dtype, ws + pl.off_fin, st);
+        if (rc) return rc;
+    } else if (approx || (fin2 && finish2_smem_bytes(dim, pl.kprime) <= 200 * 1024)) {
         int rc = launch_finish2(fp, dtype, st);
         if (rc) return rc;
     } else if (dtype == B200RAG_F16) {

@@ -32,12 +32,22 @@ struct FinishParams {
     const int32_t* q_list = nullptr;
     const int32_t* gate = nullptr;
     int approx = 0;       // B200RAG_DENSE_APPROX: rank by the tensor-core (fp32) scores, no fp64 re-score, no proof
+    // split finish (launch_finish3): the selection of every query, handed from the select kernel to the wide re-score kernel
+    // and on to the rank kernel through the workspace
+    unsigned long long* fin_sel = nullptr;   // [n_q, kprime] (tensor score bits << 32) | row
+    double* fin_exact = nullptr;             // [n_q, kprime] canonical fp64 scores
+    int* fin_n = nullptr;                    // [n_q] candidates selected
+    float* fin_m = nullptr;                  // [n_q] bound on the tensor score of every row outside the selection
 };
 
 
 // Second generation (dense_finish.cu): one 128-thread CTA per query, warp-level selection, one thread per candidate row.
 size_t finish2_smem_bytes(int dim, int kprime);
 int launch_finish2(const FinishParams& fp, int dtype, cudaStream_t st);
+// Split finish: the same selection kernel, then the fp64 re-score as its own grid over (query, 16 candidate rows) -- every
+// candidate row of the batch in flight at once instead of 16 per query -- then a rank / proof / emit kernel.
+size_t finish3_workspace_bytes(int n_q, int kprime);
+int launch_finish3(FinishParams fp, int dtype, void* fin_ws, cudaStream_t st);
 // Warp-per-query replacement of sample_threshold_kernel.
 int launch_sample_threshold2(const unsigned long long* cand, int cap, int nqb, int n_chunks, int rank, unsigned int* gthr,
                              cudaStream_t st, const int* gate);

@@ -130,7 +130,7 @@ int b200rag_debug_set_stats_buffer(int32_t kind, uint64_t* device_buf, size_t n_
 /* A/B options for measurements (tools/scan_ab.py, tools/sparse_ab.py).  Process-wide integer knobs, set explicitly and read
  * with atomic loads -- nothing is read from the environment.  value < 0 restores the built-in default.
  *   "scan_version" 1|3, "qg_span", "epi" 0|1, "no_sample" 0|1, "stage_rows" 8|16|32, "sample_mult", "mmr_path" (0 auto, 1 general
- *   kernel), "sparse_slices", "sparse_flags", "no_tier0" 0|1, "finish_version".
+ *   kernel), "sparse_slices", "sparse_flags", "no_tier0" 0|1, "finish_version" 0 auto | 1 | 2 | 3.
  * b200rag_get_option returns the stored value (-1 = default in force, -2 = unknown name). */
 int b200rag_set_option(const char* name, int64_t value);
 int64_t b200rag_get_option(const char* name);

@@ -59,6 +59,25 @@ def test_tensor_path_matches_oracle(eng, oracle_lib, n, d, b, k, dt):
     assert np.all(err <= eps / 4), (err.max(), eps.min())
 
 
+@pytest.mark.parametrize("finish_version", [1, 2, 3])
+@pytest.mark.parametrize("n,d,b,k,dt", [(100, 64, 3, 100, "f16"), (20000, 1024, 64, 100, "bf16"), (30000, 128, 16, 500, "f16"),
+                                         (3000, 4096, 130, 10, "bf16"), (60000, 384, 1024, 10, "f16")])
+def test_every_finish_generation_matches_oracle(eng, oracle_lib, finish_version, n, d, b, k, dt):
+    """The three finish-stage generations (1: block-wide streaming top-k, 2: warp-select monolithic, 3: split select /
+    wide re-score / rank) are selected by k' in the product path; forced one by one they must all return the oracle's answer."""
+    from b200rag import _lib
+    _lib.set_option("finish_version", finish_version)
+    try:
+        s, i, f, err, ref_s, ref_i, qf, rnb = _case(eng, oracle_lib, n, d, b, k, dt, seed=n + d + b + 1)
+    finally:
+        _lib.set_option("finish_version", -1)
+    assert np.array_equal(i, ref_i)
+    assert np.array_equal(s.view(np.uint64), ref_s.view(np.uint64))
+    assert f.sum() == 0
+    eps = 2.0 * d * 2.0 ** -23 * np.sqrt((qf ** 2).sum(1)) * rnb
+    assert np.all(err <= eps / 4), (err.max(), eps.min())
+
+
 def test_tensor_path_ip_metric_unnormalised(eng, oracle_lib):
     s, i, f, err, ref_s, ref_i, qf, rnb = _case(eng, oracle_lib, 50000, 256, 40, 20, "f16", seed=3, metric="IP")
     assert np.array_equal(i, ref_i) and np.array_equal(s, ref_s)
