@@ -23,17 +23,114 @@ constexpr int F2_THREADS = 128;
 constexpr int F2_ROWS = F2_THREADS / 8;     // candidate rows re-scored per batch: eight threads share a row
 constexpr int F2_GATHER = 1024;             // survivors gathered per round (8 KB, aliased with the row staging buffer)
 
-__host__ __device__ inline int finish2_sel_cap(int kprime) { return 2 * kprime <= 512 ? 512 : 2 * kprime; }
 constexpr int F2_SEG = 384;                 // elements of a row staged at a time (768 bytes): the staging buffer does not grow with dim,
                                             // so eight CTAs fit an SM and 1024 queries finish in ONE wave (at 16 whole 768-d rows:
                                             // five per SM, 1.4 waves)
 __host__ __device__ inline int finish2_seg(int dim) { return dim < F2_SEG ? dim : F2_SEG; }
+// The staging region doubles as the selection's working set: k' running winners + one round of gathered survivors.
+__host__ __device__ inline size_t finish2_stage_bytes(int dim, int kprime) {
+    size_t stage = (size_t)F2_ROWS * ((size_t)finish2_seg(dim) * 2 + 16);
+    const size_t work = ((size_t)kprime + F2_GATHER / 2) * 8;
+    if (work > stage) stage = work;
+    if (kprime > 256) {                                  // the bitonic rank sorts (score, row) pairs of the next power of two here
+        size_t np2 = 512;
+        while (np2 < (size_t)kprime) np2 <<= 1;
+        if (np2 * 12 > stage) stage = np2 * 12;
+    }
+    return stage;
+}
 
 size_t finish2_smem_bytes(int dim, int kprime) {
-    const int sel = finish2_sel_cap(kprime);
-    size_t stage = (size_t)F2_ROWS * ((size_t)finish2_seg(dim) * 2 + 16);
-    if (stage < (size_t)F2_GATHER * 8) stage = (size_t)F2_GATHER * 8;
-    return (size_t)dim * 8 + (size_t)sel * 8 + (size_t)sel * 4 + (size_t)kprime * (8 + 4) + 256 * 4 + stage + 64;
+    return (size_t)dim * 8 + (size_t)kprime * (8 + 8 + 4) + 256 * 4 + 256 * 4 + finish2_stage_bytes(dim, kprime) + 64;
+}
+
+// Block-wide selection of the kprime best of work[0, cnt) by tensor-core score (the high 32 bits of an entry, compared as
+// order-preserving keys).  The scores of one query share their exponent, so the keys are first made relative to the set's
+// minimum and shifted up to fill 32 bits: the four 8-bit radix passes that narrow the key of the kprime-th best entry then
+// see evenly filled histograms and plain shared-memory atomics do not pile up (a first version aggregated them per warp with
+// match.any -- a third of the kernel's stall samples).  Warp 0 picks the digit after each pass; one more pass moves the winners
+// to out[0, kprime): everything above the threshold key and as many of its ties as are still needed (which ties does not
+// matter: the caller's bound m covers every dropped entry, and a result is only returned if the proof holds).  Returns the
+// threshold score.  All F2_THREADS threads call; cnt > kprime.
+__device__ float block_select(const unsigned long long* work, int cnt, int kprime, unsigned long long* out, int* hist, int* s_sel) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
+    for (int i = tid; i < cnt; i += F2_THREADS) {
+        const uint32_t key = mono32(__uint_as_float((uint32_t)(work[i] >> 32)));
+        kmin = min(kmin, key);
+        kmax = max(kmax, key);
+    }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) { hist[warp] = (int)kmin; hist[8 + warp] = (int)kmax; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < F2_THREADS / 32; ++w) { kmin = min(kmin, (uint32_t)hist[w]); kmax = max(kmax, (uint32_t)hist[8 + w]); }
+    __syncthreads();
+    const int lz = kmax > kmin ? __clz(kmax - kmin) : 0;           // (all keys equal: every digit is 0, the tie rule takes kprime of them)
+    uint32_t prefix = 0u;
+    int need = kprime;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int b = tid; b < 256; b += F2_THREADS) hist[b] = 0;
+        __syncthreads();
+        for (int i = tid; i < cnt; i += F2_THREADS) {
+            const uint32_t key = (mono32(__uint_as_float((uint32_t)(work[i] >> 32))) - kmin) << lz;
+            if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // the digit d of the kprime-th best: the largest d with  sum_{b >= d} hist[b] >= need
+            int h[8], mine = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = hist[lane * 8 + j]; mine += h[j]; }
+            int above = mine;                                    // inclusive suffix sum over lanes (lane 31 holds the top digits)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_down_sync(0xffffffffu, above, o);
+                if (lane + o < 32) above += u;
+            }
+            const int higher = above - mine;                     // entries in the lanes above this one
+            if (higher < need && above >= need) {                // exactly one lane
+                int acc = higher, d = 7;
+                for (; d > 0; --d) {
+                    if (acc + h[d] >= need) break;
+                    acc += h[d];
+                }
+                s_sel[0] = lane * 8 + d;
+                s_sel[1] = need - acc;                           // still to take among the entries that carry this digit
+            }
+        }
+        __syncthreads();
+        prefix |= (uint32_t)s_sel[0] << shift;
+        need = s_sel[1];
+        __syncthreads();
+    }
+    if (tid == 0) { s_sel[2] = 0; s_sel[3] = 0; }
+    __syncthreads();
+    const int n_above = kprime - need;
+    for (int i0 = 0; i0 < cnt; i0 += F2_THREADS) {
+        const int i = i0 + tid;
+        unsigned long long e = 0ull;
+        uint32_t key = 0u;
+        if (i < cnt) { e = work[i]; key = (mono32(__uint_as_float((uint32_t)(e >> 32))) - kmin) << lz; }
+        const bool gt = i < cnt && key > prefix, eq = i < cnt && key == prefix;
+        const unsigned bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
+        int base_g = 0, base_e = 0;
+        if (lane == 0) {
+            if (bg) base_g = atomicAdd(&s_sel[2], __popc(bg));
+            if (be) base_e = atomicAdd(&s_sel[3], __popc(be));
+        }
+        base_g = __shfl_sync(0xffffffffu, base_g, 0);
+        base_e = __shfl_sync(0xffffffffu, base_e, 0);
+        if (gt) out[base_g + __popc(bg & ((1u << lane) - 1u))] = e;
+        if (eq) {
+            const int t = base_e + __popc(be & ((1u << lane) - 1u));
+            if (t < need) out[n_above + t] = e;
+        }
+    }
+    __syncthreads();
+    return unmono32(kmin + (prefix >> lz));
 }
 
 template <int DTYPE>
@@ -46,15 +143,15 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
     if (p.gate && slot_q >= __ldg(p.gate)) return;
     const int q = p.q_list ? __ldg(p.q_list + slot_q) : slot_q;
     const int qb = slot_q / TC_BM, ql = slot_q % TC_BM;
-    const int sel_cap = finish2_sel_cap(p.kprime);
     double* qd = reinterpret_cast<double*>(smem);                                         // [dim] the query in fp64
-    unsigned long long* buf = reinterpret_cast<unsigned long long*>(qd + p.dim);          // [sel_cap] (score bits << 32) | row
-    uint32_t* scratch = reinterpret_cast<uint32_t*>(buf + sel_cap);                        // [sel_cap] keys of the smem select
-    double* exact = reinterpret_cast<double*>(scratch + sel_cap);                          // [kprime]
+    unsigned long long* buf = reinterpret_cast<unsigned long long*>(qd + p.dim);          // [kprime] the selection: (score bits << 32) | row
+    double* exact = reinterpret_cast<double*>(buf + p.kprime);                             // [kprime]
     uint32_t* rows = reinterpret_cast<uint32_t*>(exact + p.kprime);                        // [kprime]
     int* s_cnt = reinterpret_cast<int*>(rows + p.kprime);                                  // [<= 256] survivors per chunk
-    char* stage = reinterpret_cast<char*>(s_cnt + 256);
+    int* hist = s_cnt + 256;                                                               // [256] radix histogram of the selection
+    char* stage = reinterpret_cast<char*>(hist + 256);
     stage = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(stage) + 15) & ~uintptr_t(15));
+    __shared__ int s_sel[4], s_wcnt;
     __shared__ int s_n, s_total;
     __shared__ float s_m;
     __shared__ double s_q2[F2_THREADS / 32];
@@ -82,68 +179,66 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
     }
     __syncthreads();
     const int total = s_total;
-    // ---- 1. the k' best by tensor-core score over all chunks of this query.  All threads first copy the survivors -- a handful
-    //         per chunk, ~8 k' in all -- into shared memory with independent loads (one round trip instead of one per 32
-    //         entries), F2_GATHER at a time into the region the re-score later stages rows in; warp 0 then selects from there.
-    unsigned long long* gathered = reinterpret_cast<unsigned long long*>(stage);
-    int cnt = 0;                                         // (warp 0's running state across the rounds)
+    // ---- 1. the k' best by tensor-core score over all chunks of this query.  The survivors -- a handful per chunk, ~8 k' in
+    //         all -- are copied into the working set in shared memory (the region the re-score later stages rows in) with
+    //         independent loads, one round trip per round; whenever the set holds more than k' entries the whole block selects
+    //         the k' best (block_select) and later rounds only admit entries above the threshold that left.
+    unsigned long long* work = reinterpret_cast<unsigned long long*>(stage);
+    const int round = (int)(finish2_stage_bytes(p.dim, p.kprime) / 8) - p.kprime;      // survivors admitted per round
     float thr = -CUDART_INF_F;
     bool compacted = false;
-    for (int g0 = 0; g0 < total; g0 += F2_GATHER) {
-        const int g_n = min(F2_GATHER, total - g0);
-        for (int i = tid; i < g_n; i += F2_THREADS) {
-            const int pos = g0 + i;
-            int lo = 0, hi = p.n_chunks - 1;             // last chunk whose prefix is <= pos
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (s_cnt[mid] <= pos) lo = mid;
-                else hi = mid - 1;
+    if (tid == 0) s_wcnt = 0;
+    __syncthreads();
+    for (int g0 = 0; g0 < total; g0 += round) {
+        const int g_n = min(round, total - g0);
+        for (int i0 = 0; i0 < g_n; i0 += F2_THREADS) {
+            const int i = i0 + tid;
+            unsigned long long e = 0ull;
+            bool pass = false;
+            if (i < g_n) {
+                const int pos = g0 + i;
+                int lo = 0, hi = p.n_chunks - 1;         // last chunk whose prefix is <= pos
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_cnt[mid] <= pos) lo = mid;
+                    else hi = mid - 1;
+                }
+                e = __ldg(p.cand + (((size_t)(lo * p.nqb + qb)) * TC_BM + ql) * p.cap + (pos - s_cnt[lo]));
+                pass = !compacted || __uint_as_float((uint32_t)(e >> 32)) > thr;
             }
-            gathered[i] = __ldg(p.cand + (((size_t)(lo * p.nqb + qb)) * TC_BM + ql) * p.cap + (pos - s_cnt[lo]));
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            int base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&s_wcnt, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) work[base + __popc(bal & ((1u << lane) - 1u))] = e;
         }
         __syncthreads();
-        if (warp == 0) {
-            for (int i0 = 0; i0 < g_n; i0 += 32) {
-                const int i = i0 + lane;
-                unsigned long long e = 0ull;
-                bool pass = false;
-                if (i < g_n) {
-                    e = gathered[i];
-                    pass = !compacted || __uint_as_float((uint32_t)(e >> 32)) > thr;
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                if (pass) buf[cnt + __popc(bal & ((1u << lane) - 1u))] = e;
-                cnt += __popc(bal);
-                if (cnt > sel_cap - 32) {
-                    __syncwarp();
-                    thr = fmaxf(thr, warp_compact(buf, cnt, p.kprime, sel_cap, smem_u32(scratch), lane));
-                    cnt = p.kprime;
-                    compacted = true;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (warp == 0) {
-        __syncwarp();
+        const int cnt = s_wcnt;
         if (cnt > p.kprime) {
-            thr = fmaxf(thr, warp_compact(buf, cnt, p.kprime, sel_cap, smem_u32(scratch), lane));
-            cnt = p.kprime;
+            thr = fmaxf(thr, block_select(work, cnt, p.kprime, buf, hist, s_sel));
             compacted = true;
+            for (int i = tid; i < p.kprime; i += F2_THREADS) work[i] = buf[i];
+            if (tid == 0) s_wcnt = p.kprime;
+            __syncthreads();
         }
-        if (lane == 0) {
+    }
+    {
+        const int cnt = s_wcnt;
+        if (!compacted) for (int i = tid; i < cnt; i += F2_THREADS) buf[i] = work[i];
+        if (tid == 0) {
             s_n = cnt;
             // m: every row outside the candidate set has tensor-core score <= m (-inf if nothing was ever dropped): the scan
-            // drops a row only below a threshold it pushed to gthr, the merge above only at or below its last threshold
+            // drops a row only below a threshold it pushed to gthr, the selection above only at or below its last threshold
             const unsigned int gk = p.gthr[slot_q];
             s_m = fmaxf(compacted ? thr : -CUDART_INF_F, gk ? unmono32(gk) : -CUDART_INF_F);
             s_err = 0.f;
             s_ek_sh = -CUDART_INF;
         }
-    } else if (!p.fin_sel) {
+    }
+    if (!p.fin_sel) {
         // ---- the query in fp64 and its squared norm
         double q2 = 0.0;
-        for (int d = tid - 32; d < p.dim; d += F2_THREADS - 32) {
+        for (int d = tid; d < p.dim; d += F2_THREADS) {
             const double v = bits_to_double<DTYPE>(p.queries[(size_t)q * p.dim + d]);
             qd[d] = v;
             q2 = fma(v, v, q2);
@@ -220,18 +315,51 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
     if (p.err_max) atomicMax(reinterpret_cast<int*>(&s_err), __float_as_int(my_err));       // non-negative floats order as ints
     __syncthreads();
 
-    // ---- 3. rank by (exact desc, row asc) and emit: all-pairs rank count
+    // ---- 3. rank by (exact desc, row asc) and emit.  Up to 256 candidates: all-pairs rank count (n^2 / 128 comparisons per
+    //         thread, no barriers).  Deeper candidate sets (k' = 640 in the tier-0 re-scan: 3200 fp64 comparisons per thread)
+    //         are sorted instead: bitonic network over (score, row) pairs in the staging region, which is free again.
     const int kk = min(p.k, n);
-    for (int i = tid; i < n; i += F2_THREADS) {
-        const double e = exact[i];
-        const uint32_t r = rows[i];
-        int rk = 0;
-        for (int j = 0; j < n; ++j) rk += (exact[j] > e) || (exact[j] == e && rows[j] < r);
-        if (rk < p.k) {
-            p.out_scores[(size_t)q * p.k + rk] = e;
-            p.out_ids[(size_t)q * p.k + rk] = p.id_offset + (int64_t)r;
+    if (n <= 256) {
+        for (int i = tid; i < n; i += F2_THREADS) {
+            const double e = exact[i];
+            const uint32_t r = rows[i];
+            int rk = 0;
+            for (int j = 0; j < n; ++j) rk += (exact[j] > e) || (exact[j] == e && rows[j] < r);
+            if (rk < p.k) {
+                p.out_scores[(size_t)q * p.k + rk] = e;
+                p.out_ids[(size_t)q * p.k + rk] = p.id_offset + (int64_t)r;
+            }
+            if (rk == kk - 1) s_ek_sh = e;
         }
-        if (rk == kk - 1) s_ek_sh = e;
+    } else {
+        int np2 = 512;
+        while (np2 < n) np2 <<= 1;
+        double* sk = reinterpret_cast<double*>(stage);                     // [np2] scores, padded with -inf
+        uint32_t* sr = reinterpret_cast<uint32_t*>(sk + np2);              // [np2] rows, padded with the largest id
+        for (int i = tid; i < np2; i += F2_THREADS) {
+            sk[i] = i < n ? exact[i] : -CUDART_INF;
+            sr[i] = i < n ? rows[i] : 0xffffffffu;
+        }
+        for (int size = 2; size <= np2; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                __syncthreads();
+                for (int t = tid; t < np2 / 2; t += F2_THREADS) {
+                    const int i = 2 * t - (t & (stride - 1));             // lower index of the pair
+                    const int j = i + stride;
+                    const bool desc = (i & size) == 0;                     // this block of the network sorts best-first
+                    const double a = sk[i], b = sk[j];
+                    const uint32_t ra = sr[i], rb = sr[j];
+                    const bool a_first = (a > b) || (a == b && ra < rb);   // a ranks before b
+                    if (a_first != desc) { sk[i] = b; sk[j] = a; sr[i] = rb; sr[j] = ra; }
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < kk; i += F2_THREADS) {
+            p.out_scores[(size_t)q * p.k + i] = sk[i];
+            p.out_ids[(size_t)q * p.k + i] = p.id_offset + (int64_t)sr[i];
+        }
+        if (tid == 0 && kk > 0) s_ek_sh = sk[kk - 1];
     }
     for (int i = kk + tid; i < p.k; i += F2_THREADS) {
         p.out_scores[(size_t)q * p.k + i] = -CUDART_INF;
@@ -239,7 +367,7 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
     }
     __syncthreads();
     if (tid == 0) {
-        const double q2 = s_q2[1] + s_q2[2] + s_q2[3];
+        const double q2 = s_q2[0] + s_q2[1] + s_q2[2] + s_q2[3];
         const double eps = 2.0 * (double)p.dim * 1.1920928955078125e-07 * sqrt(q2) * p.row_norm_bound;
         const float m = s_m;
         // proven complete iff nothing was dropped (m = -inf) or the k-th exact score clears m + eps

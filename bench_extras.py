@@ -232,7 +232,9 @@ def near_duplicates(dev, n=1_000_000, d=768, b=1024, k=100, copies=64, reps=5):
         idx.add(rows)
         t, (s_, i_, f_) = timed(lambda: idx.search(q, k), reps)
         sx, ix, _ = idx.search(q[:8], k, engine.DENSE_EXACT)
-        out[name] = {"ms": t, "flagged_fraction": float(f_.float().mean()),
+        out[name] = {"ms": t, "flagged_fraction": float((f_ != 0).float().mean()),            # not proven by the first pass
+                     "served_by_tier0_fraction": float(((f_ & 2) != 0).float().mean()),
+                     "served_by_exact_fallback_fraction": float(((f_ & 1) != 0).float().mean()),
                      "exact": bool(torch.equal(i_[:8], ix) and torch.equal(s_[:8], sx))}
         del idx
         torch.cuda.empty_cache()
