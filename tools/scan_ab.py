@@ -1,6 +1,6 @@
 """A/B the tensor-core scan generations in ONE process on one resident index, in steady state (power-capped clocks).
 
-For each (B200RAG_SCAN_VERSION, B200RAG_CLUSTER) setting: `reps` back-to-back searches; the b200rag_profile_next_scan hook
+For each (scan_version, epi, qg_span, sample_mult) option setting (b200rag_set_option): `reps` back-to-back searches; the b200rag_profile_next_scan hook
 times the FULL scan kernel alone, CUDA events time the whole search (prepare + sample pass + scan + finish), and the
 per-role cycle counters of the last scan give the effective SM clock (mma_total cycles / scan time).
 """
@@ -39,11 +39,11 @@ flops = 2.0 * args.batch * args.rows * args.dim
 print(f"{args.dtype} rows={args.rows} dim={args.dim} B={args.batch} k={args.k} reps={args.reps} mode={args.mode}")
 for cfg in args.configs.split(","):
     ver, cs, span, mult = (cfg.split(":") + ["0", "8"])[:4] if cfg.count(":") >= 3 else (cfg.split(":") + ["0"])[:3] + ["8"]
-    os.environ["B200RAG_SAMPLE_MULT"] = mult            # fourth field: expected rows above the sampled threshold, in k'
-    os.environ["B200RAG_EPI"] = cs                      # second field: epilogue variant (0 = compare chain, 1 = sub-group maxima)
-    os.environ["B200RAG_SCAN_VERSION"] = ver
-    os.environ["B200RAG_CLUSTER"] = cs
-    os.environ["B200RAG_QG_SPAN"] = span
+    _lib.set_option("sample_mult", int(mult))           # fourth field: expected rows above the sampled threshold, in k'
+    _lib.set_option("epi", int(cs))                     # second field: epilogue variant (0 = compare chain, 1 = sub-group maxima)
+    _lib.set_option("scan_version", int(ver))
+    _lib.set_option("qg_span", int(span) if int(span) > 0 else -1)
+    stats = torch.zeros((256, 16), dtype=torch.int64, device=dev)
     for i in range(3):
         idx.search(qs[i], args.k, mode)
     torch.cuda.synchronize()
@@ -55,15 +55,15 @@ for cfg in args.configs.split(","):
     flagged = 0
     for it in range(args.reps):
         if it == args.reps - 1:
-            lib.b200rag_debug_scan_stats(1, None, 0)
+            lib.b200rag_debug_set_stats_buffer(0, stats.data_ptr(), stats.numel())
         lib.b200rag_profile_next_scan(evs[it][0].cuda_event, evs[it][1].cuda_event)
         tot[it][0].record()
         s_, i_, f_ = idx.search(qs[it % 8], args.k, mode)
         tot[it][1].record()
     torch.cuda.synchronize()
     flagged = int(f_.sum())
-    buf = np.zeros((256, 16), dtype=np.uint64)
-    lib.b200rag_debug_scan_stats(0, buf.ctypes.data_as(ctypes.c_void_p), 256)
+    lib.b200rag_debug_set_stats_buffer(0, None, 0)
+    buf = stats.cpu().numpy()
     used = buf[buf[:, 0] > 0].astype(np.float64)
     scan = [a.elapsed_time(b) for a, b in evs][5:]
     step = [a.elapsed_time(b) for a, b in tot][5:]
@@ -74,3 +74,5 @@ for cfg in args.configs.split(","):
     print(f"v{ver} epi={cs} span={span} mult={mult}: scan median {sm:6.2f} ms = {flops / sm / 1e9:5.0f} TFLOP/s (min {min(scan):.2f} max {max(scan):.2f}); "
           f"search {st:6.2f} ms = {args.batch / st * 1e3:7.0f} QPS; clock ~{mma_total / last_scan / 1e6:.3f} GHz, "
           f"MMA issue busy {100 * mma_busy:.0f}%, CTAs with MMA {len(used)}, flagged(last) {flagged}")
+for name in ("sample_mult", "epi", "scan_version", "qg_span"):
+    _lib.set_option(name, -1)
