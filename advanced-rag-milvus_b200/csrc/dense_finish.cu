@@ -5,14 +5,16 @@
 // PROVE completeness (see dense_tc.cu's header).  Round 1 ran one 256-thread CTA per query around a block-level streaming
 // top-k: 63 M warp instructions for 1024 queries, three quarters of them in the selection's barriers, histograms and
 // bitonic passes (profiles/r1: 0.18 ms, 37 % issue utilisation, 3 CTAs per SM).  This generation:
-//   * one 128-thread CTA per query, ~40 KB of shared memory -> 5 CTAs per SM, no block-level selection at all;
-//   * warp 0 streams the chunk lists -- 32 survivors at a time, across as many chunks as they span -- through a 512-entry buffer
-//     and keeps the k' greatest with the same register-resident radix select the scan epilogue uses (tc_common.cuh:
-//     warp_compact): typically two or three compactions per query; meanwhile warps 1..3 convert the query to fp64;
-//   * re-score from rows staged with warp-wide 16-byte cp.async copies (coalesced 512-byte requests), eight threads per row,
-//     one per canonical fp64 lane.  (A first version of this generation let one thread walk a whole row straight from global
-//     memory: 16-byte requests from 32 different rows per warp instruction -- 262 us, slower than round 1.)
-//   * all-pairs rank count in shared memory (k' <= 640 -> at most 3200 compares per thread), no sort.
+//   * one 128-thread CTA per query, ~24 KB of shared memory -> 8 CTAs per SM: 1024 queries finish in one wave;
+//   * all threads gather the query's survivors (~8 k', a handful per chunk) into a working set that aliases the row staging
+//     region; whenever it holds more than k' entries the whole block selects the k' best with a radix select over
+//     range-normalised keys (block_select below).  (The first version of this generation let warp 0 stream the survivors 32 at a
+//     time through a register-resident radix select: 59 us of selection per batch against 37 us now, and 1 ms at k' = 640.)
+//   * re-score from rows staged 16 at a time, in 384-element segments, with warp-wide 16-byte cp.async copies (coalesced
+//     requests), eight threads per row, one per canonical fp64 lane.  (One thread walking a whole row straight from global
+//     memory -- 16-byte requests from 32 different rows per warp instruction -- measured 262 us, slower than round 1.)
+//   * rank: all-pairs count in shared memory up to 256 candidates, bitonic sort of (score, row) pairs above.
+// Split mode (launch_finish3, finish_version 3) runs the same selection, then the re-score as its own grid and a rank kernel.
 // Which candidates survive a tie at the k'-th tensor-core score is immaterial: every dropped row has a tensor-core score
 // <= m either way, so the proof -- and with it the exact result -- does not depend on it.
 #include "finish.cuh"
