@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
     __shared__ int s_sel[4], s_wcnt;
     __shared__ int s_n, s_total;
     __shared__ float s_m;
+    __shared__ double s_tau;                             // bound on the tensor score of candidates dropped before the re-score
     __shared__ double s_q2[F2_THREADS / 32];
     __shared__ float s_err;
     __shared__ double s_ek_sh;
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
             s_m = fmaxf(compacted ? thr : -CUDART_INF_F, gk ? unmono32(gk) : -CUDART_INF_F);
             s_err = 0.f;
             s_ek_sh = -CUDART_INF;
+            s_tau = -CUDART_INF;
         }
     }
     if (!p.fin_sel) {
@@ -250,7 +252,42 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
         if (lane == 0) s_q2[warp] = q2;
     }
     __syncthreads();
-    const int n = s_n;
+    int n = s_n;
+    // ---- 1b. deep candidate sets (the tier-0 re-scan keeps k' = 640 for k = 100): only the candidates whose tensor-core score
+    //          is within 3 eps of the k-th best one can reach the exact top k -- a candidate below  tau = t_k - 3 eps  has an
+    //          exact score < tau + eps = t_k - 2 eps, while the k best by tensor-core score all have exact scores >= t_k - eps.
+    //          The others are dropped before the re-score (the FP64 pipe bounds it: one conversion and one DFMA per element) and
+    //          the proof treats them like rows outside the candidate set: bound tau instead of m.
+    if (!p.approx && !p.fin_sel && n >= 2 * p.k) {
+        const double q2b = s_q2[0] + s_q2[1] + s_q2[2] + s_q2[3];
+        const double epsb = 2.0 * (double)p.dim * 1.1920928955078125e-07 * sqrt(q2b) * p.row_norm_bound;
+        const float t_k = block_select(buf, n, p.k, reinterpret_cast<unsigned long long*>(exact), hist, s_sel);
+        const double tau = (double)t_k - 3.0 * epsb;
+        if (tid == 0) s_wcnt = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += F2_THREADS) {
+            const int i = i0 + tid;
+            unsigned long long e = 0ull;
+            bool keep = false;
+            if (i < n) {
+                e = buf[i];
+                keep = (double)__uint_as_float((uint32_t)(e >> 32)) >= tau;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            int base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&s_wcnt, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) work[base + __popc(bal & ((1u << lane) - 1u))] = e;
+        }
+        __syncthreads();
+        const int kept = s_wcnt;
+        if (kept < n) {
+            for (int i = tid; i < kept; i += F2_THREADS) buf[i] = work[i];
+            if (tid == 0) { s_n = kept; s_tau = tau; }
+            n = kept;
+        }
+        __syncthreads();
+    }
     if (p.fin_sel) {                                     // split finish: hand the selection over and leave
         for (int i = tid; i < n; i += F2_THREADS) p.fin_sel[(size_t)slot_q * p.kprime + i] = buf[i];
         if (tid == 0) {
@@ -371,9 +408,9 @@ __global__ void __launch_bounds__(F2_THREADS) dense_finish2_kernel(const FinishP
     if (tid == 0) {
         const double q2 = s_q2[0] + s_q2[1] + s_q2[2] + s_q2[3];
         const double eps = 2.0 * (double)p.dim * 1.1920928955078125e-07 * sqrt(q2) * p.row_norm_bound;
-        const float m = s_m;
+        const double m = fmax((double)s_m, s_tau);
         // proven complete iff nothing was dropped (m = -inf) or the k-th exact score clears m + eps
-        const bool proven = p.approx || (m == -CUDART_INF_F) || (n >= p.k && s_ek_sh > (double)m + eps);
+        const bool proven = p.approx || (m == -CUDART_INF) || (n >= p.k && s_ek_sh > m + eps);
         const int flag = proven ? 0 : 1;
         if (p.out_flags) p.out_flags[q] = flag | (p.q_list ? 2 : 0);      // bit 1: the query went through the tier-0 re-scan
         if (flag) p.flag_list[atomicAdd(p.n_flagged, 1)] = q;

@@ -624,12 +624,15 @@ static TensorPlan plan_tensor(int64_t n_rows, int dim, int n_q, int k) {
         pl.t0_chunks = want_t0 < tiles3 ? want_t0 : tiles3;
         if (pl.t0_chunks < 1) pl.t0_chunks = 1;
         pl.t0_items = spans * pl.t0_chunks;
-        // strided sample pass of the re-scan (same sizing rule as the first pass, for k' = 640)
-        pl.t0_s_stride = option(OPT_SAMPLE_MULT, 8) * pl.t0_kprime / TC_SAMPLE_R;
+        // strided sample pass of the re-scan.  About 4 k' rows above the threshold instead of the first pass's 8 k': at
+        // k' = 640 every survivor costs the epilogue's slow path and the finish kernel's gather (8 k': 1.64 ms for the re-scan
+        // of 1M rows, B = 1024), and a query that ends up with fewer than k' survivors here -- P(Gamma(16) < 4) ~ 4e-6 -- is
+        // still answered exactly, by the last tier.
+        pl.t0_s_stride = TC_T0_SAMPLE_MULT * pl.t0_kprime / TC_SAMPLE_R;
         if (pl.t0_s_stride > tiles3 / 4) pl.t0_s_stride = tiles3 / 4;
         if (pl.t0_s_stride < 1) pl.t0_s_stride = 1;
         pl.t0_s_tiles = tiles3 / pl.t0_s_stride;
-        pl.t0_sample = pl.t0_s_tiles >= 4 && TC_SAMPLE_R * pl.t0_s_stride >= 6 * pl.t0_kprime && option(OPT_NO_SAMPLE, 0) == 0;
+        pl.t0_sample = pl.t0_s_tiles >= 4 && TC_SAMPLE_R * pl.t0_s_stride >= 3 * pl.t0_kprime && option(OPT_NO_SAMPLE, 0) == 0;
         const int want_s = pl.t0_clusters / gcd_int(qg, pl.t0_clusters);
         pl.t0_s_chunks = want_s < pl.t0_s_tiles ? want_s : (pl.t0_s_tiles > 0 ? pl.t0_s_tiles : 1);
         pl.t0_s_items = qg * pl.t0_s_chunks;

@@ -465,6 +465,7 @@ __device__ __forceinline__ void epi_filter_finish(int& cnt, unsigned long long* 
 // (r distinct rows reach it), and equals it unless two of the top r rows share a group -- so the threshold derived
 // from it is never too high because of the grouping, at worst a little low (a few more survivors in the full scan).
 constexpr int TC_SAMPLE_R = 16;
+constexpr int TC_T0_SAMPLE_MULT = 4;   // tier-0 re-scan: rows above the sampled threshold, in k'
 
 __device__ __forceinline__ void epi_sample_tile(uint32_t taddr, int n_groups, int64_t row0, int64_t n_rows,
                                                 float (&top)[TC_SAMPLE_R], const uint32_t* row_mask) {
