@@ -478,6 +478,56 @@ def test_mmr_batches_beyond_one_wave_agree_with_the_bitset_kernels(eng):
     assert np.array_equal(out[3][1], out[2][1]) and np.array_equal(out[3][0], out[2][0])
 
 
+def test_fuse_select_matches_the_tensor_restatement(eng):
+    """b200rag_fuse_select (the tail of the fusion stage as one kernel) against the chain of tensor operations it replaced
+    (reference retrieval.py:322-333, 441-461, 485-491, 512-516): mixed MMR / plain queries, picks padded with -1, fewer fused
+    entries than top_k, an empty query."""
+    rng = np.random.default_rng(41)
+    nl, b, kmax, t_max = 3, 37, 24, 15
+    tot = nl * kmax
+    lsc = rng.random((nl, b, kmax))
+    n_f = rng.integers(0, tot + 1, size=b).astype(np.int32)
+    n_f[3] = 0
+    ids = np.full((b, tot), -1, np.int64)
+    sc = np.zeros((b, tot))
+    mask = np.zeros((b, tot), np.int32)
+    first = np.full((b, tot), -1, np.int32)
+    for q in range(b):
+        ids[q, : n_f[q]] = rng.permutation(10_000)[: n_f[q]]
+        sc[q, : n_f[q]] = np.sort(rng.random(n_f[q]))[::-1]
+        mask[q, : n_f[q]] = rng.integers(1, 8, size=n_f[q])
+        first[q, : n_f[q]] = rng.integers(0, tot, size=n_f[q])
+    top = rng.integers(1, t_max + 1, size=b).astype(np.int32)
+    use = (rng.random(b) < 0.5).astype(np.int32)
+    picks = np.full((b, t_max), -1, np.int32)
+    for q in range(b):
+        m = min(int(n_f[q]), int(top[q]))
+        if m:
+            picks[q, :m] = rng.permutation(int(n_f[q]))[:m]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    fused = eng.FusedBatch(t(ids), t(sc), t(mask), t(first), t(n_f))
+    rows, scores, msk, n_out, fm, orig = eng.fuse_select(fused, t(picks), t(use), t(top), t(lsc), t_max)
+    # the tensor-operation chain (what B200HybridRetriever._fuse_local did before the kernel existed)
+    pos = np.tile(np.arange(t_max), (b, 1))
+    pos = np.where(use[:, None] != 0, np.maximum(picks, 0), pos)
+    pos = np.minimum(pos, tot - 1)
+    n_ref = np.minimum(n_f, top)
+    valid = np.arange(t_max)[None, :] < n_ref[:, None]
+    take = lambda a: np.take_along_axis(a, pos, 1)
+    assert np.array_equal(n_out.cpu().numpy(), n_ref)
+    assert np.array_equal(rows.cpu().numpy(), np.where(valid, take(ids), -1))
+    assert np.array_equal(scores.cpu().numpy(), np.where(valid, take(sc), -np.inf))
+    assert np.array_equal(msk.cpu().numpy(), np.where(valid, take(mask), 0))
+    f = np.maximum(take(first), 0)
+    assert np.array_equal(fm.cpu().numpy(), f // kmax)
+    flat = lsc.transpose(1, 0, 2).reshape(b, -1)
+    assert np.array_equal(orig.cpu().numpy(), np.take_along_axis(flat, f.astype(np.int64), 1))
+    # no MMR anywhere: picks / use_mmr may be omitted
+    rows2, *_ = eng.fuse_select(fused, None, None, t(top), t(lsc), t_max)
+    pos0 = np.minimum(np.tile(np.arange(t_max), (b, 1)), tot - 1)
+    assert np.array_equal(rows2.cpu().numpy(), np.where(valid, np.take_along_axis(ids, pos0, 1), -1))
+
+
 def test_mmr_heavy_cap_and_long_documents(eng):
     """The heavy/light MMR kernel outside its comfort zone: a 3000-token vocabulary where the sample calls far more than 384
     tokens heavy (the cap moves the rest to the light lists), two documents of 1500 and 1100 tokens (several rounds of the per-pick
